@@ -1,0 +1,312 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference/src through oracle/ref_import.py (gym / orbit-sim / matplotlib stubs),
+drives the reference classes on small seeded inputs and stores inputs + outputs as
+``tests/golden/*.npz``.  The GPU box has no /root/reference, so tests only read the .npz files.
+
+Every benefit tensor is fp32-representable (generated as float32, handed to the reference as
+float64), so the float64 reference and an fp32-input device path see identical numbers.
+Tie-heavy cases run the reference under ``stable_argsort`` (numpy's default unstable sort has
+a CPU-dependent tie order); tie-free cases run it untouched.
+"""
+from __future__ import annotations
+
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import cpu_oracle as O  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+
+def _run_real(R, S, M, N, L, lam, T_ctor, actions, stable, task_prios=None):
+    """One RealConstellationEnv episode; returns per-step records."""
+    n, m, T = S.shape
+    ctx = ref_import.stable_argsort() if stable else _null()
+    with ctx:
+        env = R.real_env.RealConstellationEnv(1, n, m=m, T=T_ctor, N=N, M=M, L=L, lambda_=lam,
+                                              sat_prox_mat=S.astype(np.float64), graphs=1, task_prios=task_prios)
+        env.reset()
+        rec = {"obs": [], "beta": [], "prev": [], "rewards": [], "done": []}
+
+        def snap():
+            pre = env.get_pretransition_data()
+            rec["obs"].append(np.array(pre["obs"][0], dtype=np.float64))
+            rec["beta"].append(np.array(pre["beta"][0], dtype=np.float64))
+            rec["prev"].append(np.array(pre["prev_assigns"][0], dtype=np.int64))
+            assert np.all(np.array(pre["avail_actions"][0]) == 1)
+
+        snap()
+        for t in range(actions.shape[0]):
+            r, d, info = env.step(list(actions[t]))
+            assert info == {}
+            rec["rewards"].append(np.array(r, dtype=np.float64))
+            rec["done"].append(bool(d))
+            snap()
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out.update(n=env.n, m=env.m, T=env.T, L=env.L, obs_size=env.get_obs_size())
+    return out
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def golden_kat1(R):
+    """KAT-1: the author's fixture, experiments.py:265-288."""
+    S = np.zeros((4, 4, 2), dtype=np.float32)
+    S[:, :, 0] = [[5, 0, 0, 1], [2, 0, 0, 0], [3, 1, 4, 2], [1, 3, 0, 10]]
+    S[:, :, 1] = 1
+    actions = np.array([[0, 0, 2, 3], [1, 1, 1, 3]], dtype=np.int64)
+    out = _run_real(R, S, M=2, N=2, L=2, lam=0.5, T_ctor=1, actions=actions, stable=True)
+    np.savez_compressed(os.path.join(HERE, "kat1_real.npz"), S=S, actions=actions, M=2, N=2, L_arg=2, T_ctor=1,
+             lambda_=0.5, **out)
+
+
+def golden_real_random(R):
+    cases = [
+        # name, gen, n, m, T, L, M, N, stable, seed, prios
+        ("real_exact_tiefree", "exact", 7, 11, 6, 3, 4, 3, False, 1, False),
+        ("real_dense", "dense", 12, 16, 5, 3, 6, 4, False, 2, False),
+        ("real_ties", "ties", 9, 14, 6, 3, 4, 3, True, 3, False),
+        ("real_reflike", "ref", 10, 24, 8, 3, 6, 3, True, 4, False),
+        ("real_prios_L2", "dense", 8, 13, 5, 2, 4, 2, False, 5, True),
+        ("real_L1", "exact", 6, 9, 4, 1, 2, 2, True, 6, False),
+        ("real_mid", "dense", 24, 40, 4, 3, 10, 10, False, 7, False),
+    ]
+    for name, gen, n, m, T, L, M, N, stable, seed, prios in cases:
+        rng = np.random.default_rng(seed)
+        if gen == "exact":
+            # tie-free by rejection: distinct row sums are almost surely distinct on the grid plus offsets
+            S = O.gen_exact(rng, 1, n, m, T)[0]
+            off = (rng.permutation(n * m).reshape(n, m, 1).astype(np.float32) + 1) * np.float32(2.0 ** -20)
+            S = (S + off).astype(np.float32)
+        elif gen == "dense":
+            S = O.gen_dense(rng, 1, n, m, T)[0]
+        elif gen == "ties":
+            S = O.gen_exact(rng, 1, n, m, T, zero_frac=0.6)[0]
+            S = (np.round(S * 8) / 8).astype(np.float32)  # coarse grid -> many duplicates
+        else:
+            S = O.gen_ref_like(rng, 1, n, m, T)[0]
+        tp = (rng.integers(1, 5, size=m).astype(np.float64) * 0.25) if prios else None
+        actions = rng.integers(0, m, size=(T, n), dtype=np.int64)
+        # make conflicts and "stay on the same task" cases frequent
+        actions[:, : n // 2] = actions[:, :1]
+        actions[1::2, n // 2:] = actions[0::2, n // 2:][: actions[1::2].shape[0]]
+        out = _run_real(R, S, M=M, N=N, L=L, lam=0.5, T_ctor=T, actions=actions, stable=stable, task_prios=tp)
+        extra = {} if tp is None else {"task_prios": tp}
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), S=S, actions=actions, M=M, N=N, L_arg=L, T_ctor=T,
+                 lambda_=0.5, stable=stable, **extra, **out)
+
+
+def golden_mock(R):
+    for name, n, m, T, L, seed, gen in [("mock_small", 5, 7, 6, 3, 11, "dense"),
+                                        ("mock_ref", 10, 10, 12, 3, 12, "ref"),
+                                        ("mock_L4", 6, 9, 5, 4, 13, "exact")]:
+        rng = np.random.default_rng(seed)
+        S = {"dense": O.gen_dense, "ref": O.gen_ref_like, "exact": O.gen_exact}[gen](rng, 1, n, m, T)[0]
+        actions = rng.integers(0, m, size=(T, n), dtype=np.int64)
+        actions[:, : n // 2] = actions[:, :1]
+        np.random.seed(seed)
+        env = R.mock_env.MockConstellationEnv(n, m, T, L, 0.5, sat_prox_mat=S.astype(np.float64))
+        env.reset()
+        prev0 = np.array(env.prev_assigns, dtype=np.int64)
+        rec = {"obs": [], "beta": [], "rewards": [], "done": []}
+
+        def snap():
+            pre = env.get_pretransition_data()
+            assert set(pre) == {"obs", "avail_actions", "beta"}
+            rec["obs"].append(np.array(pre["obs"][0], dtype=np.float64))
+            rec["beta"].append(np.array(pre["beta"][0], dtype=np.float64))
+
+        snap()
+        for t in range(T):
+            r, d, info = env.step(list(actions[t]))
+            rec["rewards"].append(np.array(r, dtype=np.float64))
+            rec["done"].append(bool(d))
+            snap()
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), S=S, actions=actions, prev0=prev0, L=L, lambda_=0.5,
+                 **{k: np.stack(v) for k, v in rec.items()})
+
+
+def golden_selectors(R):
+    import torch as th
+
+    rng = np.random.default_rng(21)
+    B, n, A = 3, 5, 9
+    args = SimpleNamespace(epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=1000,
+                           evaluation_epsilon=0.0, use_mps_action_selection=True, device="cpu",
+                           env_args={"M": 4})
+    out = {}
+    # --- epsilon schedule ---
+    sched = R.schedules.DecayThenFlatSchedule(1.0, 0.05, 1000, decay="linear")
+    ts = np.array([0, 1, 250, 999, 1000, 5000], dtype=np.int64)
+    out["sched_t"] = ts
+    out["sched_eps"] = np.array([sched.eval(int(t)) for t in ts])
+
+    # --- classic epsilon greedy with injected draws ---
+    q = rng.standard_normal((B, n, A)).astype(np.float32)
+    q[0, 0, 3] = q[0, 0, 5] = q[0, 0].max() + 1  # argmax tie -> first index
+    avail = rng.random((B, n, A)) > 0.3
+    avail[..., 0] |= ~avail.any(-1)
+    avail[0, 0, 3] = avail[0, 0, 5] = True
+    q[1, 1, 2] = 100.0
+    avail[1, 1, 2] = False  # best action masked out
+    u_explore = rng.random((B, n), dtype=np.float32)
+    u_action = rng.random((B, n), dtype=np.float32)
+    sel = R.classic_selectors.EpsilonGreedyActionSelector(args)
+    picks = []
+    t_envs = [0, 500, 1000]
+    u_explore[2, 4] = np.float32(sched.eval(500))  # u == eps exactly -> not random (strict <)
+    for t_env in t_envs + ["test"]:
+        with _inject(th, R, [u_explore], u_action):
+            if t_env == "test":
+                a = sel.select_action(th.tensor(q), th.tensor(avail), 0, test_mode=True)
+            else:
+                a = sel.select_action(th.tensor(q), th.tensor(avail), t_env, test_mode=False)
+        picks.append(a.numpy())
+    out.update(eg_q=q, eg_avail=avail, eg_u_explore=u_explore, eg_u_action=u_action,
+               eg_t_env=np.array(t_envs), eg_actions=np.stack(picks))
+
+    # --- filtered epsilon greedy ---
+    M, m, L = 4, 9, 3
+    qf = rng.standard_normal((B, n, M + 1)).astype(np.float32)
+    qf[0, 1, :M] = -5.0  # baseline wins -> decided by tie noise (or first index)
+    qf[0, 2, M] = 0.5  # |base| >= 0.25 -> noise below half ulp -> first non-top index
+    qf[0, 2, :M] = 0.0
+    beta = O.gen_exact(rng, B, n, m, L)[..., :L]
+    beta = (beta + (rng.permutation(B * n * m).reshape(B, n, m, 1) + 1).astype(np.float32) * np.float32(2.0 ** -20))
+    beta = beta.astype(np.float32)
+    u_tie = rng.random((B, n, m), dtype=np.float32)
+    u_explore2 = rng.random((B, n), dtype=np.float32)
+    u_action2 = rng.random((B, n), dtype=np.float32)
+    fsel = R.filtered_selectors.FilteredEpsilonGreedyActionSelector(args)
+    fpicks = []
+    for t_env in t_envs + ["test"]:
+        with _inject(th, R, [u_tie, u_explore2], u_action2):
+            if t_env == "test":
+                a = fsel.select_action(th.tensor(qf), th.tensor(avail), 0, test_mode=True, beta=th.tensor(beta))
+            else:
+                a = fsel.select_action(th.tensor(qf), th.tensor(avail), t_env, test_mode=False, beta=th.tensor(beta))
+        fpicks.append(a.numpy())
+    out.update(fg_q=qf, fg_beta=beta, fg_u_tie=u_tie, fg_u_explore=u_explore2, fg_u_action=u_action2,
+               fg_actions=np.stack(fpicks), fg_M=M)
+    out.update(eps_start=1.0, eps_finish=0.05, eps_anneal=1000, eval_eps=0.0)
+    np.savez_compressed(os.path.join(HERE, "selectors.npz"), **out)
+
+
+class _inject:
+    """Feed injected uniforms to th.rand_like (in call order) and replace Categorical.sample by the
+    rank-select contract of oracle.random_available_action."""
+
+    def __init__(self, th, R, rand_like_values, u_action):
+        self.th, self.vals, self.u_action = th, list(rand_like_values), u_action
+
+    def __enter__(self):
+        from torch.distributions import Categorical
+
+        th = self.th
+        self._rl, self._cs, self.Cat = th.rand_like, Categorical.sample, Categorical
+        vals, u_action = self.vals, self.u_action
+
+        def rand_like(x, *a, **k):
+            v = vals.pop(0)
+            assert tuple(v.shape) == tuple(x.shape), (v.shape, x.shape)
+            return th.tensor(v, dtype=x.dtype)
+
+        def sample(dist, sample_shape=th.Size()):
+            avail = dist.probs.numpy() > 0
+            return th.tensor(O.random_available_action(avail, u_action))
+
+        th.rand_like = rand_like
+        Categorical.sample = sample
+        return self
+
+    def __exit__(self, *a):
+        self.th.rand_like = self._rl
+        self.Cat.sample = self._cs
+        return False
+
+
+def golden_buffer(R):
+    """EpisodeBatch.update casting + OneHot + ReplayBuffer ring insert (episode_buffer.py)."""
+    import torch as th
+
+    rng = np.random.default_rng(31)
+    n, m, L, T = 3, 5, 2, 4
+    env_scheme = {
+        "obs": {"vshape": 6, "group": "agents", "dtype": th.float16},
+        "actions": {"vshape": (1,), "group": "agents", "dtype": th.int16},
+        "avail_actions": {"vshape": (m,), "group": "agents", "dtype": th.bool},
+        "rewards": {"vshape": (n,), "dtype": th.float16},
+        "terminated": {"vshape": (1,), "dtype": th.bool},
+        "prev_assigns": {"vshape": (n,), "dtype": th.int16, "part_of_state": True},
+        "beta": {"vshape": (n, m, L), "dtype": th.float16, "part_of_state": True},
+    }
+    groups = {"agents": n}
+    pre = {"actions": ("actions_onehot", [R.transforms.OneHot(out_dim=m)])}
+    EB, RB = R.episode_buffer.EpisodeBatch, R.episode_buffer.ReplayBuffer
+    rb = RB(dict(env_scheme), groups, 5, T + 1, preprocess=pre, device="cpu")
+    eps = []
+    raw = []
+    for e in range(4):
+        B = 2
+        batch = EB(dict(env_scheme), groups, B, T + 1, preprocess=pre, device="cpu")
+        rec = {"obs": rng.standard_normal((B, T + 1, n, 6)) * 3,
+               "rewards": rng.standard_normal((B, T, n)) * 2,
+               "actions": rng.integers(0, m, size=(B, T, n)),
+               "beta": rng.random((B, T + 1, n, m, L))}
+        for t in range(T + 1):
+            batch.update({"obs": [rec["obs"][b, t] for b in range(B)],
+                          "beta": [rec["beta"][b, t] for b in range(B)],
+                          "avail_actions": [[[1] * m] * n for b in range(B)],
+                          "prev_assigns": [np.arange(n) for b in range(B)]}, ts=t)
+            if t < T:
+                batch.update({"actions": th.tensor(rec["actions"][:, t]),
+                              "rewards": [(list(rec["rewards"][b, t]),) for b in range(B)],
+                              "terminated": [(t == T - 1,) for b in range(B)]}, ts=t)
+        rb.insert_episode_batch(batch)
+        raw.append(rec)
+        eps.append({k: v.numpy().copy() if v.dtype != th.bool else v.numpy().copy()
+                    for k, v in batch.data.transition_data.items()})
+    out = {}
+    for e, (rec, ep) in enumerate(zip(raw, eps)):
+        for k, v in rec.items():
+            out[f"raw{e}_{k}"] = v
+        for k, v in ep.items():
+            out[f"ep{e}_{k}"] = v
+    for k, v in rb.data.transition_data.items():
+        out[f"rb_{k}"] = v.numpy().copy()
+    out["rb_buffer_index"] = rb.buffer_index
+    out["rb_episodes_in_buffer"] = rb.episodes_in_buffer
+    out["max_t_filled"] = int(rb.max_t_filled())
+    np.savez_compressed(os.path.join(HERE, "buffer.npz"), n=n, m=m, L=L, T=T, **out)
+
+
+def main():
+    assert ref_import.reference_available(), "needs /root/reference"
+    R = ref_import.ref_modules()
+    golden_kat1(R)
+    golden_real_random(R)
+    golden_mock(R)
+    golden_selectors(R)
+    golden_buffer(R)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""The CPU oracle replayed against vectors recorded from the unmodified reference
+(tests/golden/make_golden.py).  This is what pins the oracle (prompt section 3)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REAL = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "real_*.npz"))) + ["kat1_real.npz"]
+MOCK = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "mock_*.npz")))
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
+
+
+def test_kat1_known_answers():
+    """KAT-1 values as listed in SURVEY.md section 8c (author's fixture, experiments.py:265-288)."""
+    g = _load("kat1_real.npz")
+    assert (int(g["n"]), int(g["m"]), int(g["T"]), int(g["L"])) == (4, 4, 2, 1)
+    np.testing.assert_array_equal(g["obs"][0][0], [5, 1, 1, 10, 3, 2, 3, 4, 1, 0])
+    np.testing.assert_array_equal(g["obs"][0][3], [10, 3, 2, 1, 1, 0, 4, 5, 1, 0])
+    np.testing.assert_allclose(g["rewards"][0], [2.5, 0.75, 4.0, 10.0])
+    np.testing.assert_allclose(g["rewards"][1], [1 / 6, 1 / 6, 1 / 6, 1.0])
+    assert list(g["done"]) == [False, True]
+    assert not g["obs"][2].any() and not g["beta"][2].any()
+
+
+@pytest.mark.parametrize("name", REAL)
+def test_real_env_oracle_matches_reference(name):
+    g = _load(name)
+    S = g["S"].astype(np.float64)[None]
+    st = O.RealState(S, int(g["L_arg"]), int(g["M"]), int(g["N"]), float(g["lambda_"]),
+                     task_prios=g.get("task_prios"), T_ctor=int(g["T_ctor"]))
+    assert (st.n, st.m, st.T, st.L, st.obs_size) == tuple(int(g[k]) for k in ("n", "m", "T", "L", "obs_size"))
+    st.reset()
+    for t in range(g["actions"].shape[0] + 1):
+        pre = st.pretransition()
+        np.testing.assert_array_equal(pre["obs"][0], g["obs"][t])          # bit-exact: values are gathers
+        np.testing.assert_array_equal(pre["beta"][0], g["beta"][t])
+        np.testing.assert_array_equal(pre["prev_assigns"][0], g["prev"][t])
+        if t < g["actions"].shape[0]:
+            r, d = st.step(g["actions"][t][None])
+            np.testing.assert_array_equal(r[0], g["rewards"][t])           # same float64 ops -> identical
+            assert d == bool(g["done"][t])
+
+
+@pytest.mark.parametrize("name", MOCK)
+def test_mock_env_oracle_matches_reference(name):
+    g = _load(name)
+    st = O.MockState(g["S"].astype(np.float64)[None], int(g["L"]), float(g["lambda_"]))
+    st.reset(g["prev0"][None])
+    T = g["actions"].shape[0]
+    for t in range(T + 1):
+        pre = st.pretransition()
+        np.testing.assert_array_equal(pre["obs"][0], g["obs"][t])
+        np.testing.assert_array_equal(pre["beta"][0], g["beta"][t])
+        if t < T:
+            r, d = st.step(g["actions"][t][None])
+            np.testing.assert_array_equal(r[0], g["rewards"][t])
+            assert d == bool(g["done"][t])
+
+
+def test_selectors_oracle_matches_reference():
+    g = _load("selectors.npz")
+    for t, e in zip(g["sched_t"], g["sched_eps"]):
+        assert O.epsilon_linear(float(g["eps_start"]), float(g["eps_finish"]), float(g["eps_anneal"]), int(t)) == e
+    eps_list = [O.epsilon_linear(1.0, 0.05, 1000, int(t)) for t in g["eg_t_env"]] + [float(g["eval_eps"])]
+    for eps, want in zip(eps_list, g["eg_actions"]):
+        got = O.select_epsilon_greedy(g["eg_q"], g["eg_avail"], eps, g["eg_u_explore"], g["eg_u_action"])
+        np.testing.assert_array_equal(got, want)
+    top = O.top_m_tasks(g["fg_beta"], int(g["fg_M"]))
+    m = g["fg_beta"].shape[2]
+    for eps, want in zip(eps_list, g["fg_actions"]):
+        got = O.select_filtered_epsilon_greedy(g["fg_q"], top, g["eg_avail"], m, eps, g["fg_u_tie"],
+                                               g["fg_u_explore"], g["fg_u_action"])
+        np.testing.assert_array_equal(got, want)
+
+
+def test_real_beta_hat_full_consistent():
+    """beta_hat at the chosen entry equals the full tensor's entry (real_constellation_env.py:282-328)."""
+    rng = np.random.default_rng(0)
+    S = O.gen_ref_like(rng, 3, 6, 8, 5).astype(np.float64)
+    beta = O.real_window(S, 1, 3)
+    prev = rng.integers(0, 8, size=(3, 6))
+    a = rng.integers(0, 8, size=(3, 6))
+    full = O.real_beta_hat_full(beta, prev, 0.5)
+    chosen = O.real_beta_hat_chosen(beta, prev, a, 0.5)
+    np.testing.assert_array_equal(np.take_along_axis(full[..., 0], a[..., None], 2)[..., 0], chosen)
+
+
+def test_rollout_timeline_real():
+    """A.5 timeline: filled = 1 for t in [0,T], terminated only at T-1, final obs zeros."""
+    rng = np.random.default_rng(5)
+    S = O.gen_dense(rng, 2, 6, 8, 4).astype(np.float64)
+    st = O.RealState(S, 3, 4, 2, 0.5)
+    acts = rng.integers(0, 8, size=(4, 2, 6))
+    out = O.rollout(st, lambda t, pre: acts[t], "real")
+    assert out["filled"].sum() == 2 * 5
+    assert out["terminated"][:, :3].sum() == 0 and out["terminated"][:, 3].all() and not out["terminated"][:, 4].any()
+    assert not out["obs"][:, 4].any() and not out["beta"][:, 4].any()
+    np.testing.assert_array_equal(out["prev_assigns"][:, 4], acts[3])
