@@ -1,0 +1,169 @@
+/*
+ * marl_sap_b200 -- C ABI of the B200-native rollout hot path of josh-holder/marl_sap.
+ *
+ * The reference is 100 % Python and has no FFI; its boundary for this path is three Python
+ * registries plus EpisodeBatch.  Each entry point below names the
+ * reference function (file:line under /root/reference/src) it replaces.  The Python host
+ * (marl_sap_b200/) mirrors the reference classes and calls these through ctypes; any other
+ * host (C, C++, cffi ...) can bind the same symbols -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all memory; nothing is allocated, freed or retained by the library;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit sync;
+ *     no host-side read of device data, so every call is CUDA-graph capturable
+ *     (except *_host uploads, which issue a cudaMemcpyAsync from the given host buffer);
+ *   - return value: 0 = ok, < 0 = argument error (SAP_E_*), > 0 = cudaError_t of the launch;
+ *     sap_last_error() returns a thread-local message for the last non-zero return;
+ *   - never throws, never exits, re-entrant.
+ *
+ * Benefit tensor layouts
+ *   reference layout  sat_prox_mat[n, m, T]  (T innermost), batched as [B, n, m, T];
+ *   device layout     planes[B, T, n, m]     (one contiguous n x m plane per time step) so the
+ *                     look-ahead window beta_k = planes[k .. k+L) is L contiguous planes.
+ */
+#ifndef MARL_SAP_B200_H
+#define MARL_SAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAP_ABI_VERSION 1
+
+/* element types of episode-buffer fields (the reference schemes use exactly these:
+ * real_constellation_env.py:95-107 fp16/int16/bool, mock_constellation_env.py:73-85 fp32/int64/bool) */
+enum SapDtype { SAP_F32 = 0, SAP_F16 = 1, SAP_I64 = 2, SAP_I16 = 3, SAP_I32 = 4, SAP_U8 = 5 };
+
+enum SapError {
+  SAP_OK = 0,
+  SAP_E_NULL = -1,      /* required pointer is null */
+  SAP_E_DIMS = -2,      /* non-positive or inconsistent dimension */
+  SAP_E_CONSTRAINT = -3,/* reference precondition violated: m >= n, n > N, m >= M + M/2, M even */
+  SAP_E_DTYPE = -4,     /* dtype not supported for that field */
+  SAP_E_SMEM = -5,      /* required scratch buffer missing for this problem size */
+  SAP_E_ALIGN = -6      /* pointer not aligned for vector access */
+};
+
+typedef struct SapEnvDims {
+  int32_t B; /* independent environments in this launch            */
+  int32_t n; /* agents                                               */
+  int32_t m; /* tasks (= actions per agent)                          */
+  int32_t T; /* episode length = number of benefit planes            */
+  int32_t L; /* look-ahead window (already clamped: min(L, T_ctor))  */
+  int32_t M; /* top tasks per agent in the observation   (real env)  */
+  int32_t N; /* rival agents per agent in the observation (real env) */
+  int32_t shared_planes; /* 1 = all B envs read env 0's planes (one sat_prox_mat for every worker,
+                            like ParallelRunner's identical env_args), 0 = planes[B,T,n,m] */
+} SapEnvDims;
+
+/* One field of an EpisodeBatch ([B, T+1, ...] tensor, episode_buffer.py:30-77).
+ * Element (b, t, x) lives at ptr + (b*env_stride + t*t_stride + x) * sizeof(dtype). */
+typedef struct SapField {
+  void* ptr;          /* null = field absent / not materialised */
+  int64_t env_stride; /* in elements */
+  int64_t t_stride;   /* in elements */
+  int32_t dtype;      /* SapDtype */
+  int32_t reserved;
+} SapField;
+
+/* The episode-batch slots one env step writes (A.5 timeline of SURVEY.md):
+ * at time t = k_old: actions, actions_onehot, rewards, terminated;
+ * at time t+1:       obs, prev_assigns, beta, avail_actions, filled. */
+typedef struct SapBatchView {
+  SapField obs;            /* [n, obs_size]   f32|f16   required            */
+  SapField rewards;        /* [n]             f32|f16   nullable            */
+  SapField actions;        /* [n, 1]          i64|i16   nullable            */
+  SapField actions_onehot; /* [n, m]          i64|i16|f32 nullable (OneHot) */
+  SapField terminated;     /* [1]             u8        nullable            */
+  SapField filled;         /* [1]             i64       nullable            */
+  SapField prev_assigns;   /* [n]             i64|i16   nullable (real env) */
+  SapField beta;           /* real [n,m,L] / mock [n,m]  f32|f16 nullable   */
+  SapField avail_actions;  /* [n, m]          u8        nullable (all ones) */
+} SapBatchView;
+
+int sap_abi_version(void);
+const char* sap_last_error(void);
+
+/* ---- benefit tensors ------------------------------------------------------------------
+ * Replaces the per-step slicing sat_prox_mat[:, :, k:k+L] (real_constellation_env.py:127,
+ * 167-170; mock_constellation_env.py:104,110,150,157) by a one-off re-layout
+ * [B,n,m,T] -> [B,T,n,m]. */
+int sap_benefit_ingest(const float* src_nmT, float* dst_Tnm, int32_t B, int32_t n, int32_t m, int32_t T,
+                       void* stream);
+/* Same, from a HOST buffer: cudaMemcpyAsync into staging_dev ([B,n,m,T]) then re-layout. */
+int sap_benefit_upload_host(const float* src_nmT_host, float* staging_dev, float* dst_Tnm, int32_t B, int32_t n,
+                            int32_t m, int32_t T, void* stream);
+
+/* ---- RealConstellationEnv ---------------------------------------------------------------
+ * sap_real_reset  = RealConstellationEnv.reset + get_pretransition_data
+ *                   (real_constellation_env.py:116-133, 232-244): k=0, prev=arange(n),
+ *                   obs_0 via _build_obs (:177-230) written to slot t=0, filled[0]=1.
+ * sap_real_step   = RealConstellationEnv.step (:135-175) incl. beta_hat (:282-328) at the
+ *                   chosen entries, conflict counts, reward split, k+=1, done, next window,
+ *                   _build_obs, + the EpisodeRunner buffer writes of episode_runner.py:86-100.
+ * state:  k[B] int32 in/out, prev[B,n] int32 in/out, ep_return[B] f64 accumulators.
+ * top_out [B,n,M] int32 (nullable): agent i's top-M task indices of the NEW observation
+ *         (shared with the filtered selector so top-M is computed once).
+ * scratch: B*n*m doubles, required only when n*m*8 bytes do not fit shared memory. */
+int sap_real_reset(const SapEnvDims* dims, const float* planes, const float* task_prios, int32_t* k, int32_t* prev,
+                   double* ep_return, const SapBatchView* view, int32_t* top_out, double* scratch, void* stream);
+int sap_real_step(const SapEnvDims* dims, const float* planes, const float* task_prios, const float* T_trans,
+                  double lambda_, const int64_t* actions, int32_t* k, int32_t* prev, double* ep_return,
+                  int32_t* counts_out, const SapBatchView* view, int32_t* top_out, double* scratch, void* stream);
+/* bytes of dynamic shared memory / scratch doubles the real-env kernels need for these dims */
+int64_t sap_real_scratch_doubles(const SapEnvDims* dims);
+
+/* ---- MockConstellationEnv ---------------------------------------------------------------
+ * sap_mock_reset = MockConstellationEnv.reset (mock_constellation_env.py:94-114); prev0[B,n]
+ *                  replaces the np.random.choice draw at :105 (injected).
+ * sap_mock_step  = MockConstellationEnv.step (:116-162) + beta_hat (:228-274) + buffer writes. */
+int sap_mock_reset(const SapEnvDims* dims, const float* planes, const int64_t* prev0, int32_t* k, int32_t* prev,
+                   double* ep_return, const SapBatchView* view, void* stream);
+int sap_mock_step(const SapEnvDims* dims, const float* planes, const float* T_trans, double lambda_,
+                  const int64_t* actions, int32_t* k, int32_t* prev, double* ep_return, int32_t* counts_out,
+                  const SapBatchView* view, void* stream);
+
+/* ---- action selectors ---------------------------------------------------------------------
+ * sap_select_epsilon_greedy = EpsilonGreedyActionSelector.select_action
+ *   (action_selectors/classic_selectors.py:37-54): mask -> -inf, Bernoulli(eps) explore,
+ *   uniform-over-available random action, else first-index argmax.
+ * sap_select_filtered_epsilon_greedy = FilteredEpsilonGreedyActionSelector.select_action
+ *   (action_selectors/filtered_classic_selectors.py:17-63); `top` replaces its th.topk(beta.sum(-1)).
+ * Random draws: injected uniforms (u_* non-null, fp32 in [0,1)) or Philox4x32-10 keyed by
+ *   (seed; b*n+i, *episode_ctr, k[b], draw id).  avail null = everything available. */
+int sap_select_epsilon_greedy(const float* q, const uint8_t* avail, int32_t B, int32_t n, int32_t A, float eps,
+                              uint64_t seed, const uint64_t* episode_ctr, const int32_t* k, const float* u_explore,
+                              const float* u_action, int64_t* actions_out, void* stream);
+int sap_select_filtered_epsilon_greedy(const float* q, const int32_t* top, const uint8_t* avail, int32_t B, int32_t n,
+                                       int32_t m, int32_t M, float eps, uint64_t seed, const uint64_t* episode_ctr,
+                                       const int32_t* k, const float* u_tie, const float* u_explore,
+                                       const float* u_action, int64_t* actions_out, void* stream);
+/* top-M task indices from a beta tensor [B,n,m,L] (dtype f32|f16), stable (value desc, index asc);
+ * replaces th.topk(beta.sum(-1), M).indices (filtered_classic_selectors.py:50). */
+int sap_topm_from_beta(const void* beta, int32_t dtype, int32_t B, int32_t n, int32_t m, int32_t L, int32_t M,
+                       int32_t* top_out, void* stream);
+
+/* ---- episode buffer -------------------------------------------------------------------------
+ * sap_buffer_insert  = ReplayBuffer.insert_episode_batch (components/episode_buffer.py:244-259):
+ *   copies `count` episode rows of `row_bytes` each from src (starting at src_row0) into the ring
+ *   dst of `ring_rows` rows starting at dst_row0, wrapping around.
+ * sap_buffer_gather  = ReplayBuffer.sample's fancy-index copy (:264-271): dst[r] = src[ids[r]].
+ * sap_onehot         = OneHot.transform (components/transforms.py:16-19) for materialising
+ *   actions_onehot from actions after the fact.
+ * sap_real_beta_window = the `beta` buffer field ([rows, n, m, L]) rebuilt from the planes:
+ *   row r = (env b = r / (T+1), time t = r % (T+1)), zero for t >= T (real_constellation_env.py:167-170, 226-228). */
+int sap_buffer_insert(void* dst, const void* src, int64_t row_bytes, int64_t ring_rows, int64_t dst_row0,
+                      int64_t src_row0, int64_t count, void* stream);
+int sap_buffer_gather(void* dst, const void* src, const int64_t* ids, int64_t row_bytes, int64_t count, void* stream);
+int sap_onehot(const void* actions, int32_t actions_dtype, void* onehot, int32_t onehot_dtype, int64_t rows, int32_t m,
+               void* stream);
+int sap_real_beta_window(const SapEnvDims* dims, const float* planes, const float* task_prios, void* beta,
+                         int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARL_SAP_B200_H */

@@ -1,0 +1,27 @@
+"""Selector registry with the reference's ten keys (/root/reference/src/action_selectors/__init__.py:9-18).
+
+The two keys on the rollout hot path are implemented as CUDA kernels; the rest raise a clear error
+(SURVEY.md section 8f lists them as "next" rows: SAP/REDA selectors need a batched GPU assignment solver).
+"""
+from .selectors import EpsilonGreedyActionSelector, FilteredEpsilonGreedyActionSelector
+
+
+def _next_row(name, why):
+    class _Unavailable:
+        def __init__(self, args):
+            raise NotImplementedError(f"action selector '{name}' is not built yet: {why} (DESIGN.md, 'out of scope')")
+    _Unavailable.__name__ = f"Unavailable_{name}"
+    return _Unavailable
+
+
+REGISTRY = {}
+REGISTRY["epsilon_greedy"] = EpsilonGreedyActionSelector
+REGISTRY["filtered_const_epsilon_greedy"] = FilteredEpsilonGreedyActionSelector
+REGISTRY["multinomial"] = _next_row("multinomial", "policy-sampling selector, next after the epsilon-greedy pair")
+REGISTRY["soft_policies"] = _next_row("soft_policies", "policy-sampling selector, next after the epsilon-greedy pair")
+REGISTRY["filtered_const_soft_policies"] = _next_row("filtered_const_soft_policies", "policy-sampling selector")
+REGISTRY["continuous"] = _next_row("continuous", "bids-as-actions path (scipy linear_sum_assignment in the env)")
+REGISTRY["sap"] = _next_row("sap", "needs a batched GPU linear-sum-assignment (next row 1)")
+REGISTRY["epsilon_greedy_sap_test"] = _next_row("epsilon_greedy_sap_test", "needs a batched GPU linear-sum-assignment")
+REGISTRY["filtered_const_sap"] = _next_row("filtered_const_sap", "needs a batched GPU linear-sum-assignment")
+REGISTRY["filtered_const_epsgr_sap_test"] = _next_row("filtered_const_epsgr_sap_test", "needs a batched GPU linear-sum-assignment")

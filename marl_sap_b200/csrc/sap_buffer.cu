@@ -1,0 +1,216 @@
+// Episode-buffer data movement and benefit-tensor re-layout.
+//
+// Replaces /root/reference/src/components/episode_buffer.py:244-271 (ReplayBuffer ring insert and the
+// fancy-index copy of sample), components/transforms.py:16-19 (OneHot) and the per-step window slicing of
+// the envs (real_constellation_env.py:127,167-170).  All kernels are pure HBM streaming.
+#include <stdarg.h>
+
+#include "sap_common.cuh"
+
+// ----------------------------------------------------------------------------- last error (thread-local)
+static thread_local char g_sap_error[512] = "";
+void sap_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_sap_error, sizeof(g_sap_error), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* sap_last_error(void) { return g_sap_error; }
+extern "C" int sap_abi_version(void) { return SAP_ABI_VERSION; }
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// [B,n,m,T] -> [B,T,n,m]: per env a (n*m) x T matrix transpose through a padded shared tile.
+__global__ void __launch_bounds__(kThreads) sap_ingest_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                              int nm, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* s = src + (size_t)b * nm * T;
+  float* d = dst + (size_t)b * nm * T;
+  const int x0 = blockIdx.x * 32;  // along T (src inner)
+  const int y0 = blockIdx.y * 32;  // along nm
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int y = y0 + r, x = x0 + tx;
+    if (y < nm && x < T) tile[r][tx] = s[(size_t)y * T + x];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int x = x0 + r, y = y0 + tx;  // dst[x][y]
+    if (x < T && y < nm) d[(size_t)x * nm + y] = tile[tx][r];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sap_rows_copy16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+                                                                   int64_t row16, int64_t ring_rows, int64_t dst_row0,
+                                                                   int64_t src_row0, int64_t total16) {
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total16; e += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = e / row16, c = e - r * row16;
+    const int64_t dr = (dst_row0 + r) % ring_rows;
+    dst[dr * row16 + c] = src[(src_row0 + r) * row16 + c];
+  }
+}
+__global__ void __launch_bounds__(kThreads) sap_rows_copy1_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                                                  int64_t row_bytes, int64_t ring_rows, int64_t dst_row0,
+                                                                  int64_t src_row0, int64_t total) {
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = e / row_bytes, c = e - r * row_bytes;
+    const int64_t dr = (dst_row0 + r) % ring_rows;
+    dst[dr * row_bytes + c] = src[(src_row0 + r) * row_bytes + c];
+  }
+}
+__global__ void __launch_bounds__(kThreads) sap_rows_gather16_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src,
+                                                                     const int64_t* __restrict__ ids, int64_t row16,
+                                                                     int64_t total16) {
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total16; e += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = e / row16, c = e - r * row16;
+    dst[e] = src[ids[r] * row16 + c];
+  }
+}
+__global__ void __launch_bounds__(kThreads) sap_rows_gather1_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                                                    const int64_t* __restrict__ ids, int64_t row_bytes,
+                                                                    int64_t total) {
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = e / row_bytes, c = e - r * row_bytes;
+    dst[e] = src[ids[r] * row_bytes + c];
+  }
+}
+
+__device__ __forceinline__ int64_t load_int(const void* base, int64_t idx, int dtype) {
+  switch (dtype) {
+    case SAP_I64: return reinterpret_cast<const int64_t*>(base)[idx];
+    case SAP_I32: return reinterpret_cast<const int32_t*>(base)[idx];
+    case SAP_I16: return reinterpret_cast<const int16_t*>(base)[idx];
+    case SAP_U8: return reinterpret_cast<const uint8_t*>(base)[idx];
+    default: return 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sap_onehot_kernel(const void* actions, int adt, void* onehot, int odt,
+                                                              int64_t rows, int m) {
+  const int64_t total = rows * m;
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = e / m;
+    const int j = (int)(e - r * m);
+    sap_store_int(onehot, e, odt, load_int(actions, r, adt) == j ? 1 : 0);
+  }
+}
+
+// beta field [B, T+1, n, m, L] rebuilt from planes [B, T, n, m]
+__global__ void __launch_bounds__(kThreads) sap_beta_window_kernel(SapEnvDims d, const float* __restrict__ planes,
+                                                                   const float* __restrict__ prios, void* beta, int dtype) {
+  const int64_t nm = (int64_t)d.n * d.m;
+  const int64_t total = (int64_t)d.B * (d.T + 1) * nm;
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+    const int64_t bt = e / nm, x = e - bt * nm;
+    const int b = (int)(bt / (d.T + 1)), t = (int)(bt - (int64_t)b * (d.T + 1));
+    const int j = (int)(x % d.m);
+    const double pr = prios ? (double)prios[j] : 1.0;
+    for (int l = 0; l < d.L; ++l) {
+      const double v = (t + l < d.T) ? (double)planes[((int64_t)(d.shared_planes ? 0 : b) * d.T + t + l) * nm + x] * pr : 0.0;
+      sap_store_real(beta, e * d.L + l, dtype, v);
+    }
+  }
+}
+
+inline unsigned grid_for(int64_t work) {
+  int64_t blocks = (work + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)SAP_NUM_SMS * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace
+
+extern "C" int sap_benefit_ingest(const float* src_nmT, float* dst_Tnm, int32_t B, int32_t n, int32_t m, int32_t T,
+                                  void* stream) {
+  SAP_REQUIRE(src_nmT && dst_Tnm, SAP_E_NULL, "sap_benefit_ingest: src/dst is null");
+  SAP_REQUIRE(B > 0 && n > 0 && m > 0 && T > 0 && B <= 65535, SAP_E_DIMS, "sap_benefit_ingest: bad dims B=%d n=%d m=%d T=%d",
+              B, n, m, T);
+  const int nm = n * m;
+  dim3 grid((T + 31) / 32, (nm + 31) / 32, B);
+  SAP_REQUIRE(grid.y <= 65535, SAP_E_DIMS, "sap_benefit_ingest: n*m too large");
+  sap_ingest_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(src_nmT, dst_Tnm, nm, T);
+  SAP_CUDA_LAUNCH_CHECK("sap_ingest_kernel");
+  return SAP_OK;
+}
+
+extern "C" int sap_benefit_upload_host(const float* src_nmT_host, float* staging_dev, float* dst_Tnm, int32_t B,
+                                       int32_t n, int32_t m, int32_t T, void* stream) {
+  SAP_REQUIRE(src_nmT_host && staging_dev && dst_Tnm, SAP_E_NULL, "sap_benefit_upload_host: null pointer");
+  SAP_REQUIRE(B > 0 && n > 0 && m > 0 && T > 0, SAP_E_DIMS, "sap_benefit_upload_host: bad dims");
+  cudaError_t e = cudaMemcpyAsync(staging_dev, src_nmT_host, sizeof(float) * (size_t)B * n * m * T,
+                                  cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    sap_set_error("sap_benefit_upload_host: cudaMemcpyAsync: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  return sap_benefit_ingest(staging_dev, dst_Tnm, B, n, m, T, stream);
+}
+
+extern "C" int sap_buffer_insert(void* dst, const void* src, int64_t row_bytes, int64_t ring_rows, int64_t dst_row0,
+                                 int64_t src_row0, int64_t count, void* stream) {
+  SAP_REQUIRE(dst && src, SAP_E_NULL, "sap_buffer_insert: dst/src is null");
+  SAP_REQUIRE(row_bytes > 0 && ring_rows > 0 && count >= 0 && dst_row0 >= 0 && dst_row0 < ring_rows && src_row0 >= 0 &&
+                  count <= ring_rows,
+              SAP_E_DIMS, "sap_buffer_insert: bad arguments");
+  if (count == 0) return SAP_OK;
+  if (row_bytes % 16 == 0 && sap_aligned16(dst) && sap_aligned16(src)) {
+    const int64_t row16 = row_bytes / 16, total = row16 * count;
+    sap_rows_copy16_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>((uint4*)dst, (const uint4*)src, row16,
+                                                                                  ring_rows, dst_row0, src_row0, total);
+  } else {
+    const int64_t total = row_bytes * count;
+    sap_rows_copy1_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>((uint8_t*)dst, (const uint8_t*)src,
+                                                                                 row_bytes, ring_rows, dst_row0, src_row0,
+                                                                                 total);
+  }
+  SAP_CUDA_LAUNCH_CHECK("sap_rows_copy_kernel");
+  return SAP_OK;
+}
+
+extern "C" int sap_buffer_gather(void* dst, const void* src, const int64_t* ids, int64_t row_bytes, int64_t count,
+                                 void* stream) {
+  SAP_REQUIRE(dst && src && ids, SAP_E_NULL, "sap_buffer_gather: dst/src/ids is null");
+  SAP_REQUIRE(row_bytes > 0 && count >= 0, SAP_E_DIMS, "sap_buffer_gather: bad arguments");
+  if (count == 0) return SAP_OK;
+  if (row_bytes % 16 == 0 && sap_aligned16(dst) && sap_aligned16(src)) {
+    const int64_t row16 = row_bytes / 16, total = row16 * count;
+    sap_rows_gather16_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>((uint4*)dst, (const uint4*)src, ids,
+                                                                                    row16, total);
+  } else {
+    const int64_t total = row_bytes * count;
+    sap_rows_gather1_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>((uint8_t*)dst, (const uint8_t*)src, ids,
+                                                                                   row_bytes, total);
+  }
+  SAP_CUDA_LAUNCH_CHECK("sap_rows_gather_kernel");
+  return SAP_OK;
+}
+
+extern "C" int sap_onehot(const void* actions, int32_t actions_dtype, void* onehot, int32_t onehot_dtype, int64_t rows,
+                          int32_t m, void* stream) {
+  SAP_REQUIRE(actions && onehot, SAP_E_NULL, "sap_onehot: actions/onehot is null");
+  SAP_REQUIRE(rows >= 0 && m > 0, SAP_E_DIMS, "sap_onehot: bad dims");
+  SAP_REQUIRE(actions_dtype == SAP_I64 || actions_dtype == SAP_I32 || actions_dtype == SAP_I16, SAP_E_DTYPE,
+              "sap_onehot: actions must be i64|i32|i16");
+  if (rows == 0) return SAP_OK;
+  sap_onehot_kernel<<<grid_for(rows * m), kThreads, 0, (cudaStream_t)stream>>>(actions, actions_dtype, onehot,
+                                                                              onehot_dtype, rows, m);
+  SAP_CUDA_LAUNCH_CHECK("sap_onehot_kernel");
+  return SAP_OK;
+}
+
+extern "C" int sap_real_beta_window(const SapEnvDims* dims, const float* planes, const float* task_prios, void* beta,
+                                    int32_t dtype, void* stream) {
+  SAP_REQUIRE(dims && planes && beta, SAP_E_NULL, "sap_real_beta_window: null pointer");
+  SAP_REQUIRE(dtype == SAP_F32 || dtype == SAP_F16, SAP_E_DTYPE, "sap_real_beta_window: beta must be f32|f16");
+  SAP_REQUIRE(dims->B > 0 && dims->n > 0 && dims->m > 0 && dims->T > 0 && dims->L > 0, SAP_E_DIMS,
+              "sap_real_beta_window: bad dims");
+  const int64_t total = (int64_t)dims->B * (dims->T + 1) * dims->n * dims->m;
+  sap_beta_window_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(*dims, planes, task_prios, beta, dtype);
+  SAP_CUDA_LAUNCH_CHECK("sap_beta_window_kernel");
+  return SAP_OK;
+}

@@ -1,0 +1,221 @@
+// Action selectors: masked epsilon-greedy / argmax, one warp per (env, agent) row.
+//
+// Replaces /root/reference/src/action_selectors/classic_selectors.py:37-54
+// (EpsilonGreedyActionSelector.select_action) and filtered_classic_selectors.py:17-63
+// (FilteredEpsilonGreedyActionSelector.select_action).  Random draws are either injected
+// (parity with the reference under patched torch.rand_like / Categorical.sample) or Philox4x32-10.
+#include "sap_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// first-index argmax over lanes (value desc, idx asc) on fp32 keys; idx < 0 = empty
+__device__ __forceinline__ void warp_argmax_f32(float& v, int& i) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    float ov = __shfl_xor_sync(SAP_FULL_MASK, v, off);
+    int oi = __shfl_xor_sync(SAP_FULL_MASK, i, off);
+    bool take = (oi >= 0) && (i < 0 || ov > v || (ov == v && oi < i));
+    if (take) {
+      v = ov;
+      i = oi;
+    }
+  }
+}
+
+// the rank-th available action of a row (rank counted over set bits in index order), one warp
+__device__ __forceinline__ int warp_rank_select(const uint8_t* avail_row, int A, int rank, int lane) {
+  int seen = 0, found = -1;
+  for (int base = 0; base < A && found < 0; base += 32) {
+    const int j = base + lane;
+    const bool av = (j < A) && (avail_row ? avail_row[j] != 0 : true);
+    const unsigned bal = __ballot_sync(SAP_FULL_MASK, av);
+    const int c = __popc(bal);
+    if (rank < seen + c) {
+      // the (rank-seen)-th set bit of bal
+      const int want = rank - seen;
+      const int before = __popc(bal & ((1u << lane) - 1u));
+      const unsigned hit = __ballot_sync(SAP_FULL_MASK, av && before == want);
+      found = base + (__ffs(hit) - 1);
+    }
+    seen += c;
+  }
+  return found;
+}
+
+struct SelParams {
+  const float* q;
+  const int32_t* top;    // filtered only
+  const uint8_t* avail;  // nullable
+  int B, n, A, m, M;
+  float eps;
+  uint64_t seed;
+  const uint64_t* episode_ctr;
+  const int32_t* k;
+  const float* u_tie;
+  const float* u_explore;
+  const float* u_action;
+  int64_t* out;
+};
+
+template <bool kFiltered>
+__global__ void __launch_bounds__(kThreads) sap_select_kernel(SelParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int64_t rows = (int64_t)p.B * p.n;
+  if (row >= rows) return;
+  const int b = (int)(row / p.n);
+  const int A = kFiltered ? p.m : p.A;  // width of the action space
+  const uint8_t* av = p.avail ? p.avail + row * A : nullptr;
+  const uint32_t ep_lo = p.episode_ctr ? (uint32_t)(*p.episode_ctr) : 0u;
+  const uint32_t step = p.k ? (uint32_t)p.k[b] : 0u;
+  const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+
+  // ---- greedy branch: first-index argmax
+  float bv = 0.f;
+  int bi = -1;
+  int n_avail = 0;
+  if (!kFiltered) {
+    const float* qr = p.q + row * A;
+    for (int j = lane; j < A; j += 32) {
+      const bool ok = av ? av[j] != 0 : true;
+      n_avail += ok;
+      const float v = ok ? qr[j] : -INFINITY;  // classic_selectors.py:46-47
+      if (bi < 0 || v > bv) {
+        bv = v;
+        bi = j;
+      }
+    }
+  } else {
+    const float* qr = p.q + row * (p.M + 1);
+    const int32_t* tp = p.top + row * p.M;
+    const float base = qr[p.M];  // filtered_classic_selectors.py:42
+    for (int j = lane; j < A; j += 32) {
+      n_avail += av ? (av[j] != 0) : 1;
+      float u;
+      if (p.u_tie) {
+        u = p.u_tie[row * A + j];
+      } else {
+        SapPhilox4 r = sap_philox4x32_10((uint32_t)row, ep_lo, step, 1u + (uint32_t)(j >> 2), k0, k1);
+        const uint32_t bits = (j & 3) == 0 ? r.x : (j & 3) == 1 ? r.y : (j & 3) == 2 ? r.z : r.w;
+        u = sap_u01(bits);
+      }
+      float v = __fadd_rn(base, __fmul_rn(u, 1e-8f));  // :46-47, no FMA contraction
+      for (int qi = 0; qi < p.M; ++qi)
+        if (tp[qi] == j) v = qr[qi];  // :53-54
+      if (bi < 0 || v > bv) {  // no availability mask on the greedy branch of this selector
+        bv = v;
+        bi = j;
+      }
+    }
+  }
+  warp_argmax_f32(bv, bi);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) n_avail += __shfl_xor_sync(SAP_FULL_MASK, n_avail, off);
+
+  // ---- explore branch
+  float ue, ua;
+  if (p.u_explore && p.u_action) {
+    ue = p.u_explore[row];
+    ua = p.u_action[row];
+  } else {
+    SapPhilox4 r = sap_philox4x32_10((uint32_t)row, ep_lo, step, 0u, k0, k1);
+    ue = sap_u01(r.x);
+    ua = sap_u01(r.y);
+  }
+  int action = bi;
+  if (ue < p.eps && n_avail > 0) {  // :49-50 ; Categorical over the 0/1 mask = uniform over available
+    int rank = (int)floorf(__fmul_rn(ua, (float)n_avail));
+    rank = min(rank, n_avail - 1);
+    action = warp_rank_select(av, A, rank, lane);
+  }
+  if (lane == 0) p.out[row] = (int64_t)action;
+}
+
+// top-M task indices per (env, agent) row from a beta tensor, stable (value desc, idx asc)
+template <typename TB>
+__global__ void __launch_bounds__(kThreads) sap_topm_kernel(const TB* beta, int64_t rows, int m, int L, int M,
+                                                            int32_t* top) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TB* br = beta + row * (int64_t)m * L;
+  double lastv = 0.0;
+  int lasti = -1;
+  for (int r = 0; r < M; ++r) {
+    double bv = 0.0;
+    int bi = -1;
+    for (int j = lane; j < m; j += 32) {
+      double v = 0.0;
+      for (int l = 0; l < L; ++l) v += (double)(float)br[(int64_t)j * L + l];
+      if (lasti >= 0 && !sap_better(lastv, lasti, v, j, false)) continue;
+      if (sap_better(v, j, bv, bi, false)) {
+        bv = v;
+        bi = j;
+      }
+    }
+    sap_warp_argbest(bv, bi, false);
+    lastv = bv;
+    lasti = bi;
+    if (lane == 0) top[row * M + r] = bi;
+  }
+}
+
+}  // namespace
+
+extern "C" int sap_select_epsilon_greedy(const float* q, const uint8_t* avail, int32_t B, int32_t n, int32_t A, float eps,
+                                         uint64_t seed, const uint64_t* episode_ctr, const int32_t* k,
+                                         const float* u_explore, const float* u_action, int64_t* actions_out,
+                                         void* stream) {
+  SAP_REQUIRE(q && actions_out, SAP_E_NULL, "sap_select_epsilon_greedy: q/actions_out is null");
+  SAP_REQUIRE(B > 0 && n > 0 && A > 0, SAP_E_DIMS, "sap_select_epsilon_greedy: bad dims B=%d n=%d A=%d", B, n, A);
+  SAP_REQUIRE((u_explore == nullptr) == (u_action == nullptr), SAP_E_NULL,
+              "sap_select_epsilon_greedy: u_explore and u_action must be given together");
+  SelParams p{};
+  p.q = q; p.avail = avail; p.B = B; p.n = n; p.A = A; p.eps = eps; p.seed = seed;
+  p.episode_ctr = episode_ctr; p.k = k; p.u_explore = u_explore; p.u_action = u_action; p.out = actions_out;
+  const int64_t rows = (int64_t)B * n;
+  sap_select_kernel<false><<<(unsigned)((rows + kWarps - 1) / kWarps), kThreads, 0, (cudaStream_t)stream>>>(p);
+  SAP_CUDA_LAUNCH_CHECK("sap_select_kernel<classic>");
+  return SAP_OK;
+}
+
+extern "C" int sap_select_filtered_epsilon_greedy(const float* q, const int32_t* top, const uint8_t* avail, int32_t B,
+                                                  int32_t n, int32_t m, int32_t M, float eps, uint64_t seed,
+                                                  const uint64_t* episode_ctr, const int32_t* k, const float* u_tie,
+                                                  const float* u_explore, const float* u_action, int64_t* actions_out,
+                                                  void* stream) {
+  SAP_REQUIRE(q && top && actions_out, SAP_E_NULL, "sap_select_filtered_epsilon_greedy: q/top/actions_out is null");
+  SAP_REQUIRE(B > 0 && n > 0 && m > 0 && M > 0 && M <= m, SAP_E_DIMS,
+              "sap_select_filtered_epsilon_greedy: bad dims B=%d n=%d m=%d M=%d", B, n, m, M);
+  SAP_REQUIRE((u_explore == nullptr) == (u_action == nullptr), SAP_E_NULL,
+              "sap_select_filtered_epsilon_greedy: u_explore and u_action must be given together");
+  SelParams p{};
+  p.q = q; p.top = top; p.avail = avail; p.B = B; p.n = n; p.m = m; p.M = M; p.eps = eps; p.seed = seed;
+  p.episode_ctr = episode_ctr; p.k = k; p.u_tie = u_tie; p.u_explore = u_explore; p.u_action = u_action;
+  p.out = actions_out;
+  const int64_t rows = (int64_t)B * n;
+  sap_select_kernel<true><<<(unsigned)((rows + kWarps - 1) / kWarps), kThreads, 0, (cudaStream_t)stream>>>(p);
+  SAP_CUDA_LAUNCH_CHECK("sap_select_kernel<filtered>");
+  return SAP_OK;
+}
+
+extern "C" int sap_topm_from_beta(const void* beta, int32_t dtype, int32_t B, int32_t n, int32_t m, int32_t L, int32_t M,
+                                  int32_t* top_out, void* stream) {
+  SAP_REQUIRE(beta && top_out, SAP_E_NULL, "sap_topm_from_beta: beta/top_out is null");
+  SAP_REQUIRE(B > 0 && n > 0 && m > 0 && L > 0 && M > 0 && M <= m, SAP_E_DIMS,
+              "sap_topm_from_beta: bad dims B=%d n=%d m=%d L=%d M=%d", B, n, m, L, M);
+  const int64_t rows = (int64_t)B * n;
+  const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps);
+  if (dtype == SAP_F32) {
+    sap_topm_kernel<float><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const float*)beta, rows, m, L, M, top_out);
+  } else if (dtype == SAP_F16) {
+    sap_topm_kernel<__half><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const __half*)beta, rows, m, L, M, top_out);
+  } else {
+    SAP_REQUIRE(false, SAP_E_DTYPE, "sap_topm_from_beta: beta must be f32|f16");
+  }
+  SAP_CUDA_LAUNCH_CHECK("sap_topm_kernel");
+  return SAP_OK;
+}

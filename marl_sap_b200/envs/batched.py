@@ -1,0 +1,222 @@
+"""Device-resident batches of sequential-assignment environments (B independent envs per launch).
+
+``BatchedRealConstellationEnv``  <- /root/reference/src/envs/real_constellation_env.py  (RealConstellationEnv :17-328)
+``BatchedMockConstellationEnv``  <- /root/reference/src/envs/mock_constellation_env.py  (MockConstellationEnv :13-274)
+
+State lives in HBM: benefit planes [B, T, n, m] fp32 (re-laid out once from the reference's
+[n, m, T]), step counters k[B], prev_assigns[B, n], per-env return accumulators.  ``reset`` and
+``step`` are single kernel launches that write their slots straight into an EpisodeBatch.
+There is no CPU path: construction fails without CUDA or without the built library.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch as th
+
+from .. import _lib
+from ..components.transforms import OneHot
+
+
+def real_obs_size(M, N, L):
+    """real_constellation_env.py:263-265."""
+    return M * L + N * M * L + N * M // 2 * L + M
+
+
+def real_scheme(n, m, L, obs_size):
+    """real_constellation_env.py:89-114 (discrete actions)."""
+    scheme = {
+        "obs": {"vshape": obs_size, "group": "agents", "dtype": th.float16},
+        "actions": {"vshape": (1,), "group": "agents", "dtype": th.int16},
+        "avail_actions": {"vshape": (m,), "group": "agents", "dtype": th.bool},
+        "rewards": {"vshape": (n,), "dtype": th.float16},
+        "terminated": {"vshape": (1,), "dtype": th.bool},
+        "prev_assigns": {"vshape": (n,), "dtype": th.int16, "part_of_state": True},
+        "beta": {"vshape": (n, m, L), "dtype": th.float16, "part_of_state": True},
+    }
+    return scheme, {"actions": ("actions_onehot", [OneHot(out_dim=m)])}
+
+
+def mock_scheme(n, m, L):
+    """mock_constellation_env.py:67-92 (discrete actions)."""
+    scheme = {
+        "obs": {"vshape": L * m + m, "group": "agents", "dtype": th.float32},
+        "actions": {"vshape": (1,), "group": "agents", "dtype": th.int64},
+        "avail_actions": {"vshape": (m,), "group": "agents", "dtype": th.bool},
+        "rewards": {"vshape": (n,), "dtype": th.float32},
+        "terminated": {"vshape": (1,), "dtype": th.bool},
+        "prev_assigns": {"vshape": (n,), "dtype": th.int64, "part_of_state": True},
+        "beta": {"vshape": (n, m), "dtype": th.float32, "part_of_state": True},
+    }
+    return scheme, {"actions": ("actions_onehot", [OneHot(out_dim=m)])}
+
+
+class _BatchedEnvBase:
+    kind = "base"
+
+    def __init__(self, B, n, m, T, L, M, N, lambda_, T_trans, device):
+        self.lib = _lib.load()
+        if not th.cuda.is_available():
+            raise RuntimeError("marl_sap_b200: a CUDA device is required (there is no CPU path)")
+        self.device = th.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError(f"marl_sap_b200: envs live on a CUDA device, got {self.device}")
+        self.B, self.n, self.m, self.T, self.L, self.M, self.N = B, n, m, T, L, M, N
+        self.lambda_ = float(lambda_)
+        dev = self.device
+        self.k = th.zeros(B, dtype=th.int32, device=dev)
+        self.prev = th.zeros(B, n, dtype=th.int32, device=dev)
+        self.ep_return = th.zeros(B, dtype=th.float64, device=dev)
+        self.counts = th.zeros(B, m, dtype=th.int32, device=dev)
+        self.T_trans = None if T_trans is None else th.as_tensor(np.asarray(T_trans), dtype=th.float32).contiguous().to(dev)
+        if self.T_trans is not None and tuple(self.T_trans.shape) != (m, m):
+            raise ValueError(f"T_trans must be [m, m] = [{m}, {m}], got {tuple(self.T_trans.shape)}")
+        self.planes = None
+        self.shared_planes = False
+        self._staging = None
+        self.t_host = 0  # host mirror of k (all envs step in lockstep)
+
+    # ------------------------------------------------------------------ benefits
+    def load_benefits(self, sat_prox_mat):
+        """Install benefit tensors given in the REFERENCE layout: [n, m, T] (shared by all B envs, like
+        ParallelRunner's identical env_args) or [B, n, m, T].  Host arrays are uploaded with
+        ``sap_benefit_upload_host``; CUDA tensors are re-laid out in place with ``sap_benefit_ingest``."""
+        S = sat_prox_mat
+        if isinstance(S, np.ndarray):
+            S = th.from_numpy(np.ascontiguousarray(S, dtype=np.float32))
+        if S.dtype != th.float32:
+            S = S.to(th.float32)
+        shared = S.dim() == 3
+        Bp = 1 if shared else S.shape[0]
+        if tuple(S.shape[-3:]) != (self.n, self.m, self.T) or (not shared and Bp != self.B):
+            raise ValueError(f"sat_prox_mat must be [n,m,T]=[{self.n},{self.m},{self.T}] or [B,n,m,T] with B={self.B}, "
+                             f"got {tuple(S.shape)}")
+        S = S.contiguous()
+        if self.planes is None or self.planes.shape[0] != Bp:
+            self.planes = th.empty(Bp, self.T, self.n, self.m, dtype=th.float32, device=self.device)
+        stream = _lib.stream_ptr(self.device)
+        if S.is_cuda:
+            _lib.check(self.lib.sap_benefit_ingest(S.data_ptr(), self.planes.data_ptr(), Bp, self.n, self.m, self.T, stream),
+                       "sap_benefit_ingest")
+            self._keepalive = S
+        else:
+            if self._staging is None or self._staging.numel() != S.numel():
+                self._staging = th.empty(S.numel(), dtype=th.float32, device=self.device)
+            _lib.check(self.lib.sap_benefit_upload_host(S.data_ptr(), self._staging.data_ptr(), self.planes.data_ptr(), Bp,
+                                                        self.n, self.m, self.T, stream), "sap_benefit_upload_host")
+            self._keepalive = S  # the async copy reads the host buffer until the stream reaches it
+        self.shared_planes = shared
+        return self
+
+    def set_planes(self, planes, shared=False):
+        """Adopt an already device-laid-out tensor [B or 1, T, n, m] (no copy)."""
+        _lib.require_cuda(planes, "planes")
+        assert planes.dtype == th.float32 and planes.is_contiguous()
+        assert tuple(planes.shape[1:]) == (self.T, self.n, self.m)
+        self.planes, self.shared_planes = planes, bool(shared)
+        return self
+
+    def dims(self):
+        return _lib.SapEnvDims(self.B, self.n, self.m, self.T, self.L, self.M, self.N, 1 if self.shared_planes else 0)
+
+    def _check_batch(self, batch):
+        if batch.batch_size != self.B or batch.max_seq_length != self.T + 1:
+            raise ValueError(f"EpisodeBatch must be [B={self.B}, T+1={self.T + 1}], got "
+                             f"[{batch.batch_size}, {batch.max_seq_length}]")
+        if self.planes is None:
+            raise RuntimeError("no benefit tensor loaded: call load_benefits() first")
+
+    def _check_actions(self, actions):
+        _lib.require_cuda(actions, "actions")
+        if actions.dtype != th.int64:
+            actions = actions.long()
+        actions = actions.reshape(self.B, self.n).contiguous()
+        return actions
+
+    def episode_returns(self):
+        return self.ep_return
+
+
+class BatchedRealConstellationEnv(_BatchedEnvBase):
+    kind = "real"
+
+    def __init__(self, B, n, m, T, L, M, N, lambda_, sat_prox_mat=None, task_prios=None, T_trans=None, device=None,
+                 T_ctor=None):
+        # L = min(L, T_ctor) is taken BEFORE T is overridden by sat_prox_mat.shape[2]
+        # (real_constellation_env.py:38 vs :58-60); callers pass T_ctor when they mirror the ctor.
+        L = min(L, T_ctor if T_ctor is not None else T)
+        super().__init__(B, n, m, T, L, M, N, lambda_, T_trans, device)
+        self.obs_size = real_obs_size(M, N, L)
+        self.task_prios = None if task_prios is None else \
+            th.as_tensor(np.asarray(task_prios), dtype=th.float32).contiguous().to(self.device)
+        self.top = th.zeros(B, n, M, dtype=th.int32, device=self.device)
+        self.scheme, self.preprocess = real_scheme(n, m, L, self.obs_size)
+        need = int(self.lib.sap_real_scratch_doubles(self.dims()))
+        self.scratch = th.empty(need, dtype=th.float64, device=self.device) if need > 0 else None
+        if sat_prox_mat is not None:
+            self.load_benefits(sat_prox_mat)
+
+    def reset(self, batch):
+        self._check_batch(batch)
+        view = batch.kernel_view()
+        _lib.check(self.lib.sap_real_reset(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios), _lib.ptr(self.k),
+                                           _lib.ptr(self.prev), _lib.ptr(self.ep_return), view, _lib.ptr(self.top),
+                                           _lib.ptr(self.scratch), _lib.stream_ptr(self.device)), "sap_real_reset")
+        self.t_host = 0
+
+    def step(self, actions, batch):
+        actions = self._check_actions(actions)
+        view = batch.kernel_view()
+        _lib.check(self.lib.sap_real_step(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios),
+                                          _lib.ptr(self.T_trans), self.lambda_, actions.data_ptr(), _lib.ptr(self.k),
+                                          _lib.ptr(self.prev), _lib.ptr(self.ep_return), _lib.ptr(self.counts), view,
+                                          _lib.ptr(self.top), _lib.ptr(self.scratch), _lib.stream_ptr(self.device)),
+                   "sap_real_step")
+        self.t_host += 1
+        return self.t_host >= self.T
+
+    def beta_field(self, dtype=th.float16):
+        """The `beta` buffer field [B, T+1, n, m, L] rebuilt from the planes (lazy materialisation)."""
+        out = th.empty(self.B, self.T + 1, self.n, self.m, self.L, dtype=dtype, device=self.device)
+        _lib.check(self.lib.sap_real_beta_window(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios),
+                                                 out.data_ptr(), _lib.sap_dtype(dtype), _lib.stream_ptr(self.device)),
+                   "sap_real_beta_window")
+        return out
+
+
+class BatchedMockConstellationEnv(_BatchedEnvBase):
+    kind = "mock"
+
+    def __init__(self, B, n, m, T, L, lambda_, sat_prox_mat=None, T_trans=None, device=None):
+        super().__init__(B, n, m, T, L, 0, 0, lambda_, T_trans, device)
+        self.obs_size = (L + 1) * m
+        self.scheme, self.preprocess = mock_scheme(n, m, L)
+        if sat_prox_mat is not None:
+            self.load_benefits(sat_prox_mat)
+
+    def draw_prev_assigns(self):
+        """mock_constellation_env.py:105: np.random.choice(m, n, replace=False) per env, host RNG like the reference."""
+        if self.m < self.n:
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        return np.stack([np.random.choice(self.m, self.n, replace=False) for _ in range(self.B)]).astype(np.int64)
+
+    def reset(self, batch, prev0=None):
+        self._check_batch(batch)
+        if prev0 is None:
+            prev0 = self.draw_prev_assigns()
+        prev0 = th.as_tensor(np.asarray(prev0) if not isinstance(prev0, th.Tensor) else prev0, dtype=th.int64)
+        prev0 = prev0.reshape(self.B, self.n).contiguous().to(self.device)
+        view = batch.kernel_view()
+        _lib.check(self.lib.sap_mock_reset(self.dims(), _lib.ptr(self.planes), prev0.data_ptr(), _lib.ptr(self.k),
+                                           _lib.ptr(self.prev), _lib.ptr(self.ep_return), view,
+                                           _lib.stream_ptr(self.device)), "sap_mock_reset")
+        self.t_host = 0
+
+    def step(self, actions, batch):
+        actions = self._check_actions(actions)
+        view = batch.kernel_view()
+        _lib.check(self.lib.sap_mock_step(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.T_trans), self.lambda_,
+                                          actions.data_ptr(), _lib.ptr(self.k), _lib.ptr(self.prev),
+                                          _lib.ptr(self.ep_return), _lib.ptr(self.counts), view,
+                                          _lib.stream_ptr(self.device)), "sap_mock_step")
+        self.t_host += 1
+        return self.t_host >= self.T

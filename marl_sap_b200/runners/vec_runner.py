@@ -1,0 +1,228 @@
+"""Batched CUDA rollout runner behind the reference's runner interface.
+
+Replaces /root/reference/src/runners/parallel_runner.py:12-299 (ParallelRunner + env_worker processes +
+pickle over Pipes) and runners/episode_runner.py:8-137 (EpisodeRunner) for the SAP envs: all
+``batch_size_run`` environments live in one device-resident batched env and advance in lockstep, one fused
+kernel launch per timestep (select -> step -> obs(t+1) -> buffer writes).
+
+Same surface as the reference runners: ``Runner(args, logger)``, ``setup(scheme, groups, preprocess, mac)``,
+``get_env()``, ``run(test_mode) -> EpisodeBatch``, ``close_env()``, ``save_replay()``, attributes
+``batch_size, t_env, T, log_train_stats_t`` and the ``logger.log_stat`` keys ``return_mean/std``,
+``ep_length_mean``, ``epsilon``, ``steps`` (with the ``test_`` prefix in test mode).
+
+Semantics follow EpisodeRunner (A.5 timeline of SURVEY.md): ``terminated`` is the env's done flag (True only
+at t = T-1), no extra selection at t = T, independent per-(env, agent, step) random streams.  The reference
+ParallelRunner's bugs (terminated list-truthiness, extra select, shared numpy RNG) are NOT
+reproduced.
+
+Multi-GPU: one process per GPU, each rank owns ``batch_size_run`` envs (block partition); the only collective
+is one all-reduce of [sum return, sum return^2, n_episodes, sum ep_length] per ``run()``.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import numpy as np
+import torch as th
+
+from ..components.episode_buffer import EpisodeBatch
+from ..envs import BATCHED as batched_REGISTRY
+from ..envs import REGISTRY as env_REGISTRY
+
+
+def build_batched_env(env_name, env_args, B, device):
+    """Translate the reference's ``env_args`` (config yaml + explicit_dict_items) into a batched device env."""
+    if env_name not in batched_REGISTRY:
+        env_REGISTRY[env_name]()  # raises the explanatory NotImplementedError for off-path envs
+    ea = dict(env_args)
+    S = ea.get("sat_prox_mat", None)
+    if S is None:
+        raise NotImplementedError("batched runners need env_args['sat_prox_mat'] ([n,m,T] shared or [B,n,m,T]); "
+                                  "on-device benefit generation is a 'next' row (SURVEY.md 8f-4)")
+    shape = tuple(S.shape)
+    n, m, T = shape[-3:]
+    if ea.get("bids_as_actions"):
+        raise NotImplementedError("bids_as_actions is outside the B200 hot path")
+    if env_name == "real_constellation_env":
+        return batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["M"], ea["N"], ea["lambda_"], sat_prox_mat=S,
+                                          task_prios=ea.get("task_prios"), T_trans=ea.get("T_trans"), device=device,
+                                          T_ctor=ea.get("T", T))
+    return batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["lambda_"], sat_prox_mat=S, T_trans=ea.get("T_trans"),
+                                      device=device)
+
+
+class _EnvInfo:
+    """What ``run.py`` reads from ``runner.get_env()`` (run.py:113-131): shapes, scheme and preprocess."""
+
+    def __init__(self, env):
+        self.n, self.m, self.T, self.L = env.n, env.m, env.T, env.L
+        self.scheme, self.preprocess = env.scheme, env.preprocess
+        self.obs_size = env.obs_size
+        self.M, self.N = getattr(env, "M", None), getattr(env, "N", None)
+
+    def get_obs_size(self):
+        return self.obs_size
+
+    def get_total_actions(self):
+        return self.m
+
+    def get_env_info(self):
+        return {"obs_shape": self.obs_size, "m": self.m, "n": self.n, "T": self.T}
+
+
+class CudaVecRunner:
+    """One batched env of ``batch_size_run`` environments per process (= per GPU)."""
+
+    def __init__(self, args, logger):
+        self.args = args
+        self.logger = logger
+        self.batch_size = self.args.batch_size_run
+        dev = getattr(args, "device", "cuda")
+        self.device = th.device(dev if str(dev).startswith("cuda") else "cuda")
+        self.env = build_batched_env(self.args.env, self.args.env_args, self.batch_size, self.device)
+        self.T = self.env.T
+        self.t = 0
+        self.t_env = 0
+        self.lazy = tuple(getattr(args, "lazy_buffer_fields", ()) or ())
+        self.reuse_batch = bool(getattr(args, "reuse_episode_batch", False))
+        self.train_returns, self.test_returns = _Moments(), _Moments()
+        self.train_stats, self.test_stats = {}, {}
+        self.log_train_stats_t = -100000
+        self.episode_ctr = th.zeros(1, dtype=th.int64, device=self.device)
+        self.last_episode_returns = None
+        self._batch = None
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ reference runner API
+    def setup(self, scheme, groups, preprocess, mac):
+        self.new_batch = partial(EpisodeBatch, scheme, groups, self.batch_size, self.T + 1, preprocess=preprocess,
+                                 device=self.device, lazy=self.lazy)
+        self.mac = mac
+        self.scheme, self.groups, self.preprocess = scheme, groups, preprocess
+        self.mac.action_selector.envs = [self.get_env()]
+        if hasattr(self.mac.action_selector, "bind_counters"):
+            self.mac.action_selector.bind_counters(self.episode_ctr, self.env.k)
+
+    def get_env(self):
+        return _EnvInfo(self.env)
+
+    def get_env_info(self):
+        return self.get_env().get_env_info()
+
+    def save_replay(self):
+        raise NotImplementedError("the SAP envs have no replay format (the reference's env.save_replay does not exist either)")
+
+    def close_env(self):
+        return None
+
+    def reset(self, **reset_kwargs):
+        if self.reuse_batch and self._batch is not None:
+            self.batch = self._batch
+            for v in self.batch.data.transition_data.values():
+                v.zero_()
+        else:
+            self.batch = self.new_batch()
+            self._batch = self.batch
+        if "beta" in self.lazy and self.env.kind == "real":
+            dtype = self.batch.scheme["beta"]["dtype"]
+            self.batch.set_lazy_provider("beta", lambda _b, env=self.env, dtype=dtype: env.beta_field(dtype))
+        if self.env.kind == "real":
+            self.batch.top_agent_tasks = self.env.top
+        self.env.reset(self.batch, **reset_kwargs)
+        self.kernel_launches += 1
+        self.t = 0
+
+    def run(self, test_mode=False, **reset_kwargs):
+        self.reset(**reset_kwargs)
+        self.mac.init_hidden(batch_size=self.batch_size)
+        for t in range(self.T):
+            # agent forward (torch) + selection kernel; obs / avail / beta for slot t were written by the env kernel
+            actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+            # fused env kernel: rewards/actions/terminated at slot t, obs/prev_assigns/filled at slot t+1
+            self.env.step(actions, self.batch)
+            self.kernel_launches += 2
+            self.t += 1
+        self.episode_ctr += 1
+        self.last_episode_returns = self.env.ep_return.clone()
+        self._finish_run(test_mode)
+        return self.batch
+
+    # ------------------------------------------------------------------ statistics (A.6 of SURVEY.md)
+    def _finish_run(self, test_mode):
+        ret = self.last_episode_returns
+        mom = th.stack([ret.sum(), (ret * ret).sum(),
+                        th.tensor(float(self.batch_size), dtype=th.float64, device=ret.device),
+                        th.tensor(float(self.batch_size * self.T), dtype=th.float64, device=ret.device)])
+        world = 1
+        if th.distributed.is_available() and th.distributed.is_initialized():
+            th.distributed.all_reduce(mom)  # the only collective of a rollout
+            world = th.distributed.get_world_size()
+        s, s2, n_ep, ep_len = mom.tolist()  # one host read per run()
+        cur_stats = self.test_stats if test_mode else self.train_stats
+        cur_returns = self.test_returns if test_mode else self.train_returns
+        log_prefix = "test_" if test_mode else ""
+        cur_stats["n_episodes"] = int(n_ep) + cur_stats.get("n_episodes", 0)
+        cur_stats["ep_length"] = int(ep_len) + cur_stats.get("ep_length", 0)
+        cur_returns.add(n_ep, s, s2)
+        if not test_mode:
+            self.t_env += int(ep_len)
+
+        n_test_runs = max(1, self.args.test_nepisode // (self.batch_size * world)) * self.batch_size * world
+        if test_mode and (cur_returns.count == n_test_runs):
+            self._log(cur_returns, cur_stats, log_prefix)
+        elif self.t_env - self.log_train_stats_t >= self.args.runner_log_interval:
+            self._log(cur_returns, cur_stats, log_prefix)
+            if hasattr(self.mac.action_selector, "epsilon"):
+                self.logger.log_stat("epsilon", self.mac.action_selector.epsilon, self.t_env)
+            self.log_train_stats_t = self.t_env
+            self.logger.log_stat("steps", self.t_env, self.t_env)
+
+    def _log(self, returns, stats, prefix):
+        self.logger.log_stat(prefix + "return_mean", returns.mean(), self.t_env)
+        self.logger.log_stat(prefix + "return_std", returns.std(), self.t_env)
+        returns.clear()
+        for k, v in stats.items():
+            if k != "n_episodes":
+                self.logger.log_stat(prefix + k + "_mean", v / stats["n_episodes"], self.t_env)
+        stats.clear()
+
+
+class _Moments:
+    """Sufficient statistics of the episode returns since the last log (np.mean / np.std, population)."""
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self.count, self.s, self.s2 = 0, 0.0, 0.0
+
+    def add(self, n, s, s2):
+        self.count += int(n)
+        self.s += s
+        self.s2 += s2
+
+    def __len__(self):
+        return self.count
+
+    def mean(self):
+        return self.s / self.count if self.count else float("nan")
+
+    def std(self):
+        if not self.count:
+            return float("nan")
+        mu = self.s / self.count
+        return math.sqrt(max(self.s2 / self.count - mu * mu, 0.0))
+
+
+class ParallelRunner(CudaVecRunner):
+    """REGISTRY["parallel"]: ``batch_size_run`` envs per launch (parallel_runner.py:12-243)."""
+
+
+class EpisodeRunner(CudaVecRunner):
+    """REGISTRY["episode"]: one env (episode_runner.py:8-137)."""
+
+    def __init__(self, args, logger):
+        assert args.batch_size_run == 1, "EpisodeRunner only supports batch size 1"
+        super().__init__(args, logger)
+        self.log_train_stats_t = -1000000

@@ -1,0 +1,289 @@
+"""GPU parity of the env kernels (through the C ABI) against the golden vectors recorded from the
+reference and against the CPU oracle on seeded inputs.  Bit-exact for indices/flags; obs/beta values are
+gathers (exact after the single rounding to the scheme dtype); rewards rounded once from float64."""
+import copy
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import cpu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REAL = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "real_*.npz"))) + ["kat1_real.npz"]
+MOCK = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "mock_*.npz")))
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
+
+
+def _batch_for(env, B, real_dtype=None, lazy=()):
+    from marl_sap_b200.components.episode_buffer import EpisodeBatch
+
+    scheme = copy.deepcopy(env.scheme)
+    if real_dtype is not None:
+        for k in ("obs", "rewards", "beta"):
+            scheme[k]["dtype"] = real_dtype
+    return EpisodeBatch(scheme, {"agents": env.n}, B, env.T + 1, preprocess=env.preprocess, device="cuda", lazy=lazy)
+
+
+def _cast(x64, dtype):
+    """The reference's single rounding th.tensor(np.array(v), dtype=...) (episode_buffer.py:107-108)."""
+    return th.tensor(np.asarray(x64), dtype=dtype)
+
+
+@pytest.mark.parametrize("name", REAL)
+@pytest.mark.parametrize("real_dtype", [th.float16, th.float32])
+@pytest.mark.parametrize("shared", [True, False])
+def test_real_env_matches_reference_golden(name, real_dtype, shared):
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    g = _load(name)
+    B = 3
+    S = g["S"]
+    n, m, T = S.shape
+    Sin = S if shared else np.broadcast_to(S, (B, n, m, T)).copy()
+    env = BatchedRealConstellationEnv(B, n, m, T, int(g["L_arg"]), int(g["M"]), int(g["N"]), float(g["lambda_"]),
+                                      sat_prox_mat=Sin, task_prios=g.get("task_prios"), T_ctor=int(g["T_ctor"]))
+    assert env.L == int(g["L"]) and env.obs_size == int(g["obs_size"])
+    batch = _batch_for(env, B, real_dtype)
+    env.reset(batch)
+    acts = g["actions"]
+    for t in range(acts.shape[0]):
+        a = th.tensor(np.broadcast_to(acts[t], (B, n)).copy(), device="cuda")
+        done = env.step(a, batch)
+        assert done == bool(g["done"][t])
+    th.cuda.synchronize()
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    Tn = acts.shape[0]
+    for b in range(B):
+        assert th.equal(td["obs"][b], _cast(g["obs"], real_dtype)), f"obs mismatch env {b}"
+        assert th.equal(td["beta"][b], _cast(g["beta"], real_dtype))
+        assert th.equal(td["prev_assigns"][b], _cast(g["prev"], th.int16))
+        assert th.equal(td["rewards"][b, :Tn], _cast(g["rewards"], real_dtype))
+        assert th.equal(td["actions"][b, :Tn, :, 0], _cast(acts, th.int16))
+        assert th.equal(td["actions_onehot"][b, :Tn], _cast(O.one_hot(acts, m, np.int16), th.int16))
+        assert td["terminated"][b, :Tn, 0].tolist() == [bool(d) for d in g["done"]]
+        assert td["filled"][b, :, 0].tolist() == [1] * (Tn + 1)
+        assert bool(td["avail_actions"][b].all())
+    # slots never written stay zero
+    assert not td["rewards"][:, Tn:].any() and not td["actions"][:, Tn:].any() and not td["terminated"][:, Tn:].any()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(B=5, n=50, m=50, T=6, L=3, M=10, N=10, gen="dense", seed=0),
+    dict(B=3, n=20, m=64, T=5, L=3, M=10, N=10, gen="ties", seed=1),
+    dict(B=2, n=100, m=100, T=4, L=3, M=10, N=10, gen="dense", seed=2),
+    dict(B=2, n=33, m=47, T=5, L=2, M=6, N=5, gen="ref", seed=3),
+    dict(B=2, n=40, m=130, T=3, L=4, M=8, N=3, gen="ref", seed=4),
+])
+def test_real_env_matches_oracle(cfg):
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    rng = np.random.default_rng(cfg["seed"])
+    B, n, m, T, L, M, N = (cfg[k] for k in ("B", "n", "m", "T", "L", "M", "N"))
+    if cfg["gen"] == "dense":
+        S = O.gen_dense(rng, B, n, m, T)
+    elif cfg["gen"] == "ties":
+        S = (np.round(O.gen_exact(rng, B, n, m, T, zero_frac=0.5) * 4) / 4).astype(np.float32)
+    else:
+        S = O.gen_ref_like(rng, B, n, m, T)
+    prios = (rng.integers(1, 4, size=m) * 0.5).astype(np.float32) if cfg["seed"] % 2 else None
+    acts = rng.integers(0, m, size=(T, B, n))
+    acts[:, :, : n // 3] = acts[:, :, :1]
+    st = O.RealState(S.astype(np.float64), L, M, N, 0.5, task_prios=prios)
+    want = O.rollout(st, lambda t, pre: acts[t], "real")
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S, task_prios=prios)
+    batch = _batch_for(env, B, th.float32)
+    env.reset(batch)
+    tops = [env.top.cpu().numpy().copy()]
+    counts = []
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+        tops.append(env.top.cpu().numpy().copy())
+        counts.append(env.counts.cpu().numpy().copy())
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    assert th.equal(td["obs"], _cast(want["obs"], th.float32))
+    assert th.equal(td["beta"], _cast(want["beta"], th.float32))
+    assert th.equal(td["rewards"], _cast(want["rewards"], th.float32))
+    assert th.equal(td["prev_assigns"], _cast(want["prev_assigns"], th.int16))
+    assert th.equal(td["terminated"][..., 0], th.tensor(want["terminated"]))
+    assert th.equal(td["filled"][..., 0], th.tensor(want["filled"]))
+    np.testing.assert_array_equal(np.stack(counts, 1), want["counts"][:, :T])
+    # the env's shared top-M equals the oracle's stable top-M of every pre-transition beta
+    for t in range(T):
+        np.testing.assert_array_equal(tops[t], O.top_m_tasks(want["beta"][:, t], M))
+    np.testing.assert_allclose(env.ep_return.cpu().numpy(), want["rewards"].sum((1, 2)), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", MOCK)
+def test_mock_env_matches_reference_golden(name):
+    from marl_sap_b200.envs.batched import BatchedMockConstellationEnv
+
+    g = _load(name)
+    S = g["S"]
+    n, m, T = S.shape
+    B = 2
+    env = BatchedMockConstellationEnv(B, n, m, T, int(g["L"]), float(g["lambda_"]), sat_prox_mat=S)
+    batch = _batch_for(env, B)
+    env.reset(batch, prev0=np.broadcast_to(g["prev0"], (B, n)).copy())
+    acts = g["actions"]
+    for t in range(T):
+        done = env.step(th.tensor(np.broadcast_to(acts[t], (B, n)).copy(), device="cuda"), batch)
+        assert done == bool(g["done"][t])
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    for b in range(B):
+        assert th.equal(td["obs"][b], _cast(g["obs"], th.float32))
+        assert th.equal(td["beta"][b], _cast(g["beta"], th.float32))
+        assert th.equal(td["rewards"][b, :T], _cast(g["rewards"], th.float32))
+        assert th.equal(td["actions"][b, :T, :, 0], th.tensor(acts))
+        assert not td["prev_assigns"][b].any()  # the mock env never emits prev_assigns (mock_constellation_env.py:170-174)
+        assert td["terminated"][b, :T, 0].tolist() == [bool(d) for d in g["done"]]
+        assert td["filled"][b, :, 0].tolist() == [1] * (T + 1)
+
+
+@pytest.mark.parametrize("cfg", [dict(B=4, n=10, m=10, T=7, L=3), dict(B=3, n=100, m=100, T=5, L=3),
+                                 dict(B=2, n=17, m=23, T=4, L=2), dict(B=2, n=50, m=52, T=3, L=5)])
+def test_mock_env_matches_oracle(cfg):
+    from marl_sap_b200.envs.batched import BatchedMockConstellationEnv
+
+    B, n, m, T, L = (cfg[k] for k in ("B", "n", "m", "T", "L"))
+    rng = np.random.default_rng(B * 1000 + n)
+    S = O.gen_ref_like(rng, B, n, m, T)
+    prev0 = np.stack([rng.permutation(m)[:n] for _ in range(B)])
+    acts = rng.integers(0, m, size=(T, B, n))
+    acts[:, :, : n // 2] = acts[:, :, :1]
+    Tt = rng.integers(0, 2, size=(m, m)).astype(np.float64) if n == 17 else None
+    st = O.MockState(S.astype(np.float64), L, 0.5, T_trans=Tt)
+    want = O.rollout(st, lambda t, pre: acts[t], "mock", prev0=prev0)
+    env = BatchedMockConstellationEnv(B, n, m, T, L, 0.5, sat_prox_mat=S, T_trans=Tt)
+    batch = _batch_for(env, B)
+    env.reset(batch, prev0=prev0)
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    assert th.equal(td["obs"], _cast(want["obs"], th.float32))
+    assert th.equal(td["beta"], _cast(want["beta"], th.float32))
+    assert th.equal(td["rewards"], _cast(want["rewards"], th.float32))
+    assert th.equal(td["terminated"][..., 0], th.tensor(want["terminated"]))
+    assert th.equal(td["actions_onehot"][:, :T], th.tensor(O.one_hot(np.moveaxis(acts, 0, 1), m, np.int64)))
+
+
+def test_real_env_custom_T_trans_and_lazy_fields():
+    """T_trans override (real_constellation_env.py:66, :314) and the lazy buffer mode (beta rebuilt on access)."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    rng = np.random.default_rng(9)
+    B, n, m, T, L, M, N = 2, 12, 20, 5, 3, 4, 3
+    S = O.gen_ref_like(rng, B, n, m, T)
+    Tt = rng.integers(0, 2, size=(m, m)).astype(np.float64)
+    acts = rng.integers(0, m, size=(T, B, n))
+    st = O.RealState(S.astype(np.float64), L, M, N, 0.5, T_trans=Tt)
+    want = O.rollout(st, lambda t, pre: acts[t], "real")
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S, T_trans=Tt)
+    batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
+    batch.set_lazy_provider("beta", lambda _b: env.beta_field(th.float16))
+    env.reset(batch)
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+    assert "beta" not in batch.data.transition_data and "avail_actions" not in batch.data.transition_data
+    assert th.equal(batch["rewards"].cpu(), _cast(want["rewards"], th.float16))
+    assert th.equal(batch["obs"].cpu(), _cast(want["obs"], th.float16))
+    assert th.equal(batch["beta"].cpu(), _cast(want["beta"], th.float16))
+    assert bool(batch["avail_actions"].all()) and batch["avail_actions"].shape == (B, T + 1, n, m)
+    oh = batch["actions_onehot"].cpu()
+    assert th.equal(oh[:, :T], _cast(O.one_hot(np.moveaxis(acts, 0, 1), m, np.int16), th.int16))
+
+
+def test_real_env_large_shape_properties():
+    """BASELINE-size envs (100 x 100, M = N = 10): size-independent properties instead of an oracle replay."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    B, n, m, T, L, M, N = 64, 100, 100, 8, 3, 10, 10
+    g = th.Generator().manual_seed(0)
+    S = th.rand(B, n, m, T, generator=g)
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S.cuda())
+    batch = _batch_for(env, B, th.float32, lazy=("beta", "avail_actions", "actions_onehot"))
+    env.reset(batch)
+    planes = env.planes.double()
+    for t in range(T):
+        acts = th.randint(0, m, (B, n), generator=g).cuda()
+        env.step(acts, batch)
+        # conflict counts: a histogram of the actions
+        want_cnt = th.zeros(B, m, dtype=th.int32, device="cuda").scatter_add_(1, acts, th.ones_like(acts, dtype=th.int32))
+        assert th.equal(env.counts, want_cnt)
+        if t + 1 < T:
+            tot = planes[:, t + 1:t + 1 + L].sum(1)  # [B,n,m] float64 window sums
+            top = env.top.long()
+            top_vals = tot.gather(2, top)
+            assert bool((top_vals[..., :-1] >= top_vals[..., 1:]).all()), "top-M not sorted by window sum"
+            rest = tot.scatter(2, top, float("-inf")).max(-1).values
+            assert bool((rest <= top_vals[..., -1]).all()), "an excluded task beats the M-th task"
+            obs = batch["obs"][:, t + 1]
+            local = obs[..., : M * L].reshape(B, n, M, L)
+            Leff = min(L, T - (t + 1))
+            want_local = planes[:, t + 1:t + 1 + Leff].permute(0, 2, 3, 1).gather(
+                2, top[..., None].expand(B, n, M, Leff)).float()
+            assert th.equal(local[..., :Leff], want_local)
+            flags = obs[..., -M:]
+            assert th.equal(flags, (top == acts[..., None]).float())
+    assert not batch["obs"][:, T].any()
+    # determinism: a second identical rollout gives identical bytes
+    first = batch["obs"].clone()
+    g2 = th.Generator().manual_seed(0)
+    _ = th.rand(B, n, m, T, generator=g2)
+    env.reset(batch)
+    for t in range(T):
+        env.step(th.randint(0, m, (B, n), generator=g2).cuda(), batch)
+    assert th.equal(first, batch["obs"])
+
+
+def test_real_env_precondition_errors():
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    S = np.zeros((1, 4, 3, 2), dtype=np.float32)  # m < n
+    env = BatchedRealConstellationEnv(1, 4, 3, 2, 1, 2, 2, 0.5, sat_prox_mat=S)
+    batch = _batch_for(env, 1)
+    with pytest.raises(RuntimeError, match="m >= n"):
+        env.reset(batch)
+    S = np.zeros((1, 4, 9, 2), dtype=np.float32)
+    env = BatchedRealConstellationEnv(1, 4, 9, 2, 1, 3, 2, 0.5, sat_prox_mat=S)  # odd M
+    with pytest.raises(RuntimeError, match="even"):
+        env.reset(_batch_for(env, 1))
+    with pytest.raises(ValueError):
+        env.load_benefits(np.zeros((4, 9, 3), dtype=np.float32))
+
+
+def test_single_env_facade_kat1():
+    """REGISTRY['real_constellation_env'] object driven like the reference env (KAT-1, experiments.py:265-288)."""
+    from marl_sap_b200.envs import REGISTRY
+
+    g = _load("kat1_real.npz")
+    env = REGISTRY["real_constellation_env"](num_planes=1, num_sats_per_plane=4, m=4, T=1, N=2, M=2, L=2, lambda_=0.5,
+                                             sat_prox_mat=g["S"].astype(np.float64), graphs=1)
+    assert (env.n, env.m, env.T, env.L) == (4, 4, 2, 1)
+    env.reset()
+    pre = env.get_pretransition_data()
+    np.testing.assert_array_equal(np.array(pre["obs"][0]), g["obs"][0])
+    np.testing.assert_array_equal(pre["prev_assigns"][0], np.arange(4))
+    r, d, info = env.step([0, 0, 2, 3])
+    np.testing.assert_allclose(r, [2.5, 0.75, 4.0, 10.0])
+    assert d is False and info == {}
+    import copy as _copy
+    import pickle
+
+    env2 = _copy.deepcopy(env)
+    r, d, info = env.step([1, 1, 1, 3])
+    np.testing.assert_allclose(r, [1 / 6, 1 / 6, 1 / 6, 1.0], rtol=1e-6)
+    assert d is True and not np.array(env.get_obs()).any()
+    r2, d2, _ = env2.step([1, 1, 1, 3])  # deep copy carries the live state (HAAL-style use)
+    np.testing.assert_allclose(r2, r)
+    env3 = pickle.loads(pickle.dumps(env))
+    assert env3.n == 4 and env3._impl is None
+    bh = env.beta_hat(g["beta"][0], np.arange(4))
+    np.testing.assert_allclose(bh[..., 0], g["beta"][0][..., 0] - 0.5 * (1 - np.eye(4)) * (g["beta"][0].sum(-1) > 1e-12))

@@ -1,0 +1,190 @@
+"""End-to-end rollout through the reference-facing API (runners.REGISTRY -> BasicMAC -> selector -> env kernels
+-> EpisodeBatch -> ReplayBuffer) against the CPU oracle's EpisodeRunner-order rollout."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch as th
+
+from oracle import cpu_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_args(env, env_args, B, selector="epsilon_greedy", agent="rnn", **kw):
+    base = dict(env=env, env_args=env_args, batch_size_run=B, device="cuda", runner="parallel", mac="basic_mac",
+                action_selector=selector, epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=50000,
+                evaluation_epsilon=0.0, agent=agent, hidden_dim=64, use_rnn=False, obs_agent_id=False,
+                obs_last_action=False, agent_output_type="q", test_nepisode=B, runner_log_interval=1, seed=3,
+                use_mps_action_selection=True)
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def build(args):
+    from marl_sap_b200.components.episode_buffer import ReplayBuffer
+    from marl_sap_b200.controllers import REGISTRY as mac_REGISTRY
+    from marl_sap_b200.runners import REGISTRY as r_REGISTRY
+    from marl_sap_b200.utils.logging import Logger
+
+    logger = Logger()
+    runner = r_REGISTRY[args.runner](args=args, logger=logger)
+    env = runner.get_env()
+    args.n, args.m, args.T = env.n, env.m, env.T  # run.py:113-116
+    groups = {"agents": args.n}
+    buffer = ReplayBuffer(env.scheme, groups, 2 * args.batch_size_run + 1, env.T + 1, preprocess=env.preprocess,
+                          device="cuda")
+    th.manual_seed(0)
+    mac = mac_REGISTRY[args.mac](buffer.scheme, groups, args)
+    mac.cuda()
+    runner.setup(scheme=env.scheme, groups=groups, preprocess=env.preprocess, mac=mac)
+    return runner, mac, buffer, logger
+
+
+class DrawInjector:
+    """Feeds pre-generated uniforms to the selector so the oracle can replay the same decisions."""
+
+    def __init__(self, selector, draws):
+        self.sel, self.draws, self.t = selector, draws, 0
+        self.orig = selector.select_action
+        selector.select_action = self
+
+    def __call__(self, *a, **k):
+        d = {name: th.tensor(v[self.t]).cuda() for name, v in self.draws.items()}
+        self.sel.inject_draws(**d)
+        self.t += 1
+        return self.orig(*a, **k)
+
+
+@pytest.mark.parametrize("env_name", ["real_constellation_env", "mock_constellation_env"])
+@pytest.mark.parametrize("obs_extra", [False, True])
+def test_runner_rollout_matches_oracle(env_name, obs_extra):
+    rng = np.random.default_rng(17)
+    B, n, m, T, L, M, N = 4, 12, 16, 9, 3, 4, 3
+    S = O.gen_dense(rng, B, n, m, T)
+    if env_name == "real_constellation_env":
+        env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=0.5, sat_prox_mat=S, graphs=1)
+        state = O.RealState(S.astype(np.float64), L, M, N, 0.5)
+        kind, real_dt, int_dt = "real", th.float16, th.int16
+    else:
+        env_args = dict(n=n, m=m, T=T, L=L, lambda_=0.5, sat_prox_mat=S)
+        state = O.MockState(S.astype(np.float64), L, 0.5)
+        kind, real_dt, int_dt = "mock", th.float32, th.int64
+    args = make_args(env_name, env_args, B, obs_agent_id=obs_extra, obs_last_action=obs_extra)
+    runner, mac, buffer, logger = build(args)
+    draws = {"u_explore": rng.random((T, B, n), dtype=np.float32), "u_action": rng.random((T, B, n), dtype=np.float32)}
+    DrawInjector(mac.action_selector, draws)
+    runner.t_env = 20000  # epsilon = 0.62: a mix of greedy and random picks
+    eps = O.epsilon_linear(1.0, 0.05, 50000, 20000)
+    prev0 = np.stack([rng.permutation(m)[:n] for _ in range(B)])
+
+    last_onehot = [np.zeros((B, n, m), dtype=np.float32)]
+
+    def policy(t, pre):
+        obs = th.tensor(pre["obs"], dtype=real_dt).float()  # buffer rounding, then .float() (basic_controller.py:82)
+        parts = [obs.reshape(B * n, -1)]
+        if obs_extra:
+            parts.append(th.tensor(last_onehot[0]).reshape(B * n, -1))
+            parts.append(th.eye(n).unsqueeze(0).expand(B, -1, -1).reshape(B * n, -1))
+        x = th.cat(parts, dim=1).cuda()
+        with th.no_grad():
+            q, _ = mac.agent(x, mac.agent.init_hidden().expand(B * n, -1))
+        q = q.view(B, n, -1).cpu().numpy()
+        a = O.select_epsilon_greedy(q, np.ones((B, n, m), bool), eps, draws["u_explore"][t], draws["u_action"][t])
+        last_onehot[0] = O.one_hot(a, m, np.float32)
+        return a
+
+    want = O.rollout(state, policy, kind, prev0=prev0)
+    with th.no_grad():
+        batch = runner.run(test_mode=False, **({"prev0": prev0} if kind == "mock" else {}))
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    assert th.equal(td["actions"][..., 0], th.tensor(want["actions"]).to(int_dt))
+    assert th.equal(td["obs"], th.tensor(want["obs"], dtype=real_dt))
+    assert th.equal(td["rewards"], th.tensor(want["rewards"], dtype=real_dt))
+    assert th.equal(td["beta"], th.tensor(want["beta"], dtype=real_dt))
+    assert th.equal(td["terminated"][..., 0], th.tensor(want["terminated"]))
+    assert th.equal(td["filled"][..., 0], th.tensor(want["filled"]))
+    assert int(batch.max_t_filled()) == T + 1
+    np.testing.assert_allclose(runner.last_episode_returns.cpu().numpy(), want["rewards"].sum((1, 2)), rtol=1e-12)
+    # statistics contract (A.6): t_env += B*T, log keys
+    assert runner.t_env == 20000 + B * T
+    rets = want["rewards"].sum((1, 2))
+    assert logger.stats["return_mean"][-1][1] == pytest.approx(np.mean(rets), rel=1e-9)
+    assert logger.stats["return_std"][-1][1] == pytest.approx(np.std(rets), rel=1e-6)
+    assert logger.stats["ep_length_mean"][-1][1] == T
+    assert logger.stats["epsilon"][-1][1] == eps
+    # ReplayBuffer insertion of the returned batch (run.py:262), twice to wrap the ring
+    buffer.insert_episode_batch(batch)
+    buffer.insert_episode_batch(batch)
+    buffer.insert_episode_batch(batch)
+    assert buffer.episodes_in_buffer == 2 * B + 1 and buffer.buffer_index == (3 * B) % (2 * B + 1)
+    assert th.equal(buffer["obs"][B:2 * B].cpu(), td["obs"])
+    assert buffer.can_sample(B)
+
+
+def test_runner_filtered_selector_and_test_mode():
+    """filtered_const_epsilon_greedy + flat_const_agent (filtered_iql.yaml) in greedy test mode."""
+    rng = np.random.default_rng(23)
+    B, n, m, T, L, M, N = 3, 10, 20, 6, 3, 4, 3
+    S = O.gen_dense(rng, B, n, m, T)
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=0.5, sat_prox_mat=S, graphs=1)
+    args = make_args("real_constellation_env", env_args, B, selector="filtered_const_epsilon_greedy", agent="flat_const_agent")
+    runner, mac, buffer, logger = build(args)
+    ut = rng.random((T, B, n, m), dtype=np.float32)
+    draws = {"u_tie": ut, "u_explore": rng.random((T, B, n), dtype=np.float32),
+             "u_action": rng.random((T, B, n), dtype=np.float32)}
+    DrawInjector(mac.action_selector, draws)
+    state = O.RealState(S.astype(np.float64), L, M, N, 0.5)
+
+    def policy(t, pre):
+        x = th.tensor(pre["obs"], dtype=th.float16).float().reshape(B * n, -1).cuda()
+        with th.no_grad():
+            q, _ = mac.agent(x, mac.agent.init_hidden().expand(B * n, -1))
+        q = q.view(B, n, -1).cpu().numpy()
+        top = O.top_m_tasks(pre["beta"], M)
+        return O.select_filtered_epsilon_greedy(q, top, np.ones((B, n, m), bool), m, 0.0, ut[t], draws["u_explore"][t],
+                                                draws["u_action"][t])
+
+    want = O.rollout(state, policy, "real")
+    with th.no_grad():
+        batch = runner.run(test_mode=True)
+    assert th.equal(batch["actions"][..., 0].cpu(), th.tensor(want["actions"]).to(th.int16))
+    assert th.equal(batch["obs"].cpu(), th.tensor(want["obs"], dtype=th.float16))
+    assert runner.t_env == 0  # test episodes do not advance t_env
+    assert "test_return_mean" in logger.stats
+
+
+def test_runner_lazy_fields_and_philox_reproducibility():
+    rng = np.random.default_rng(29)
+    B, n, m, T = 8, 10, 12, 7
+    S = O.gen_ref_like(rng, B, n, m, T)
+    env_args = dict(n=n, m=m, T=T, L=3, lambda_=0.5, sat_prox_mat=S)
+    outs = []
+    for rep in range(2):
+        args = make_args("mock_constellation_env", env_args, B, lazy_buffer_fields=("avail_actions", "actions_onehot"),
+                         epsilon_start=0.5, epsilon_finish=0.5)
+        runner, mac, buffer, logger = build(args)
+        prev0 = np.tile(np.arange(n), (B, 1))
+        with th.no_grad():
+            b1 = runner.run(prev0=prev0)
+            a1 = b1["actions"].clone()
+            b2 = runner.run(prev0=prev0)
+        assert "avail_actions" not in b1.data.transition_data
+        assert not th.equal(a1, b2["actions"])  # a new episode draws new randoms
+        outs.append((a1.cpu(), b2["actions"].cpu()))
+        oh = b2["actions_onehot"]
+        assert oh.shape == (B, T + 1, n, m) and th.equal(oh[:, :T].argmax(-1, keepdim=True), b2["actions"][:, :T])
+    assert th.equal(outs[0][0], outs[1][0]) and th.equal(outs[0][1], outs[1][1])  # same seed -> same rollout
+
+
+def test_product_path_has_no_oracle_import():
+    """The shipped package must not reach into oracle/ (prompt section 3)."""
+    import os
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "marl_sap_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
