@@ -1,0 +1,491 @@
+"""Throughput of the rollout hot path (agent-steps/s) on N B200s, with the step kernel's HBM roofline and the
+CPU port timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c1|tiny] [--impl reference]
+
+A "step" = one full rollout of the hot path over this rank's batch of synthetic environments through the
+reference-facing API: ``runner.run()`` (T timesteps of: torch agent forward -> selection kernel -> fused env
+step/obs/buffer-write kernel) followed by ``ReplayBuffer.insert_episode_batch``.  Prints ONE JSON line on rank 0.
+
+value  : whole-job agent-steps/s with the benefit tensors already resident in HBM.
+e2e    : the same call with that episode's benefit tensors arriving from pinned HOST memory (H2D inside the timed
+         region, overlapped on a copy stream) and the per-env returns / actions / rewards read back to the host.
+roofline: the fused env kernel (sap_real_kernel / sap_mock_kernel); achieved = algorithmic bytes per launch
+          / mean launch duration from CUDA events recorded around every launch in the timed region.
+cpu_baseline / --impl reference: the numpy oracle + the same torch agent on the host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: per-GPU envs, agents, tasks, T, L, M, N, env
+    "c3": dict(B=4096, n=100, m=100, T=100, L=3, M=10, N=10, env="real", desc="4096 envs x 100 agents x 100 tasks per GPU"),
+    "c2": dict(B=1024, n=50, m=50, T=100, L=3, M=10, N=10, env="real", desc="1024 envs x 50 agents x 50 tasks per GPU"),
+    "c4": dict(B=64, n=324, m=450, T=100, L=3, M=10, N=10, env="real", desc="64 envs x 324 agents x 450 tasks per GPU"),
+    "c1": dict(B=1, n=10, m=10, T=100, L=3, M=0, N=0, env="mock", desc="mock env 10 agents x 10 tasks, one env"),
+    "c3mock": dict(B=4096, n=100, m=100, T=100, L=3, M=0, N=0, env="mock", desc="mock env 4096 x 100 x 100 per GPU"),
+    "tiny": dict(B=64, n=20, m=30, T=10, L=3, M=6, N=4, env="real", desc="tiny functional check"),
+}
+
+
+def obs_size(w):
+    if w["env"] == "mock":
+        return (w["L"] + 1) * w["m"]
+    return w["M"] * w["L"] + w["N"] * w["M"] * w["L"] + w["N"] * (w["M"] // 2) * w["L"] + w["M"]
+
+
+def algorithmic_bytes_per_env_step(w, e_obs):
+    """DESIGN.md section 4 / SURVEY.md 8(d): window read + obs write + per-agent scalars."""
+    n, m, L = w["n"], w["m"], w["L"]
+    return n * m * L * 4 + n * obs_size(w) * e_obs + n * 16 + 16
+
+
+# ----------------------------------------------------------------------------------------------- CPU port
+def _agent_numpy_forward(weights, x):
+    import numpy as np
+
+    h = np.maximum(x @ weights["fc1.weight"].T + weights["fc1.bias"], 0)
+    h = np.maximum(h @ weights["rnn.weight"].T + weights["rnn.bias"], 0)
+    return h @ weights["fc2.weight"].T + weights["fc2.bias"]
+
+
+def _cpu_worker(job):
+    """One host core: the oracle env + the same fc agent + oracle selector + buffer writes for `Bc` envs."""
+    import numpy as np
+    import torch as th
+
+    from oracle import cpu_oracle as O
+
+    th.set_num_threads(1)
+    w, Bc, t_steps, seed, weights = job
+    rng = np.random.default_rng(seed)
+    n, m, L = w["n"], w["m"], w["L"]
+    T = min(w["T"], t_steps + L)  # only the planes the sampled timesteps read (per-step work is unchanged)
+    S = rng.random((Bc, n, m, T), dtype=np.float32).astype(np.float64)
+    real = w["env"] == "real"
+    state = O.RealState(S, L, w["M"], w["N"], 0.5) if real else O.MockState(S, L, 0.5)
+    real_dt = np.float16 if real else np.float32
+    osz = obs_size(w)
+    buf_obs = np.zeros((Bc, t_steps + 1, n, osz), dtype=real_dt)
+    buf_rew = np.zeros((Bc, t_steps + 1, n), dtype=real_dt)
+    buf_act = np.zeros((Bc, t_steps + 1, n), dtype=np.int16 if real else np.int64)
+    tw = {k: th.tensor(v) for k, v in weights.items()}
+    t0 = time.perf_counter()
+    if real:
+        state.reset()
+    else:
+        state.reset(np.stack([rng.permutation(m)[:n] for _ in range(Bc)]))
+    avail = np.ones((Bc, n, m), dtype=bool)
+    for t in range(t_steps):
+        pre = state.pretransition()
+        buf_obs[:, t] = pre["obs"]
+        x = th.from_numpy(buf_obs[:, t].astype(np.float32).reshape(Bc * n, -1))
+        h = th.relu(th.nn.functional.linear(x, tw["fc1.weight"], tw["fc1.bias"]))
+        h = th.relu(th.nn.functional.linear(h, tw["rnn.weight"], tw["rnn.bias"]))
+        q = th.nn.functional.linear(h, tw["fc2.weight"], tw["fc2.bias"]).numpy().reshape(Bc, n, m)
+        a = O.select_epsilon_greedy(q, avail, 0.5, rng.random((Bc, n), dtype=np.float32), rng.random((Bc, n), dtype=np.float32))
+        r, done = state.step(a)
+        buf_rew[:, t], buf_act[:, t] = r, a
+    buf_obs[:, t_steps] = state.pretransition()["obs"]
+    return time.perf_counter() - t0, Bc * n * t_steps
+
+
+def cpu_port_throughput(w, weights, target_seconds=12.0, procs=None):
+    """agent-steps/s of the CPU port on `procs` host cores over a bounded sample of the workload."""
+    import multiprocessing as mp
+
+    import psutil
+
+    procs = procs or len(os.sched_getaffinity(0)) or 1
+    # calibrate on one core, one env, two steps
+    dt, steps = _cpu_worker((w, 1, 2, 0, weights))
+    per_env_step = dt / 2
+    t_steps = min(w["T"], 10)
+    Bc = max(1, min(w["B"], int(target_seconds / max(per_env_step * t_steps, 1e-6))))
+    per_env_bytes = w["n"] * w["m"] * (t_steps + w["L"]) * 8 * 4 + w["n"] * obs_size(w) * (t_steps + 1) * 4
+    Bc = max(1, min(Bc, int(0.25 * psutil.virtual_memory().available / procs / per_env_bytes)))
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(w, Bc, t_steps, 100 + i, weights) for i in range(procs)])
+    wall = max(r[0] for r in res)
+    total = sum(r[1] for r in res)
+    sample = f"{procs} procs x {Bc} envs x {t_steps} timesteps of {w['n']}x{w['m']} ({w['env']} env, oracle + fc agent, numpy)"
+    return total / wall, procs, sample, time.perf_counter() - t0
+
+
+def default_agent_weights(w, hidden=64, seed=0):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    d_in, d_out = obs_size(w), w["m"]
+
+    def lin(o, i):
+        bound = 1.0 / np.sqrt(i)
+        return (rng.uniform(-bound, bound, (o, i)).astype(np.float32), rng.uniform(-bound, bound, o).astype(np.float32))
+
+    f1, r1, f2 = lin(hidden, d_in), lin(hidden, hidden), lin(d_out, hidden)
+    return {"fc1.weight": f1[0], "fc1.bias": f1[1], "rnn.weight": r1[0], "rnn.bias": r1[1], "fc2.weight": f2[0],
+            "fc2.bias": f2[1]}
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def build_runner(w, rank_seed, planes):
+    import torch as th
+
+    from marl_sap_b200.components.episode_buffer import ReplayBuffer
+    from marl_sap_b200.controllers import REGISTRY as mac_REGISTRY
+    from marl_sap_b200.runners import REGISTRY as r_REGISTRY
+    from marl_sap_b200.utils.logging import Logger
+
+    real = w["env"] == "real"
+    # the runner adopts the device-resident planes directly; a 1-env placeholder satisfies the env_args contract
+    placeholder = th.zeros(w["n"], w["m"], w["T"])
+    if real:
+        env_args = dict(num_planes=1, num_sats_per_plane=w["n"], m=w["m"], T=w["T"], N=w["N"], M=w["M"], L=w["L"],
+                        lambda_=0.5, sat_prox_mat=placeholder, graphs=1)
+        env_name = "real_constellation_env"
+    else:
+        env_args = dict(n=w["n"], m=w["m"], T=w["T"], L=w["L"], lambda_=0.5, sat_prox_mat=placeholder)
+        env_name = "mock_constellation_env"
+    args = SimpleNamespace(env=env_name, env_args=env_args, batch_size_run=w["B"], device="cuda", runner="parallel",
+                           mac="basic_mac", action_selector="epsilon_greedy", epsilon_start=0.5, epsilon_finish=0.5,
+                           epsilon_anneal_time=1, evaluation_epsilon=0.0, agent="rnn", hidden_dim=64, use_rnn=False,
+                           obs_agent_id=False, obs_last_action=False, agent_output_type="q", test_nepisode=w["B"],
+                           runner_log_interval=10 ** 12, seed=rank_seed, use_mps_action_selection=True,
+                           lazy_buffer_fields=("beta", "avail_actions", "actions_onehot"), reuse_episode_batch=True)
+    logger = Logger()
+    runner = r_REGISTRY["parallel"](args=args, logger=logger)
+    runner.env.set_planes(planes, shared=False)
+    env = runner.get_env()
+    args.n, args.m, args.T = env.n, env.m, env.T
+    groups = {"agents": args.n}
+    buffer = ReplayBuffer(env.scheme, groups, w["B"], env.T + 1, preprocess=env.preprocess, device="cuda",
+                          lazy=args.lazy_buffer_fields)
+    th.manual_seed(0)
+    mac = mac_REGISTRY["basic_mac"](buffer.scheme, groups, args)
+    weights = default_agent_weights(w)
+    mac.agent.load_state_dict({k: th.tensor(v) for k, v in weights.items()})
+    mac.cuda()
+    runner.setup(scheme=env.scheme, groups=groups, preprocess=env.preprocess, mac=mac)
+    return runner, buffer, weights
+
+
+def gpu_arm(opts, w):
+    import torch as th
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    th.cuda.set_device(local_rank)
+    dev = th.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, n, m, T = w["B"], w["n"], w["m"], w["T"]
+
+    # synthetic benefits, U(0,1), distinct per env and per rank, generated straight in the device layout
+    g = th.Generator(device=dev).manual_seed(1234 + rank)
+    planes = th.rand(B, T, n, m, device=dev, generator=g)
+    runner, buffer, weights = build_runner(w, 1 + rank, planes)
+    n_fields = len(buffer.data.transition_data)
+
+    # per-launch event pairs around the fused env kernel
+    ev_pairs = []
+    orig_step = runner.env.step
+
+    def timed_step(actions, batch):
+        if timed_step.enabled:
+            a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig_step(actions, batch)
+            b.record()
+            ev_pairs.append((a, b))
+            return r
+        return orig_step(actions, batch)
+
+    timed_step.enabled = False
+    runner.env.step = timed_step
+
+    def step():
+        with th.no_grad():
+            batch = runner.run(test_mode=False)
+        buffer.insert_episode_batch(batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(opts.warmup):
+        step()
+    launches0 = runner.kernel_launches
+    sampler = ClockSampler(local_rank)
+    barrier()
+    th.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    timed_step.enabled = True
+    wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(opts.steps):
+        step()
+    e1.record()
+    th.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    barrier()
+    timed_step.enabled = False
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(len(ev_pairs), 1)
+    launches = runner.kernel_launches - launches0 + opts.steps * n_fields
+    t = th.tensor([ms, kern_ms], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, kern_ms = t.tolist()
+    agent_steps = world * B * n * T * opts.steps
+    value = agent_steps / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ e2e: host benefits in, host results out
+    e2e = None
+    if not opts.no_e2e:
+        e2e = e2e_leg(opts, w, runner, buffer, planes, dev, rank, world)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    e_obs = 2 if w["env"] == "real" else 4
+    bytes_launch = algorithmic_bytes_per_env_step(w, e_obs) * B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(opts.workload)
+    except Exception:
+        pass
+    cpu = None
+    if not opts.no_cpu:
+        v, cores, sample, _ = cpu_port_throughput(w, weights, target_seconds=opts.cpu_seconds)
+        cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
+    line = {
+        "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": opts.steps,
+        "warmup": opts.warmup, "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{opts.workload}: {w['desc']}, T={T}, L={w['L']}, M={w['M']}, N={w['N']}, {w['env']} env, "
+                               "epsilon_greedy + fc agent(hidden 64)",
+                   "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch",
+                   "inputs": f"benefit planes {planes.numel() * 4 / 2 ** 30:.1f} GiB per GPU (> 126 MB L2), distinct per env",
+                   "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
+                   "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy",
+                   "parallelism": f"envs block-partitioned, {world} rank(s), no data-path collective"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "sap_real_kernel" if w["env"] == "real" else "sap_mock_kernel",
+                     "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": kern_ms, "peak_source": peak_src,
+                     "kernel_share_of_step": kern_ms * T / (ms / opts.steps)},
+        "cpu_baseline": cpu, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_leg(opts, w, runner, buffer, planes, dev, rank, world):
+    """Same step through the public API with HOST inputs/outputs: per episode the benefit tensors of all envs are
+    uploaded from pinned memory in the reference layout [B,n,m,T] (H2D + re-layout, double-buffered on a copy
+    stream so the upload of episode e+1 overlaps the rollout of episode e) and returns/actions/rewards come back."""
+    import psutil
+    import torch as th
+    import torch.distributed as dist
+
+    from marl_sap_b200 import _lib
+
+    B, n, m, T = w["B"], w["n"], w["m"], w["T"]
+    bytes_in = B * n * m * T * 4
+    free_host = psutil.virtual_memory().available
+    free_dev, _ = th.cuda.mem_get_info(dev)
+    if bytes_in * 1.5 > free_host or bytes_in * 1.3 > free_dev:
+        return {"value": None, "unit": "agent-steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 0,
+                "skipped": f"not enough memory (host free {free_host >> 30} GiB, device free {free_dev >> 30} GiB)"}
+    lib = _lib.load()
+    host = th.empty(B, n, m, T, dtype=th.float32, pin_memory=True)
+    chunk = max(1, min(B, (256 << 20) // (n * m * T * 4)))
+    for b0 in range(0, B, chunk):  # fill the pinned buffer with distinct synthetic values
+        b1 = min(B, b0 + chunk)
+        host[b0:b1].copy_(th.rand(b1 - b0, n, m, T, device=dev))
+    planes2 = th.empty_like(planes)
+    staging = [th.empty(chunk * n * m * T, dtype=th.float32, device=dev) for _ in range(2)]
+    copy_stream = th.cuda.Stream(device=dev)
+    ret_host = th.empty(B, dtype=th.float64, pin_memory=True)
+    act_host = th.empty(B, T + 1, n, 1, dtype=runner.env.scheme["actions"]["dtype"], pin_memory=True)
+    rew_host = th.empty(B, T + 1, n, dtype=runner.env.scheme["rewards"]["dtype"], pin_memory=True)
+    bytes_out = ret_host.numel() * 8 + act_host.numel() * act_host.element_size() + rew_host.numel() * rew_host.element_size()
+    bufs = [planes, planes2]
+    ready = [th.cuda.Event(), th.cuda.Event()]
+    consumed = [th.cuda.Event(), th.cuda.Event()]
+
+    def upload(dst, slot):
+        with th.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])  # the rollout that read this buffer has finished
+            for i, b0 in enumerate(range(0, B, chunk)):
+                b1 = min(B, b0 + chunk)
+                _lib.check(lib.sap_benefit_upload_host(host[b0:b1].data_ptr(), staging[i % 2].data_ptr(), dst[b0:b1].data_ptr(),
+                                                       b1 - b0, n, m, T, copy_stream.cuda_stream), "sap_benefit_upload_host")
+            ready[slot].record(copy_stream)
+
+    def e2e_step(i):
+        slot = i % 2
+        th.cuda.current_stream().wait_event(ready[slot])
+        runner.env.set_planes(bufs[slot])
+        upload(bufs[1 - slot], 1 - slot)  # next episode's benefits stream in while this one rolls out
+        with th.no_grad():
+            batch = runner.run(test_mode=False)
+        consumed[slot].record()
+        buffer.insert_episode_batch(batch)
+        ret_host.copy_(runner.last_episode_returns, non_blocking=True)
+        act_host.copy_(batch["actions"], non_blocking=True)
+        rew_host.copy_(batch["rewards"], non_blocking=True)
+
+    consumed[0].record()
+    consumed[1].record()
+    upload(bufs[0], 0)
+    steps = max(2, min(opts.steps, opts.e2e_steps))
+    e2e_step(0)  # warm-up episode (also primes the pipeline)
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(1, steps + 1):
+        e2e_step(i)
+    e1.record()
+    th.cuda.synchronize()
+    ms = th.tensor([e0.elapsed_time(e1)], dtype=th.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    runner.env.set_planes(planes)
+    val = world * B * n * T * steps / (ms.item() * 1e-3)
+    return {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
+            "steps": steps, "ms_per_step": ms.item() / steps,
+            "note": "benefit upload of episode e+1 overlaps the rollout of episode e (copy stream)"}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def reference_arm(opts, w):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    weights = default_agent_weights(w)
+    vals = []
+    for i in range(opts.warmup + opts.steps):
+        v, cores, sample, wall = cpu_port_throughput(w, weights, target_seconds=opts.cpu_seconds / 2)
+        if i >= opts.warmup:
+            vals.append((v, wall))
+    vals.sort()
+    v = vals[len(vals) // 2][0]
+    T = w["T"]
+    line = {"impl": "reference", "metric": "agent_steps_per_sec", "value": v, "unit": "agent-steps/s", "n_gpus": world,
+            "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{opts.workload}: {w['desc']}, T={T}, L={w['L']}, M={w['M']}, N={w['N']}, {w['env']} env, "
+                                   "epsilon_greedy + fc agent(hidden 64)",
+                       "note": "the reference is pure Python and cannot travel to the GPU box; this arm times the numpy "
+                               "oracle port of the same path (env step + obs + selection + agent forward + buffer writes) "
+                               "on all host cores"},
+            "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    opts = ap.parse_args()
+    opts.warmup = max(opts.warmup, 3) if opts.impl == "ours" else max(opts.warmup, 0)
+    w = dict(WORKLOADS[opts.workload])
+    if opts.envs_per_gpu:
+        w["B"] = opts.envs_per_gpu
+        w["desc"] = f"{w['B']} envs x {w['n']} agents x {w['m']} tasks per GPU"
+    if opts.impl == "reference":
+        reference_arm(opts, w)
+    else:
+        gpu_arm(opts, w)
+
+
+if __name__ == "__main__":
+    main()

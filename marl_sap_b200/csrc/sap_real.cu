@@ -8,31 +8,14 @@
 // Arithmetic: every benefit is an fp32 input; beta = S * prio, window sums, rewards are computed in
 // float64 exactly like the reference's numpy, then rounded once to the scheme dtype.  All top-k use the
 // stable total orders of sap_common.cuh, so results equal the reference's on fp32-representable inputs.
-#include "sap_common.cuh"
+#include <stdlib.h>
+
+#include "sap_real.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-
-struct RealParams {
-  SapEnvDims d;
-  const float* planes;   // [B,T,n,m]
-  const float* prios;    // [m] or null
-  const float* ttrans;   // [m,m] or null (default 1 - I)
-  double lambda_;
-  const int64_t* actions;  // [B,n]
-  int32_t* k;
-  int32_t* prev;
-  double* ep_return;
-  int32_t* counts_out;
-  SapBatchView view;
-  int32_t* top_out;
-  double* scratch;  // [B,n,ms] when tot does not fit shared memory
-  int is_reset;
-  int tot_in_smem;
-  int ms;  // row stride of tot (odd -> conflict-free column walks)
-};
 
 struct Smem {
   double* tot;
@@ -75,31 +58,6 @@ __host__ __device__ inline size_t smem_layout(const SapEnvDims& d, int ms, bool 
     s->other = reinterpret_cast<uint16_t*>(base + o_other);
   }
   return off;
-}
-
-// Successive selection of the `count` best of x[0..len) under a stable total order, one warp.
-// Round r picks the best element that ranks strictly after round r-1's winner, so no removal
-// flags are needed.  get(j) returns the float64 key of element j.
-template <typename Get, typename Put>
-__device__ __forceinline__ void warp_select(int len, int count, bool idx_desc, int lane, Get get, Put put) {
-  double lastv = 0.0;
-  int lasti = -1;
-  for (int r = 0; r < count; ++r) {
-    double bv = 0.0;
-    int bi = -1;
-    for (int j = lane; j < len; j += 32) {
-      double v = get(j);
-      if (lasti >= 0 && !sap_better(lastv, lasti, v, j, idx_desc)) continue;  // already taken
-      if (sap_better(v, j, bv, bi, idx_desc)) {
-        bv = v;
-        bi = j;
-      }
-    }
-    sap_warp_argbest(bv, bi, idx_desc);
-    lastv = bv;
-    lasti = bi;
-    if (lane == 0) put(r, bi);
-  }
 }
 
 __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
@@ -330,6 +288,12 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 int launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
+  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: exercise the generic kernel on small shapes
+  if (!(force && force[0] == '1')) {
+    int handled = 0;
+    const int rc = sap_real_fast_try(p, stream, &handled);
+    if (rc != SAP_OK || handled) return rc;
+  }
   p.ms = (d.m & 1) ? d.m : d.m + 1;
   size_t with_tot = smem_layout(d, p.ms, true, nullptr, nullptr);
   p.tot_in_smem = with_tot <= kMaxSmem;

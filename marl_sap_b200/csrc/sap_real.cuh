@@ -1,0 +1,52 @@
+// Parameters shared by the generic (sap_real.cu) and the fast (sap_real_fast.cu) RealConstellationEnv kernels.
+#pragma once
+#include "sap_common.cuh"
+
+struct RealParams {
+  SapEnvDims d;
+  const float* planes;   // [B,T,n,m]
+  const float* prios;    // [m] or null
+  const float* ttrans;   // [m,m] or null (default 1 - I)
+  double lambda_;
+  const int64_t* actions;  // [B,n]
+  int32_t* k;
+  int32_t* prev;
+  double* ep_return;
+  int32_t* counts_out;
+  SapBatchView view;
+  int32_t* top_out;
+  double* scratch;  // [B,n,ms] when tot does not fit shared memory
+  int is_reset;
+  int tot_in_smem;
+  int ms;  // row stride of tot (odd -> conflict-free column walks)
+};
+
+
+// Successive selection of the `count` best of x[0..len) under a stable total order, one warp.
+// Round r picks the best element that ranks strictly after round r-1's winner, so no removal
+// flags are needed.  get(j) returns the float64 key of element j.
+template <typename Get, typename Put>
+__device__ __forceinline__ void warp_select(int len, int count, bool idx_desc, int lane, Get get, Put put) {
+  double lastv = 0.0;
+  int lasti = -1;
+  for (int r = 0; r < count; ++r) {
+    double bv = 0.0;
+    int bi = -1;
+    for (int j = lane; j < len; j += 32) {
+      double v = get(j);
+      if (lasti >= 0 && !sap_better(lastv, lasti, v, j, idx_desc)) continue;  // already taken
+      if (sap_better(v, j, bv, bi, idx_desc)) {
+        bv = v;
+        bi = j;
+      }
+    }
+    sap_warp_argbest(bv, bi, idx_desc);
+    lastv = bv;
+    lasti = bi;
+    if (lane == 0) put(r, bi);
+  }
+}
+
+// Launches the shared-memory-resident fast kernel when the problem fits it.
+// Returns SAP_OK / error like every entry point; *handled = 0 means "not eligible, use the generic kernel".
+int sap_real_fast_try(RealParams& p, void* stream, int* handled);

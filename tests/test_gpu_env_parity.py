@@ -40,8 +40,11 @@ def _cast(x64, dtype):
 @pytest.mark.parametrize("name", REAL)
 @pytest.mark.parametrize("real_dtype", [th.float16, th.float32])
 @pytest.mark.parametrize("shared", [True, False])
-def test_real_env_matches_reference_golden(name, real_dtype, shared):
+@pytest.mark.parametrize("generic", ["0", "1"])
+def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, monkeypatch):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)  # "1": generic kernel, "0": shared-memory fast path
 
     g = _load(name)
     B = 3
@@ -81,16 +84,29 @@ def test_real_env_matches_reference_golden(name, real_dtype, shared):
     dict(B=2, n=100, m=100, T=4, L=3, M=10, N=10, gen="dense", seed=2),
     dict(B=2, n=33, m=47, T=5, L=2, M=6, N=5, gen="ref", seed=3),
     dict(B=2, n=40, m=130, T=3, L=4, M=8, N=3, gen="ref", seed=4),
+    dict(B=3, n=64, m=64, T=4, L=3, M=10, N=10, gen="dup", seed=5),
+    dict(B=2, n=30, m=45, T=4, L=3, M=10, N=10, gen="neg", seed=6),
+    dict(B=2, n=16, m=16, T=3, L=1, M=10, N=10, gen="dense", seed=7),
+    dict(B=2, n=12, m=200, T=3, L=3, M=10, N=10, gen="const", seed=8),
 ])
-def test_real_env_matches_oracle(cfg):
+@pytest.mark.parametrize("generic", ["0", "1"])
+def test_real_env_matches_oracle(cfg, generic, monkeypatch):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
+    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
     rng = np.random.default_rng(cfg["seed"])
     B, n, m, T, L, M, N = (cfg[k] for k in ("B", "n", "m", "T", "L", "M", "N"))
     if cfg["gen"] == "dense":
         S = O.gen_dense(rng, B, n, m, T)
     elif cfg["gen"] == "ties":
         S = (np.round(O.gen_exact(rng, B, n, m, T, zero_frac=0.5) * 4) / 4).astype(np.float32)
+    elif cfg["gen"] == "dup":      # duplicates above the minimum + near-ties one ulp apart: exercises the exact redo path
+        S = (np.round(O.gen_dense(rng, B, n, m, T) * 16) / 16 + 1).astype(np.float32)
+        S[:, ::3] = np.nextafter(S[:, ::3], np.float32(4))
+    elif cfg["gen"] == "neg":      # negative benefits: lo < 0, zeros are not the minimum
+        S = (O.gen_ref_like(rng, B, n, m, T) - np.float32(0.25) * (rng.random((B, n, m, T)) < 0.1)).astype(np.float32)
+    elif cfg["gen"] == "const":    # every window sum identical
+        S = np.full((B, n, m, T), 0.5, dtype=np.float32)
     else:
         S = O.gen_ref_like(rng, B, n, m, T)
     prios = (rng.integers(1, 4, size=m) * 0.5).astype(np.float32) if cfg["seed"] % 2 else None
