@@ -82,6 +82,11 @@ typedef struct SapBatchView {
   SapField prev_assigns;   /* [n]             i64|i16   nullable (real env) */
   SapField beta;           /* real [n,m,L] / mock [n,m]  f32|f16 nullable   */
   SapField avail_actions;  /* [n, m]          u8        nullable (all ones) */
+  /* Not an EpisodeBatch field: the agent network's input staging [B, n, row] f32 (nullable).  The obs of
+   * slot t+1, rounded to the obs dtype and widened back to f32 (what basic_controller.py:82
+   * `batch["obs"][:, t].float()` would produce), is written to columns [0, obs_size) of every agent row.
+   * env_stride = elements between envs, t_stride = elements between agent rows (>= obs_size). */
+  SapField agent_in;
 } SapBatchView;
 
 int sap_abi_version(void);
@@ -97,6 +102,13 @@ int sap_benefit_ingest(const float* src_nmT, float* dst_Tnm, int32_t B, int32_t 
 int sap_benefit_upload_host(const float* src_nmT_host, float* staging_dev, float* dst_Tnm, int32_t B, int32_t n,
                             int32_t m, int32_t T, void* stream);
 
+/* Per-plane range metadata, computed once per episode when the benefits are installed:
+ * stats[b, t] = {min, max} over planes[b, t, :, :].  The real-env kernels use it to scale window sums into
+ * 32-bit selection keys without an extra pass over the window (nullable there: bounds are then derived
+ * inside the kernel with an extra read of the window). */
+int sap_benefit_stats(const float* planes_Tnm, float* stats /*[B,T,2]*/, int32_t B, int32_t n, int32_t m, int32_t T,
+                      void* stream);
+
 /* ---- RealConstellationEnv ---------------------------------------------------------------
  * sap_real_reset  = RealConstellationEnv.reset + get_pretransition_data
  *                   (real_constellation_env.py:116-133, 232-244): k=0, prev=arange(n),
@@ -107,12 +119,15 @@ int sap_benefit_upload_host(const float* src_nmT_host, float* staging_dev, float
  * state:  k[B] int32 in/out, prev[B,n] int32 in/out, ep_return[B] f64 accumulators.
  * top_out [B,n,M] int32 (nullable): agent i's top-M task indices of the NEW observation
  *         (shared with the filtered selector so top-M is computed once).
+ * plane_stats [B or 1, T, 2] from sap_benefit_stats (nullable).
  * scratch: B*n*m doubles, required only when n*m*8 bytes do not fit shared memory. */
-int sap_real_reset(const SapEnvDims* dims, const float* planes, const float* task_prios, int32_t* k, int32_t* prev,
-                   double* ep_return, const SapBatchView* view, int32_t* top_out, double* scratch, void* stream);
-int sap_real_step(const SapEnvDims* dims, const float* planes, const float* task_prios, const float* T_trans,
-                  double lambda_, const int64_t* actions, int32_t* k, int32_t* prev, double* ep_return,
-                  int32_t* counts_out, const SapBatchView* view, int32_t* top_out, double* scratch, void* stream);
+int sap_real_reset(const SapEnvDims* dims, const float* planes, const float* plane_stats, const float* task_prios,
+                   int32_t* k, int32_t* prev, double* ep_return, const SapBatchView* view, int32_t* top_out,
+                   double* scratch, void* stream);
+int sap_real_step(const SapEnvDims* dims, const float* planes, const float* plane_stats, const float* task_prios,
+                  const float* T_trans, double lambda_, const int64_t* actions, int32_t* k, int32_t* prev,
+                  double* ep_return, int32_t* counts_out, const SapBatchView* view, int32_t* top_out, double* scratch,
+                  void* stream);
 /* bytes of dynamic shared memory / scratch doubles the real-env kernels need for these dims */
 int64_t sap_real_scratch_doubles(const SapEnvDims* dims);
 

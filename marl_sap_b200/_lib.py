@@ -37,7 +37,7 @@ class SapField(C.Structure):
 
 
 VIEW_FIELDS = ("obs", "rewards", "actions", "actions_onehot", "terminated", "filled", "prev_assigns", "beta",
-               "avail_actions")
+               "avail_actions", "agent_in")
 
 
 class SapBatchView(C.Structure):
@@ -52,8 +52,9 @@ SIGNATURES = {
     "sap_last_error": (C.c_char_p, []),
     "sap_benefit_ingest": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "sap_benefit_upload_host": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
-    "sap_real_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
-    "sap_real_step": (C.c_int, [_DIMS, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
+    "sap_benefit_stats": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
+    "sap_real_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
+    "sap_real_step": (C.c_int, [_DIMS, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_scratch_doubles": (C.c_int64, [_DIMS]),
     "sap_mock_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _VIEW, _P]),
     "sap_mock_step": (C.c_int, [_DIMS, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P]),

@@ -60,6 +60,8 @@ class _KernelSelectorBase:
         if avail_actions is None:
             return None
         av = avail_actions
+        if av.dim() == 3 and av.stride(0) == 0 and av.stride(1) == 0 and av.stride(2) == 0:
+            return None  # constant all-ones view of a lazy EpisodeBatch: every action available, nothing to read
         if av.dtype == th.bool:
             av = av.contiguous().view(th.uint8)
         elif av.dtype != th.uint8:

@@ -66,6 +66,21 @@ class BasicMAC:
 
     def _build_inputs(self, batch, t):
         bs = batch.batch_size
+        staged = getattr(batch, "agent_in", None)
+        if staged is not None and getattr(batch, "agent_in_t", None) == t:
+            # the env kernel already wrote float(obs[:, t]) into columns [0, obs_size) of the staging rows
+            o = batch.scheme["obs"]["vshape"]
+            o = o if isinstance(o, int) else o[0]
+            if self.args.obs_last_action:
+                m = batch.scheme["actions_onehot"]["vshape"][0]
+                staged[:, :, o:o + m] = 0
+                if t > 0:
+                    staged[:, :, o:o + m].scatter_(2, batch["actions"][:, t - 1].long(), 1.0)
+                o += m
+            if self.args.obs_agent_id and getattr(batch, "agent_in_eye_t", None) is None:
+                staged[:, :, o:o + self.n] = th.eye(self.n, device=staged.device)
+                batch.agent_in_eye_t = True
+            return staged.view(bs * self.n, -1)
         inputs = [batch["obs"][:, t].float()]
         if self.args.obs_last_action:
             if t == 0:

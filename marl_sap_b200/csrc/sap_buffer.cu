@@ -115,6 +115,37 @@ __global__ void __launch_bounds__(kThreads) sap_beta_window_kernel(SapEnvDims d,
   }
 }
 
+// per-plane {min, max}: one CTA per (env, time) plane
+__global__ void __launch_bounds__(kThreads) sap_plane_stats_kernel(const float* __restrict__ planes, float* __restrict__ stats,
+                                                                   int nm) {
+  __shared__ float smin[kThreads / 32], smax[kThreads / 32];
+  const float* p = planes + (size_t)blockIdx.x * nm;
+  float lo = INFINITY, hi = -INFINITY;
+  for (int e = threadIdx.x; e < nm; e += kThreads) {
+    const float v = p[e];
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(SAP_FULL_MASK, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(SAP_FULL_MASK, hi, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smin[threadIdx.x >> 5] = lo;
+    smax[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) {
+      lo = fminf(lo, smin[w]);
+      hi = fmaxf(hi, smax[w]);
+    }
+    stats[2 * (size_t)blockIdx.x] = lo;
+    stats[2 * (size_t)blockIdx.x + 1] = hi;
+  }
+}
+
 inline unsigned grid_for(int64_t work) {
   int64_t blocks = (work + kThreads - 1) / kThreads;
   const int64_t cap = (int64_t)SAP_NUM_SMS * 16;
@@ -135,6 +166,15 @@ extern "C" int sap_benefit_ingest(const float* src_nmT, float* dst_Tnm, int32_t 
   SAP_REQUIRE(grid.y <= 65535, SAP_E_DIMS, "sap_benefit_ingest: n*m too large");
   sap_ingest_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(src_nmT, dst_Tnm, nm, T);
   SAP_CUDA_LAUNCH_CHECK("sap_ingest_kernel");
+  return SAP_OK;
+}
+
+extern "C" int sap_benefit_stats(const float* planes_Tnm, float* stats, int32_t B, int32_t n, int32_t m, int32_t T,
+                                 void* stream) {
+  SAP_REQUIRE(planes_Tnm && stats, SAP_E_NULL, "sap_benefit_stats: planes/stats is null");
+  SAP_REQUIRE(B > 0 && n > 0 && m > 0 && T > 0 && (int64_t)B * T < 2147483647LL, SAP_E_DIMS, "sap_benefit_stats: bad dims");
+  sap_plane_stats_kernel<<<(unsigned)((int64_t)B * T), kThreads, 0, (cudaStream_t)stream>>>(planes_Tnm, stats, n * m);
+  SAP_CUDA_LAUNCH_CHECK("sap_plane_stats_kernel");
   return SAP_OK;
 }
 

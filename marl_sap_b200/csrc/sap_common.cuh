@@ -42,6 +42,10 @@ __device__ __forceinline__ void sap_store_real(void* base, int64_t idx, int dtyp
     reinterpret_cast<float*>(base)[idx] = (float)v;  // cvt.rn.f32.f64
   }
 }
+// the value a buffer field of `dtype` would hold, widened back to f32 (basic_controller.py:82 `.float()`)
+__device__ __forceinline__ float sap_round_real(int dtype, double v) {
+  return dtype == SAP_F16 ? __half2float(__double2half(v)) : (float)v;
+}
 __device__ __forceinline__ void sap_store_int(void* base, int64_t idx, int dtype, int64_t v) {
   switch (dtype) {
     case SAP_I64: reinterpret_cast<int64_t*>(base)[idx] = v; break;

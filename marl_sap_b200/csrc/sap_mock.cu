@@ -27,6 +27,7 @@ struct MockParams {
   SapBatchView view;
   int is_reset;
   int vec4;  // m % 4 == 0, fp32 obs, 16B-aligned bases
+  int ain_vec4;
 };
 
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
@@ -130,6 +131,8 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
       sap_store_real(vw.beta.ptr, bb + e, vw.beta.dtype, k_new < T ? (double)cur[e] : 0.0);
   }
   const int64_t obs_base = sap_field_off(vw.obs, b, t_slot);
+  float* ain = vw.agent_in.ptr ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
+  const int64_t ain_row = vw.agent_in.t_stride;
   if (p.vec4) {
     // obs row i = (L+1) segments of m floats = (L+1)*m/4 float4; all rows of the env are contiguous.
     float* out = reinterpret_cast<float*>(vw.obs.ptr) + obs_base;
@@ -148,6 +151,11 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
         v = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       stg_stream4(reinterpret_cast<float4*>(out) + e, v);
+      if (ain) {
+        float* dst = ain + i * ain_row + (r << 2);
+        if (p.ain_vec4) stg_stream4(reinterpret_cast<float4*>(dst), v);
+        else { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+      }
     }
   } else {
     const int total = n * obs_size;
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
       if (seg == 0) v = (act[i] == j) ? 1.0 : 0.0;                                                   // :107,:147
       else v = (k_new + seg - 1 < T) ? (double)env_planes[((size_t)(k_new + seg - 1) * n + i) * m + j] : 0.0;  // :108-112
       sap_store_real(vw.obs.ptr, obs_base + e, vw.obs.dtype, v);
+      if (ain) ain[i * ain_row + r] = sap_round_real(vw.obs.dtype, v);
     }
   }
 }
@@ -177,6 +186,9 @@ int launch(MockParams& p, void* stream) {
   const SapField& o = p.view.obs;
   p.vec4 = (d.m % 4 == 0) && o.dtype == SAP_F32 && sap_aligned16(o.ptr) && sap_aligned16(p.planes) &&
            (o.env_stride % 4 == 0) && (o.t_stride % 4 == 0);
+  const SapField& ai = p.view.agent_in;
+  p.ain_vec4 = ai.ptr && sap_aligned16(ai.ptr) && (ai.env_stride % 4 == 0) && (ai.t_stride % 4 == 0);
+  SAP_REQUIRE(!ai.ptr || ai.dtype == SAP_F32, SAP_E_DTYPE, "sap_mock: agent_in must be f32");
   size_t bytes = sizeof(int32_t) * (size_t)(d.m + d.n);
   if (bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(sap_mock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

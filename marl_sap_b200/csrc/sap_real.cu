@@ -158,8 +158,13 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
     for (int e = tid; e < n * m; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
   }
   const int64_t obs_base = sap_field_off(vw.obs, b, t_slot);
+  float* ain = vw.agent_in.ptr ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
+  const int64_t ain_row = vw.agent_in.t_stride;
   if (done) {  // :226-228  beta := 0, obs := 0
     for (int e = tid; e < n * obs_size; e += kThreads) sap_store_real(vw.obs.ptr, obs_base + e, vw.obs.dtype, 0.0);
+    if (ain)
+      for (int i = warp; i < n; i += kWarps)
+        for (int c = lane; c < obs_size; c += 32) ain[i * ain_row + c] = 0.f;
     if (vw.beta.ptr) {
       const int64_t bb = sap_field_off(vw.beta, b, t_slot);
       for (int e = tid; e < n * m * L; e += kThreads) sap_store_real(vw.beta.ptr, bb + e, vw.beta.dtype, 0.0);
@@ -251,12 +256,14 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
       for (int l = 0; l < L; ++l) {
         const double v = l < Leff ? (double)win[((size_t)l * n + a) * m + j] * pr : 0.0;
         sap_store_real(vw.obs.ptr, out + (int64_t)pp * L + l, vw.obs.dtype, v);
+        if (ain) ain[i * ain_row + pp * L + l] = sap_round_real(vw.obs.dtype, v);
       }
     }
     const int pv = p.prev[(size_t)b * n + i];
     for (int q = lane; q < M; q += 32) {
       const int j = s.D[i * M + q];
       sap_store_real(vw.obs.ptr, out + (int64_t)npairs * L + q, vw.obs.dtype, j == pv ? 1.0 : 0.0);  // :222
+      if (ain) ain[i * ain_row + npairs * L + q] = j == pv ? 1.f : 0.f;
       if (p.top_out) p.top_out[((size_t)b * n + i) * M + q] = j;
     }
   }
@@ -325,15 +332,16 @@ extern "C" int64_t sap_real_scratch_doubles(const SapEnvDims* d) {
   return (int64_t)d->B * d->n * ms;
 }
 
-extern "C" int sap_real_reset(const SapEnvDims* dims, const float* planes, const float* task_prios, int32_t* k,
-                              int32_t* prev, double* ep_return, const SapBatchView* view, int32_t* top_out,
-                              double* scratch, void* stream) {
+extern "C" int sap_real_reset(const SapEnvDims* dims, const float* planes, const float* plane_stats,
+                              const float* task_prios, int32_t* k, int32_t* prev, double* ep_return,
+                              const SapBatchView* view, int32_t* top_out, double* scratch, void* stream) {
   int rc = validate(dims, view);
   if (rc) return rc;
   SAP_REQUIRE(planes && k && prev && ep_return, SAP_E_NULL, "sap_real_reset: planes/k/prev/ep_return is null");
   RealParams p{};
   p.d = *dims;
   p.planes = planes;
+  p.plane_stats = plane_stats;
   p.prios = task_prios;
   p.k = k;
   p.prev = prev;
@@ -345,10 +353,10 @@ extern "C" int sap_real_reset(const SapEnvDims* dims, const float* planes, const
   return launch(p, stream);
 }
 
-extern "C" int sap_real_step(const SapEnvDims* dims, const float* planes, const float* task_prios, const float* T_trans,
-                             double lambda_, const int64_t* actions, int32_t* k, int32_t* prev, double* ep_return,
-                             int32_t* counts_out, const SapBatchView* view, int32_t* top_out, double* scratch,
-                             void* stream) {
+extern "C" int sap_real_step(const SapEnvDims* dims, const float* planes, const float* plane_stats,
+                             const float* task_prios, const float* T_trans, double lambda_, const int64_t* actions,
+                             int32_t* k, int32_t* prev, double* ep_return, int32_t* counts_out,
+                             const SapBatchView* view, int32_t* top_out, double* scratch, void* stream) {
   int rc = validate(dims, view);
   if (rc) return rc;
   SAP_REQUIRE(planes && k && prev && ep_return && actions, SAP_E_NULL,
@@ -356,6 +364,7 @@ extern "C" int sap_real_step(const SapEnvDims* dims, const float* planes, const 
   RealParams p{};
   p.d = *dims;
   p.planes = planes;
+  p.plane_stats = plane_stats;
   p.prios = task_prios;
   p.ttrans = T_trans;
   p.lambda_ = lambda_;

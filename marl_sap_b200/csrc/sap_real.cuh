@@ -5,6 +5,7 @@
 struct RealParams {
   SapEnvDims d;
   const float* planes;   // [B,T,n,m]
+  const float* plane_stats;  // [B,T,2] per-plane {min,max} or null
   const float* prios;    // [m] or null
   const float* ttrans;   // [m,m] or null (default 1 - I)
   double lambda_;

@@ -3,25 +3,30 @@
 // Same contract and same results as the generic kernel in sap_real.cu (reference:
 // /root/reference/src/envs/real_constellation_env.py step :135-175, beta_hat :282-328, _build_obs :177-230),
 // restructured for throughput:
-//   1. the L-plane benefit window (contiguous in the [B,T,n,m] layout) is pulled into shared memory with one
-//      TMA bulk copy (cp.async.bulk + mbarrier) issued before the reward phase, so the two overlap;
-//   2. every (agent, task) window sum is mapped ONCE to a 32-bit key T' that is monotone in the float64 sum
-//      (fixed point relative to the env's [lo, hi] range; T' = 1 marks "exactly lo", e.g. inactive pairs);
+//   1. ONE pass over the L-plane benefit window (128-bit loads): every (agent, task) pair gets its float64
+//      window sum mapped to a 32-bit selection key, and its benefits are parked in shared memory already
+//      rounded to the observation dtype (fp16 for the reference's real scheme, so the tile is 60 KB at 100x100
+//      and two CTAs share an SM);
+//   2. key = fixed-point image of the float64 sum (scale = power of two chosen from per-plane {min,max}
+//      metadata, so no extra pass) + one "inexact" bit.  The map is monotone, and two equal keys with the bit
+//      clear are PROVEN equal sums;
 //   3. all top-k's (agent's top-M tasks, top-(M+M/2) for the rivals' other tasks, top-N rivals) run as
-//      register-resident sorting networks on packed (T' | index) 32-bit words, TPL threads per list,
+//      register-resident sorting networks on packed (key | index) 32-bit words, TPL threads per list,
 //      partial lists merged with warp shuffles: one VIMNMX pair per compare-exchange;
-//   4. a list is accepted only if it is PROVABLY the exact float64 answer (strictly decreasing T', or ties
-//      inside the certified "== lo" group); otherwise it is queued and redone by the exact float64 warp
-//      selection of the generic kernel.  So results never depend on the 32-bit keys' resolution;
-//   5. observation rows are assembled in shared memory and leave with 128-bit coalesced stores.
+//   4. a list is accepted only if it is PROVABLY the exact float64 answer under the reference's stable tie
+//      rules (strictly decreasing keys, or ties between exact keys); otherwise it is queued and redone by the
+//      exact float64 warp selection.  Results never depend on the key resolution;
+//   5. observation rows are assembled in shared memory and leave with 128-bit coalesced stores, together with
+//      the fp32 copy the agent network reads (agent_in).
 #include "sap_real.cuh"
 #include "sap_sortnet.cuh"
 
 namespace {
 
-constexpr int TPL = 4;            // threads cooperating on one list
-constexpr int kMaxThreads = 512;
-constexpr size_t kMaxSmem = 227 * 1024;
+constexpr int TPL = 2;  // threads cooperating on one list
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr size_t kMaxSmem = 227 * 1024 - 1024;
 
 #define SAP_CE(a, b)            \
   {                             \
@@ -31,40 +36,37 @@ constexpr size_t kMaxSmem = 227 * 1024;
   }
 
 struct FastLayout {
-  size_t tile, k32, D, E, nbr, other, dmask, cnt, prios, red, queue, lut, total;
+  size_t tile, k32, D, E, nbr, other, dmask, cnt, prios, red, queue, total;
   int ms, mw, rows_per_pass;
 };
 
 __host__ __device__ inline size_t up16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-__host__ __device__ inline FastLayout fast_layout(const SapEnvDims& d, int nwarps, int out_esz, bool prios) {
+__host__ __device__ inline FastLayout fast_layout(const SapEnvDims& d, int out_esz, int idx_esz, bool prios) {
   FastLayout f;
   const int H = d.M / 2, K2 = d.M + H;
-  f.ms = d.m + ((4 - (d.m & 7)) & 7);  // ms = 4 (mod 8): TPL = 4 threads x 8 lists of a warp hit 32 distinct banks
+  f.ms = (d.m + 3) & ~3;
   f.mw = (d.m + 31) / 32;
   size_t off = 0;
-  f.tile = off;  off = up16(off + sizeof(float) * (size_t)d.L * d.n * d.m);
+  f.tile = off;  off = up16(off + (size_t)out_esz * d.L * d.n * d.m);
   f.k32 = off;   off = up16(off + sizeof(uint32_t) * (size_t)d.n * f.ms + 16);  // +16: staging alignment shift
-  f.D = off;     off = up16(off + sizeof(uint16_t) * (size_t)d.n * d.M);
-  f.E = off;     off = up16(off + sizeof(uint16_t) * (size_t)d.n * K2);
-  f.nbr = off;   off = up16(off + sizeof(uint16_t) * (size_t)d.n * d.N);
-  f.other = off; off = up16(off + sizeof(uint16_t) * (size_t)d.n * d.N * H);
+  f.D = off;     off = up16(off + (size_t)idx_esz * d.n * d.M);
+  f.E = off;     off = up16(off + (size_t)idx_esz * d.n * K2);
+  f.nbr = off;   off = up16(off + (size_t)idx_esz * d.n * d.N);
+  f.other = off; off = up16(off + (size_t)idx_esz * d.n * d.N * H);
   f.dmask = off; off = up16(off + sizeof(uint32_t) * (size_t)d.n * f.mw);
   f.cnt = off;   off = up16(off + sizeof(int32_t) * (size_t)d.m);
   f.prios = off; off = up16(off + (prios ? sizeof(double) * (size_t)d.m : 0));
-  f.red = off;   off = up16(off + sizeof(double) * 2 * 32 + 64);
+  f.red = off;   off = up16(off + sizeof(double) * 80);
   f.queue = off; off = up16(off + sizeof(int32_t) * (2 * (size_t)d.n + 4));
-  f.lut = off;   off = up16(off + sizeof(uint16_t) * (size_t)(d.M + d.N * d.M + d.N * H));
   f.total = off;
   const size_t row_bytes = (size_t)out_esz * (d.M * d.L + d.N * d.M * d.L + d.N * H * d.L + d.M);
   const size_t stage = sizeof(uint32_t) * (size_t)d.n * f.ms;
   int rpp = (int)(stage / row_bytes);
-  if (rpp > nwarps) rpp = nwarps;
+  if (rpp > kWarps) rpp = kWarps;
   f.rows_per_pass = rpp;
   return f;
 }
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---------------------------------------------------------------------------------------------------------
 // top-16 of a list under the packed order, TPL adjacent lanes per list.  key(e) returns the packed word of
@@ -75,7 +77,7 @@ __device__ __forceinline__ void group_top16(int len, int s, KeyFn key, uint32_t 
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     const int e = s + TPL * c;
-    top[c] = (c < per && e < len) ? key(e) : 0u;
+    top[c] = (e < len) ? key(e) : 0u;
   }
   SAP_SORT16(top);
   for (int base = 16; base < per; base += 16) {
@@ -83,7 +85,7 @@ __device__ __forceinline__ void group_top16(int len, int s, KeyFn key, uint32_t 
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const int e = s + TPL * (base + c);
-      ch[c] = (base + c < per && e < len) ? key(e) : 0u;
+      ch[c] = (e < len) ? key(e) : 0u;
     }
     SAP_SORT16(ch);
 #pragma unroll
@@ -101,14 +103,14 @@ __device__ __forceinline__ void group_top16(int len, int s, KeyFn key, uint32_t 
   }
 }
 
-// A sorted packed list certifies its first `need` entries as the exact float64 answer when every adjacent pair
-// among entries 0..need is strictly decreasing in T' or sits in the "== lo" group (T' == 1); see file header.
+// The first `need` entries of a sorted packed list are the exact float64 answer (value desc, index asc) when every
+// adjacent pair among entries 0..need is strictly decreasing in key, or ties between two EXACT keys (bit 0 clear).
 __device__ __forceinline__ bool certified(const uint32_t (&top)[16], int need, int ib) {
   bool ok = true;
 #pragma unroll
   for (int t = 0; t < 15; ++t) {
     const uint32_t a = top[t] >> ib, b = top[t + 1] >> ib;
-    if (t < need) ok = ok && (a > b || a == 1u);
+    if (t < need) ok = ok && (a > b || (a == b && !(a & 1u)));
   }
   return ok;
 }
@@ -125,36 +127,58 @@ template <>
 __device__ __forceinline__ float to_out_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __half to_out_f<__half>(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float out_to_f(float v) { return v; }
+__device__ __forceinline__ float out_to_f(__half v) { return __half2float(v); }
 
-template <typename OutT, bool kPrios>
-__global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParams p) {
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+template <typename OutT_, typename IdxT_, bool kPrios_, bool kCommon_>
+struct Cfg {
+  using OutT = OutT_;
+  using IdxT = IdxT_;
+  static constexpr bool kPrios = kPrios_;
+  static constexpr bool kCommon = kCommon_;  // M = 10, N = 10, L = 3 known at compile time
+};
+
+template <typename C>
+__global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p) {
+  using OutT = typename C::OutT;
+  using IdxT = typename C::IdxT;
+  constexpr bool kPrios = C::kPrios;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long mbar;
   const SapEnvDims d = p.d;
   const int b = blockIdx.x;
-  const int n = d.n, m = d.m, T = d.T, L = d.L, M = d.M, N = d.N, H = d.M / 2, K2 = d.M + d.M / 2;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarps = blockDim.x >> 5;
+  const int n = d.n, m = d.m, T = d.T;
+  const int L = C::kCommon ? 3 : d.L, M = C::kCommon ? 10 : d.M, N = C::kCommon ? 10 : d.N;
+  const int H = M / 2, K2 = M + H;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nm = n * m;
   const int obs_size = M * L + N * M * L + N * H * L + M;
   const int npairs = M + N * M + N * H;
-  const FastLayout f = fast_layout(d, nwarps, (int)sizeof(OutT), kPrios);
+  const FastLayout f = fast_layout(d, (int)sizeof(OutT), (int)sizeof(IdxT), kPrios);
   const int ms = f.ms, mw = f.mw;
-  float* tile = reinterpret_cast<float*>(smem + f.tile);            // [L][n][m]
-  uint32_t* K32 = reinterpret_cast<uint32_t*>(smem + f.k32);         // [n][ms] keys T'
-  uint16_t* sD = reinterpret_cast<uint16_t*>(smem + f.D);
-  uint16_t* sE = reinterpret_cast<uint16_t*>(smem + f.E);
-  uint16_t* sNbr = reinterpret_cast<uint16_t*>(smem + f.nbr);
-  uint16_t* sOther = reinterpret_cast<uint16_t*>(smem + f.other);
-  uint32_t* sMask = reinterpret_cast<uint32_t*>(smem + f.dmask);
+  OutT* tile = reinterpret_cast<OutT*>(smem + f.tile);              // [L][n][m], already in the obs dtype
+  uint32_t* K32 = reinterpret_cast<uint32_t*>(smem + f.k32);         // [n][ms] selection keys
+  IdxT* sD = reinterpret_cast<IdxT*>(smem + f.D);                    // [n][M]   top-M tasks (value desc, idx asc)
+  IdxT* sE = reinterpret_cast<IdxT*>(smem + f.E);                    // [n][K2]  top-(M+H) tasks (value desc, idx DESC)
+  IdxT* sNbr = reinterpret_cast<IdxT*>(smem + f.nbr);                // [n][N]   rivals
+  IdxT* sOther = reinterpret_cast<IdxT*>(smem + f.other);            // [n][N][H]
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(smem + f.dmask);     // [n][mw] membership bits of D[i]
   int32_t* sCnt = reinterpret_cast<int32_t*>(smem + f.cnt);
   double* sPrio = reinterpret_cast<double*>(smem + f.prios);
-  double* sRed = reinterpret_cast<double*>(smem + f.red);            // [2][32] + scalars
+  double* sRed = reinterpret_cast<double*>(smem + f.red);
   int32_t* sQ = reinterpret_cast<int32_t*>(smem + f.queue);          // [0]=rows count, [1]=nbr count, then ids
-  uint16_t* sLut = reinterpret_cast<uint16_t*>(smem + f.lut);        // pair -> (p << 8 | q)
   int32_t* qRows = sQ + 4;
   int32_t* qNbr = sQ + 4 + n;
 
-  const float* env_planes = p.planes + (d.shared_planes ? (size_t)0 : (size_t)b * T * nm);
+  const size_t env_plane0 = d.shared_planes ? (size_t)0 : (size_t)b * T;
+  const float* env_planes = p.planes + env_plane0 * nm;
   const SapBatchView& vw = p.view;
 
   const int k_old = p.is_reset ? -1 : p.k[b];
@@ -164,49 +188,25 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
   const int Leff = done ? 0 : min(L, T - k_new);
   const float* win = env_planes + (size_t)k_new * nm;
 
-  // ------------------------------------------------------------------ 1. start the window load (TMA bulk copy)
-  const size_t win_bytes = sizeof(float) * (size_t)Leff * nm;
-  // bulk copies need 16-byte sizes and addresses: every plane (n*m floats) must be a multiple of 16 bytes
-  const bool use_tma = !done && ((sizeof(float) * (size_t)nm) % 16 == 0) && ((reinterpret_cast<uintptr_t>(win) & 15) == 0);
   if (tid == 0) {
     sQ[0] = 0;
     sQ[1] = 0;
-    if (use_tma) {
-      const uint32_t bar = smem_u32(&mbar);
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)win_bytes) : "memory");
-      // one copy per plane keeps each request well inside the bulk-copy size limit
-      for (int l = 0; l < Leff; ++l)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(tile + (size_t)l * nm)),
-                     "l"(win + (size_t)l * nm), "r"((uint32_t)(sizeof(float) * nm)), "r"(bar)
-                     : "memory");
-    }
   }
   if (kPrios)
-    for (int j = tid; j < m; j += nthr) sPrio[j] = (double)p.prios[j];
-  for (int j = tid; j < m; j += nthr) sCnt[j] = 0;
-  // pair LUT for the gather phase: pp -> (rival slot p or 0xff for "self", column slot)
-  for (int pp = tid; pp < npairs; pp += nthr) {
-    uint32_t code;
-    if (pp < M) code = (0xffu << 8) | pp;
-    else if (pp < M + N * M) code = (((pp - M) / M) << 8) | ((pp - M) % M);
-    else code = (((pp - M - N * M) / H) << 8) | (0x80u + (pp - M - N * M) % H);
-    sLut[pp] = (uint16_t)code;
-  }
+    for (int j = tid; j < m; j += kThreads) sPrio[j] = (double)p.prios[j];
+  for (int j = tid; j < m; j += kThreads) sCnt[j] = 0;
   __syncthreads();
 
-  // ------------------------------------------------------------------ 2. rewards at the old window (:135-164)
+  // ------------------------------------------------------------------ 1. rewards at the old window (:135-164)
   if (!p.is_reset) {
-    for (int i = tid; i < n; i += nthr) {
+    for (int i = tid; i < n; i += kThreads) {
       int a = (int)p.actions[(size_t)b * n + i];
       a = min(max(a, 0), m - 1);
       atomicAdd(&sCnt[a], 1);
     }
     __syncthreads();
     double local_ret = 0.0;
-    for (int i = tid; i < n; i += nthr) {
+    for (int i = tid; i < n; i += kThreads) {
       int a = (int)p.actions[(size_t)b * n + i];
       a = min(max(a, 0), m - 1);
       const int pv = p.prev[(size_t)b * n + i];
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
     if (lane == 0) sRed[warp] = local_ret;
     if (vw.actions_onehot.ptr) {
       const int64_t base = sap_field_off(vw.actions_onehot, b, k_old);
-      for (int i = warp; i < n; i += nwarps) {
+      for (int i = warp; i < n; i += kWarps) {
         int a = (int)p.actions[(size_t)b * n + i];
         a = min(max(a, 0), m - 1);
         for (int j = lane; j < m; j += 32)
@@ -240,18 +240,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
       }
     }
     if (p.counts_out)
-      for (int j = tid; j < m; j += nthr) p.counts_out[(size_t)b * m + j] = sCnt[j];
+      for (int j = tid; j < m; j += kThreads) p.counts_out[(size_t)b * m + j] = sCnt[j];
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < nwarps; ++w) t += sRed[w];
+      for (int w = 0; w < kWarps; ++w) t += sRed[w];
       p.ep_return[b] += t;
       p.k[b] = k_new;
       if (vw.terminated.ptr)
         sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, done);
     }
   } else {
-    for (int i = tid; i < n; i += nthr) p.prev[(size_t)b * n + i] = i;
+    for (int i = tid; i < n; i += kThreads) p.prev[(size_t)b * n + i] = i;
     if (tid == 0) {
       p.k[b] = 0;
       p.ep_return[b] = 0.0;
@@ -259,109 +259,200 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ 3. pre-transition scalars of slot k_new
+  // ------------------------------------------------------------------ 2. pre-transition scalars of slot k_new
   const int t_slot = k_new;
   if (tid == 0 && vw.filled.ptr) sap_store_int(vw.filled.ptr, sap_field_off(vw.filled, b, t_slot), vw.filled.dtype, 1);
   if (vw.prev_assigns.ptr) {
     const int64_t base = sap_field_off(vw.prev_assigns, b, t_slot);
-    for (int i = tid; i < n; i += nthr)
+    for (int i = tid; i < n; i += kThreads)
       sap_store_int(vw.prev_assigns.ptr, base + i, vw.prev_assigns.dtype, p.prev[(size_t)b * n + i]);
   }
   if (vw.avail_actions.ptr) {
     const int64_t base = sap_field_off(vw.avail_actions, b, t_slot);
-    for (int e = tid; e < nm; e += nthr) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
+    for (int e = tid; e < nm; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
   }
   OutT* obs_out = reinterpret_cast<OutT*>(vw.obs.ptr) + sap_field_off(vw.obs, b, t_slot);
-  if (done) {
-    for (int e = tid; e < n * obs_size; e += nthr) obs_out[e] = to_out_f<OutT>(0.f);
+  float* ain = vw.agent_in.ptr ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
+  const int64_t ain_row = vw.agent_in.t_stride;
+  if (done) {  // :226-228
+    for (int e = tid; e < n * obs_size; e += kThreads) obs_out[e] = to_out_f<OutT>(0.f);
+    if (ain)
+      for (int i = warp; i < n; i += kWarps)
+        for (int c = lane; c < obs_size; c += 32) ain[i * ain_row + c] = 0.f;
     if (vw.beta.ptr) {
       const int64_t bb = sap_field_off(vw.beta, b, t_slot);
-      for (int e = tid; e < nm * L; e += nthr) sap_store_real(vw.beta.ptr, bb + e, vw.beta.dtype, 0.0);
+      for (int e = tid; e < nm * L; e += kThreads) sap_store_real(vw.beta.ptr, bb + e, vw.beta.dtype, 0.0);
     }
     return;
   }
 
-  // ------------------------------------------------------------------ 4. window in shared memory
-  if (use_tma) {
-    const uint32_t bar = smem_u32(&mbar);
-    uint32_t ok = 0;
-    while (!ok) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar)
-          : "memory");
+  // ------------------------------------------------------------------ 3. bounds of the window sums -> key scale
+  {
+    float vmin = INFINITY, vabs = 0.f;  // per thread: min value and sum over planes of max |value|
+    if (p.plane_stats) {
+      if (tid == 0) {
+        for (int l = 0; l < Leff; ++l) {
+          const float lo = p.plane_stats[2 * (env_plane0 + k_new + l)], hi = p.plane_stats[2 * (env_plane0 + k_new + l) + 1];
+          vmin = fminf(vmin, lo);
+          vabs += fmaxf(fabsf(lo), fabsf(hi));
+        }
+        sRed[64] = (double)vmin;
+        sRed[65] = (double)vabs;
+      }
+    } else {  // no metadata: one extra read of the window
+      float amax = 0.f;
+      for (int e = tid; e < Leff * nm; e += kThreads) {
+        const float v = win[e];
+        vmin = fminf(vmin, v);
+        amax = fmaxf(amax, fabsf(v));
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(SAP_FULL_MASK, vmin, off));
+        amax = fmaxf(amax, __shfl_xor_sync(SAP_FULL_MASK, amax, off));
+      }
+      if (lane == 0) {
+        sRed[warp] = (double)vmin;
+        sRed[32 + warp] = (double)amax;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double lo = sRed[0], am = sRed[32];
+        for (int w = 1; w < kWarps; ++w) {
+          lo = fmin(lo, sRed[w]);
+          am = fmax(am, sRed[32 + w]);
+        }
+        sRed[64] = lo;
+        sRed[65] = am * Leff;
+      }
+    }
+    if (tid == 0) {
+      double pabs = 1.0;
+      bool pneg = false;
+      if (kPrios) {
+        pabs = 0.0;
+        for (int j = 0; j < m; ++j) {
+          pabs = fmax(pabs, fabs(sPrio[j]));
+          pneg = pneg || sPrio[j] < 0.0;
+        }
+      }
+      const bool nonneg = sRed[64] >= 0.0 && !pneg;
+      const double hi = sRed[65] * pabs * 1.0000001;  // >= every |window sum| (margin covers fp64 rounding)
+      int e2 = 0;
+      if (hi > 0.0) (void)frexp(hi, &e2);  // hi < 2^e2
+      const int ib0 = 32 - __clz(max(n, m));  // max(n, m) <= 2^ib - 1: index code 0 is never a real element
+      const int vb1 = 31 - ib0;               // bits of the fixed-point part
+      sRed[66] = nonneg ? 0.0 : -ldexp(1.0, e2);                        // origin
+      sRed[67] = hi > 0.0 ? ldexp(1.0, vb1 - e2 - (nonneg ? 0 : 1)) : 1.0;  // scale (power of two)
+      sRed[68] = nonneg ? 1.0 : 0.0;
+    }
+    __syncthreads();
+  }
+  const int ib = 32 - __clz(max(n, m));
+  const uint32_t imask = (1u << ib) - 1u;
+  const uint32_t fixed_max = (1u << (31 - ib)) - 1u;
+  const double k_lo = sRed[66], k_scale = sRed[67];
+  const bool k_nonneg = sRed[68] != 0.0;
+
+  // key of a float64 window sum: monotone; bit 0 = "conversion was not exact"
+  auto make_key = [&](double tot) -> uint32_t {
+    const double y = (tot - k_lo) * k_scale;  // exact when k_lo == 0 (power-of-two scale)
+    uint32_t fx = __double2uint_rz(y);
+    bool inexact = !k_nonneg || ((double)fx != y);
+    if (fx > fixed_max) {
+      fx = fixed_max;
+      inexact = true;
+    }
+    return (fx << 1) | (inexact ? 1u : 0u);
+  };
+
+  // ------------------------------------------------------------------ 4. one pass over the window: keys + rounded tile
+  const bool vec4 = (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(win) & 15) == 0);
+  if (vec4) {
+    const int m4 = m >> 2, total4 = nm >> 2;
+    for (int e4 = tid; e4 < total4; e4 += kThreads) {
+      const int i = e4 / m4, j = (e4 - i * m4) << 2;
+      float4 v[4];  // L <= 4
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < Leff) v[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4 * 4);
+      double tot[4] = {0.0, 0.0, 0.0, 0.0};
+      OutT o[4][4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        if (l < L) {
+          const float x[4] = {l < Leff ? v[l].x : 0.f, l < Leff ? v[l].y : 0.f, l < Leff ? v[l].z : 0.f,
+                              l < Leff ? v[l].w : 0.f};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (kPrios) {
+              const double bv = (double)x[c] * sPrio[j + c];
+              tot[c] += bv;
+              o[l][c] = to_out<OutT>(bv);
+            } else {
+              tot[c] += (double)x[c];
+              o[l][c] = to_out_f<OutT>(x[c]);
+            }
+          }
+        }
+      }
+      uint4 kk;
+      kk.x = make_key(tot[0]);
+      kk.y = make_key(tot[1]);
+      kk.z = make_key(tot[2]);
+      kk.w = make_key(tot[3]);
+      *reinterpret_cast<uint4*>(K32 + i * ms + j) = kk;
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < L) {
+          OutT* dst = tile + (size_t)l * nm + (size_t)e4 * 4;
+          if (sizeof(OutT) == 2) {
+            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(&o[l][0]);
+          } else {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&o[l][0]);
+          }
+        }
     }
   } else {
-    for (int e = tid; e < Leff * nm; e += nthr) tile[e] = win[e];
+    for (int i = warp; i < n; i += kWarps)
+      for (int j = lane; j < m; j += 32) {
+        const double pr = kPrios ? sPrio[j] : 1.0;
+        double tot = 0.0;
+        for (int l = 0; l < L; ++l) {
+          const double bv = l < Leff ? (double)win[(size_t)l * nm + i * m + j] * pr : 0.0;
+          tot += bv;
+          tile[(size_t)l * nm + i * m + j] = to_out<OutT>(bv);
+        }
+        K32[i * ms + j] = make_key(tot);
+      }
   }
-  for (int e = Leff * nm + tid; e < L * nm; e += nthr) tile[e] = 0.f;
+  if (vw.beta.ptr) {  // eager `beta` buffer field (off the hot path: the runners keep it lazy)
+    const int64_t bb = sap_field_off(vw.beta, b, t_slot);
+    for (int i = warp; i < n; i += kWarps)
+      for (int j = lane; j < m; j += 32) {
+        const double pr = kPrios ? sPrio[j] : 1.0;
+        for (int l = 0; l < L; ++l)
+          sap_store_real(vw.beta.ptr, bb + ((int64_t)i * m + j) * L + l, vw.beta.dtype,
+                         l < Leff ? (double)win[(size_t)l * nm + i * m + j] * pr : 0.0);
+      }
+  }
   __syncthreads();
 
-  // float64 window sum of pair (a, j): the reference's beta.sum(-1) (:190)
+  // exact float64 window sum (the reference's beta.sum(-1), :190) straight from global memory: only the rare
+  // lists that cannot be certified use it
   auto tot64 = [&](int a, int j) {
     const double pr = kPrios ? sPrio[j] : 1.0;
     double s = 0.0;
-    for (int l = 0; l < Leff; ++l) s += (double)tile[(size_t)l * nm + a * m + j] * pr;
+    for (int l = 0; l < Leff; ++l) s += (double)win[(size_t)l * nm + a * m + j] * pr;
     return s;
   };
 
-  // ------------------------------------------------------------------ 5. range of the sums, then the 32-bit keys
-  {
-    double lo = INFINITY, hi = -INFINITY;
-    for (int i = warp; i < n; i += nwarps)
-      for (int j = lane; j < m; j += 32) {
-        const double s = tot64(i, j);
-        lo = fmin(lo, s);
-        hi = fmax(hi, s);
-        if (vw.beta.ptr) {
-          const int64_t bb = sap_field_off(vw.beta, b, t_slot) + ((int64_t)i * m + j) * L;
-          const double pr = kPrios ? sPrio[j] : 1.0;
-          for (int l = 0; l < L; ++l)
-            sap_store_real(vw.beta.ptr, bb + l, vw.beta.dtype, l < Leff ? (double)tile[(size_t)l * nm + i * m + j] * pr : 0.0);
-        }
-      }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      lo = fmin(lo, __shfl_xor_sync(SAP_FULL_MASK, lo, off));
-      hi = fmax(hi, __shfl_xor_sync(SAP_FULL_MASK, hi, off));
-    }
-    if (lane == 0) {
-      sRed[warp] = lo;
-      sRed[32 + warp] = hi;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < nwarps; ++w) {
-        lo = fmin(lo, sRed[w]);
-        hi = fmax(hi, sRed[32 + w]);
-      }
-      sRed[64] = lo;
-      sRed[65] = hi;
-    }
-    __syncthreads();
-  }
-  const int ib = 32 - __clz(max(n, m) - 1);  // index bits of the packed words
-  const uint32_t imask = (1u << ib) - 1u;
-  {
-    const double lo = sRed[64], hi = sRed[65];
-    const double span = hi - lo;
-    int e2 = 0;
-    if (span > 0.0) (void)frexp(span, &e2);  // span < 2^e2
-    const double scale = span > 0.0 ? ldexp(1.0, (32 - ib) - 2 - e2) : 0.0;  // (s - lo) * scale < 2^(vb - 2)
-    for (int i = warp; i < n; i += nwarps)
-      for (int j = lane; j < m; j += 32) {
-        const double s = tot64(i, j);
-        K32[i * ms + j] = (s == lo) ? 1u : 2u + __double2uint_rz((s - lo) * scale);
-      }
-  }
-  __syncthreads();
-
-  // ------------------------------------------------------------------ 6. per-agent task lists (:198, :217)
-  for (int base = 0; base < n * TPL; base += nthr) {
+  // ------------------------------------------------------------------ 5. per-agent task lists (:198, :217)
+  for (int base = 0; base < n * TPL; base += kThreads) {
     const int g = base + tid;
-    const int i = g / TPL, s = g % TPL;  // TPL is a power of two
+    const int i = g / TPL, s = g % TPL;
     const bool live = i < n;
+    if (!__any_sync(SAP_FULL_MASK, live)) continue;  // whole warp beyond the last list
     const uint32_t* row = K32 + (live ? i : 0) * ms;
     uint32_t top[16];
     group_top16(live ? m : 0, s, [&](int e) { return (row[e] << ib) | (imask - (uint32_t)e); }, top);
@@ -369,31 +460,64 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
       if (!certified(top, K2, ib)) {
         qRows[atomicAdd(&sQ[0], 1)] = i;
       } else {
+        // D: first M entries as they are (ties are proven ties, already in index-ascending order)
 #pragma unroll
         for (int t = 0; t < 16; ++t)
-          if (t < M) sD[i * M + t] = (uint16_t)(imask - (top[t] & imask));
-        int pfx = 0;
+          if (t < M) sD[i * M + t] = (IdxT)(imask - (top[t] & imask));
+        // E: same values, but ties in index-DESCENDING order and, when the tie group of the K2-th entry extends
+        // past the cut, its LARGEST indices
+        uint32_t kk[16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t)
-          if (t < K2 && (top[t] >> ib) > 1u) {
-            sE[i * K2 + t] = (uint16_t)(imask - (top[t] & imask));
-            pfx = t + 1;
+        for (int t = 0; t < 16; ++t) kk[t] = top[t] >> ib;
+        bool ties = false, ext = false;
+        uint32_t vstar = 0u;
+        int pfx = K2;
+#pragma unroll
+        for (int t = 0; t < 15; ++t) {
+          if (t < K2 - 1) ties = ties || (kk[t] == kk[t + 1]);
+          if (t == K2 - 1) {
+            ext = kk[t] == kk[t + 1];
+            vstar = kk[t];
           }
-        // the "== lo" group under (value desc, idx DESC): largest task indices first
-        for (int j = m - 1; j >= 0 && pfx < K2; --j)
-          if (row[j] == 1u) sE[i * K2 + pfx++] = (uint16_t)j;
+        }
+        if (ext) {
+          pfx = 0;
+#pragma unroll
+          for (int t = 0; t < 16; ++t)
+            if (t < K2 && kk[t] > vstar) pfx = t + 1;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t < pfx) sE[i * K2 + t] = (IdxT)(imask - (top[t] & imask));
+        if (ties) {  // reverse every run of equal keys inside the prefix (rare: duplicate values)
+          int rs = 0;
+          while (rs < pfx) {
+            int re = rs + 1;
+            const uint32_t kv = row[sE[i * K2 + rs]];
+            while (re < pfx && row[sE[i * K2 + re]] == kv) ++re;
+            for (int x = rs, y = re - 1; x < y; ++x, --y) {
+              const IdxT tmp = sE[i * K2 + x];
+              sE[i * K2 + x] = sE[i * K2 + y];
+              sE[i * K2 + y] = tmp;
+            }
+            rs = re;
+          }
+        }
+        if (ext)
+          for (int j = m - 1; j >= 0 && pfx < K2; --j)
+            if (row[j] == vstar) sE[i * K2 + pfx++] = (IdxT)j;
       }
     }
   }
   __syncthreads();
-  // exact float64 redo of the lists that could not be certified (ties / near-ties above lo)
-  for (int qi = warp; qi < sQ[0]; qi += nwarps) {
+  // exact float64 redo of the lists that could not be certified (near-ties, negative benefits)
+  for (int qi = warp; qi < sQ[0]; qi += kWarps) {
     const int i = qRows[qi];
-    warp_select(m, M, false, lane, [&](int j) { return tot64(i, j); }, [&](int r, int j) { sD[i * M + r] = (uint16_t)j; });
-    warp_select(m, K2, true, lane, [&](int j) { return tot64(i, j); }, [&](int r, int j) { sE[i * K2 + r] = (uint16_t)j; });
+    warp_select(m, M, false, lane, [&](int j) { return tot64(i, j); }, [&](int r, int j) { sD[i * M + r] = (IdxT)j; });
+    warp_select(m, K2, true, lane, [&](int j) { return tot64(i, j); }, [&](int r, int j) { sE[i * K2 + r] = (IdxT)j; });
   }
   __syncthreads();
-  for (int i = tid; i < n; i += nthr) {  // membership mask of D[i], used to filter the rivals' lists
+  for (int i = tid; i < n; i += kThreads) {  // membership mask of D[i], used to filter the rivals' lists
     for (int w = 0; w < mw; ++w) sMask[i * mw + w] = 0u;
     for (int q = 0; q < M; ++q) {
       const int j = sD[i * M + q];
@@ -401,14 +525,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
     }
   }
 
-  // ------------------------------------------------------------------ 7. rivals (:203-206)
-  for (int base = 0; base < n * TPL; base += nthr) {
+  // ------------------------------------------------------------------ 6. rivals (:203-206)
+  for (int base = 0; base < n * TPL; base += kThreads) {
     const int g = base + tid;
     const int i = g / TPL, s = g % TPL;
     const bool live = i < n;
+    if (!__any_sync(SAP_FULL_MASK, live)) continue;
     int dcol[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) dcol[q] = (live && q < M) ? sD[i * M + q] : 0;
+    for (int q = 0; q < 16; ++q) dcol[q] = (live && q < M) ? (int)sD[i * M + q] : 0;
     uint32_t top[16];
     group_top16(live ? n : 0, s,
                 [&](int a) {
@@ -426,12 +551,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
       } else {
 #pragma unroll
         for (int t = 0; t < 16; ++t)
-          if (t < N) sNbr[i * N + t] = (uint16_t)(imask - (top[t] & imask));
+          if (t < N) sNbr[i * N + t] = (IdxT)(imask - (top[t] & imask));
       }
     }
   }
   __syncthreads();
-  for (int qi = warp; qi < sQ[1]; qi += nwarps) {
+  for (int qi = warp; qi < sQ[1]; qi += kWarps) {
     const int i = qNbr[qi];
     warp_select(n, N, false, lane,
                 [&](int a) {
@@ -440,28 +565,30 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
                   for (int q = 0; q < M; ++q) best = fmax(best, tot64(a, sD[i * M + q]));
                   return best;
                 },
-                [&](int r, int a) { sNbr[i * N + r] = (uint16_t)a; });
+                [&](int r, int a) { sNbr[i * N + r] = (IdxT)a; });
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ 8. rivals' other top tasks (:212-217)
-  for (int it = tid; it < n * N; it += nthr) {
+  // ------------------------------------------------------------------ 7. rivals' other top tasks (:212-217)
+  // The M/2 best tasks of rival r outside D[i] under (value desc, idx desc) are the first M/2 entries of E[r]
+  // not in D[i]; the reference lists them ascending, so they are stored reversed.
+  for (int it = tid; it < n * N; it += kThreads) {
     const int i = it / N;
     const int r = sNbr[it];
     int c = 0;
     for (int e = 0; e < K2 && c < H; ++e) {
       const int j = sE[r * K2 + e];
       if (!((sMask[i * mw + (j >> 5)] >> (j & 31)) & 1u)) {
-        sOther[(size_t)it * H + (H - 1 - c)] = (uint16_t)j;
+        sOther[(size_t)it * H + (H - 1 - c)] = (IdxT)j;
         ++c;
       }
     }
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ 9. gather rows into shared memory, store 128-bit
-  // The key tile is dead now; it becomes the staging area.  Rows are written at the same 16-byte phase as their
-  // global destination so that the aligned interior can go out as uint4.
+  // ------------------------------------------------------------------ 8. gather rows into shared memory, store 128-bit
+  // The key tile is dead now; it becomes the staging area.  Rows are staged at the same 16-byte phase as their
+  // global destination so the aligned interior goes out as uint4.
   unsigned char* stage = reinterpret_cast<unsigned char*>(K32);
   const size_t row_bytes = sizeof(OutT) * (size_t)obs_size;
   const int rpp = f.rows_per_pass;
@@ -472,17 +599,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
     if (warp < rows) {
       const int i = r0 + warp;
       OutT* srow = reinterpret_cast<OutT*>(stage + phase + (size_t)warp * row_bytes);
-      for (int pp = lane; pp < npairs; pp += 32) {
-        const uint32_t code = sLut[pp];
-        const uint32_t ps = code >> 8, qs = code & 0xffu;
-        const int a = ps == 0xffu ? i : sNbr[i * N + ps];
-        const int j = (qs & 0x80u) ? sOther[((size_t)i * N + ps) * H + (qs & 0x7fu)] : sD[i * M + qs];
-        const float* src = tile + a * m + j;
-        for (int l = 0; l < L; ++l) {
-          if (kPrios) srow[pp * L + l] = to_out<OutT>((double)src[(size_t)l * nm] * sPrio[j]);
-          else srow[pp * L + l] = to_out_f<OutT>(src[(size_t)l * nm]);
-        }
+      // (a) own benefits on the top-M tasks
+      for (int q = lane; q < M; q += 32) {
+        const OutT* src = tile + i * m + sD[i * M + q];
+        for (int l = 0; l < L; ++l) srow[q * L + l] = src[(size_t)l * nm];
       }
+      // (b) rivals' benefits on the same tasks
+      for (int x = lane; x < N * M; x += 32) {
+        const int ps = x / M, q = x - ps * M;
+        const OutT* src = tile + (int)sNbr[i * N + ps] * m + sD[i * M + q];
+        for (int l = 0; l < L; ++l) srow[(M + x) * L + l] = src[(size_t)l * nm];
+      }
+      // (c) rivals' benefits on their other top tasks
+      for (int x = lane; x < N * H; x += 32) {
+        const int ps = x / H;
+        const OutT* src = tile + (int)sNbr[i * N + ps] * m + sOther[(size_t)i * N * H + x];
+        for (int l = 0; l < L; ++l) srow[(M + N * M + x) * L + l] = src[(size_t)l * nm];
+      }
+      // (d) "is my previous task among my top-M" flags (:222)
       const int pv = p.prev[(size_t)b * n + i];
       for (int q = lane; q < M; q += 32) {
         const int j = sD[i * M + q];
@@ -493,33 +627,40 @@ __global__ void __launch_bounds__(kMaxThreads, 1) sap_real_fast_kernel(RealParam
     __syncthreads();
     const size_t bytes = (size_t)rows * row_bytes;
     const unsigned char* ssrc = stage + phase;
-    // head (to the next 16-byte boundary), aligned body, tail; element size divides every boundary
     size_t head = (16 - phase) & 15;
     if (head > bytes) head = bytes;
     const size_t body = (bytes - head) & ~(size_t)15;
-    for (size_t o = tid * sizeof(OutT); o < head; o += nthr * sizeof(OutT))
+    for (size_t o = tid * sizeof(OutT); o < head; o += kThreads * sizeof(OutT))
       *reinterpret_cast<OutT*>(gdst + o) = *reinterpret_cast<const OutT*>(ssrc + o);
-    for (size_t o = head + (size_t)tid * 16; o < head + body; o += (size_t)nthr * 16)
+    for (size_t o = head + (size_t)tid * 16; o < head + body; o += (size_t)kThreads * 16)
       *reinterpret_cast<uint4*>(gdst + o) = *reinterpret_cast<const uint4*>(ssrc + o);
-    for (size_t o = head + body + tid * sizeof(OutT); o < bytes; o += nthr * sizeof(OutT))
+    for (size_t o = head + body + tid * sizeof(OutT); o < bytes; o += kThreads * sizeof(OutT))
       *reinterpret_cast<OutT*>(gdst + o) = *reinterpret_cast<const OutT*>(ssrc + o);
+    if (ain) {  // fp32 copy for the agent network: float(obs rounded to the buffer dtype)
+      for (int r = warp; r < rows; r += kWarps) {
+        const OutT* srow = reinterpret_cast<const OutT*>(ssrc + (size_t)r * row_bytes);
+        float* drow = ain + (int64_t)(r0 + r) * ain_row;
+        for (int c = lane; c < obs_size; c += 32) drow[c] = out_to_f(srow[c]);
+      }
+    }
     __syncthreads();
   }
 }
 
-template <typename OutT, bool kPrios>
-int launch_fast(RealParams& p, void* stream, int threads, size_t bytes) {
+template <typename C>
+int launch_fast(RealParams& p, void* stream, size_t bytes) {
   static thread_local bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sap_real_fast_kernel<OutT, kPrios>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(kMaxSmem - 1024));  // static smem (mbarrier) counts too
+    cudaError_t e = cudaFuncSetAttribute(sap_real_fast_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(sap_real_fast_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) {
       sap_set_error("sap_real_fast: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     configured = true;
   }
-  sap_real_fast_kernel<OutT, kPrios><<<p.d.B, threads, bytes, (cudaStream_t)stream>>>(p);
+  sap_real_fast_kernel<C><<<p.d.B, kThreads, bytes, (cudaStream_t)stream>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_fast_kernel");
   return SAP_OK;
 }
@@ -530,16 +671,27 @@ int sap_real_fast_try(RealParams& p, void* stream, int* handled) {
   *handled = 0;
   const SapEnvDims& d = p.d;
   const int H = d.M / 2;
-  const int out_esz = p.view.obs.dtype == SAP_F16 ? 2 : 4;
-  // eligibility: lists fit the 16-wide networks, indices fit the packed words, tile + keys fit shared memory
-  if (d.M + H + 1 > 16 || d.N + 1 > 16 || d.M > 16) return SAP_OK;
-  if (d.n > 512 || d.m > 512 || d.N >= 0xff || H >= 0x80) return SAP_OK;
-  const int lists = d.n * TPL;
-  const int threads = lists <= 256 ? 256 : 512;
-  const FastLayout f = fast_layout(d, threads / 32, out_esz, p.prios != nullptr);
-  if (f.total + 1024 > kMaxSmem || f.rows_per_pass < 1) return SAP_OK;
+  const bool half_out = p.view.obs.dtype == SAP_F16;
+  // eligibility: lists fit the 16-wide networks, indices fit the packed words, tiles fit shared memory
+  if (d.M + H + 1 > 16 || d.N + 1 > 16 || d.L > 4) return SAP_OK;
+  if (d.n > 511 || d.m > 511) return SAP_OK;
+  const bool common = d.M == 10 && d.N == 10 && d.L == 3 && half_out && !p.prios;
+  const bool idx8 = common && d.n <= 256 && d.m <= 256;
+  const FastLayout f = fast_layout(d, half_out ? 2 : 4, idx8 ? 1 : 2, p.prios != nullptr);
+  if (f.total > kMaxSmem || f.rows_per_pass < 1) return SAP_OK;
+  if (p.view.agent_in.ptr && p.view.agent_in.dtype != SAP_F32) {
+    sap_set_error("sap_real: agent_in must be f32");
+    return SAP_E_DTYPE;
+  }
   *handled = 1;
-  if (out_esz == 2) return p.prios ? launch_fast<__half, true>(p, stream, threads, f.total)
-                                   : launch_fast<__half, false>(p, stream, threads, f.total);
-  return p.prios ? launch_fast<float, true>(p, stream, threads, f.total) : launch_fast<float, false>(p, stream, threads, f.total);
+  if (common) {
+    if (idx8) return launch_fast<Cfg<__half, uint8_t, false, true>>(p, stream, f.total);
+    return launch_fast<Cfg<__half, uint16_t, false, true>>(p, stream, f.total);
+  }
+  if (half_out) {
+    if (p.prios) return launch_fast<Cfg<__half, uint16_t, true, false>>(p, stream, f.total);
+    return launch_fast<Cfg<__half, uint16_t, false, false>>(p, stream, f.total);
+  }
+  if (p.prios) return launch_fast<Cfg<float, uint16_t, true, false>>(p, stream, f.total);
+  return launch_fast<Cfg<float, uint16_t, false, false>>(p, stream, f.total);
 }

@@ -71,6 +71,7 @@ class _BatchedEnvBase:
         if self.T_trans is not None and tuple(self.T_trans.shape) != (m, m):
             raise ValueError(f"T_trans must be [m, m] = [{m}, {m}], got {tuple(self.T_trans.shape)}")
         self.planes = None
+        self.plane_stats = None
         self.shared_planes = False
         self._staging = None
         self.t_host = 0  # host mirror of k (all envs step in lockstep)
@@ -105,14 +106,28 @@ class _BatchedEnvBase:
                                                         self.n, self.m, self.T, stream), "sap_benefit_upload_host")
             self._keepalive = S  # the async copy reads the host buffer until the stream reaches it
         self.shared_planes = shared
+        self._refresh_plane_stats()
         return self
 
-    def set_planes(self, planes, shared=False):
+    def _refresh_plane_stats(self):
+        """Per-plane {min, max} metadata (sap_benefit_stats): lets the real-env kernel scale its selection keys
+        without a second pass over the window.  One pass over the planes per episode."""
+        Bp = self.planes.shape[0]
+        if getattr(self, "plane_stats", None) is None or self.plane_stats.shape[0] != Bp:
+            self.plane_stats = th.empty(Bp, self.T, 2, dtype=th.float32, device=self.device)
+        _lib.check(self.lib.sap_benefit_stats(self.planes.data_ptr(), self.plane_stats.data_ptr(), Bp, self.n, self.m,
+                                              self.T, _lib.stream_ptr(self.device)), "sap_benefit_stats")
+
+    def set_planes(self, planes, shared=False, stats=None):
         """Adopt an already device-laid-out tensor [B or 1, T, n, m] (no copy)."""
         _lib.require_cuda(planes, "planes")
         assert planes.dtype == th.float32 and planes.is_contiguous()
         assert tuple(planes.shape[1:]) == (self.T, self.n, self.m)
         self.planes, self.shared_planes = planes, bool(shared)
+        if stats is not None:
+            self.plane_stats = stats
+        else:
+            self._refresh_plane_stats()
         return self
 
     def dims(self):
@@ -158,15 +173,17 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
     def reset(self, batch):
         self._check_batch(batch)
         view = batch.kernel_view()
-        _lib.check(self.lib.sap_real_reset(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios), _lib.ptr(self.k),
-                                           _lib.ptr(self.prev), _lib.ptr(self.ep_return), view, _lib.ptr(self.top),
-                                           _lib.ptr(self.scratch), _lib.stream_ptr(self.device)), "sap_real_reset")
+        _lib.check(self.lib.sap_real_reset(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
+                                           _lib.ptr(self.task_prios), _lib.ptr(self.k), _lib.ptr(self.prev),
+                                           _lib.ptr(self.ep_return), view, _lib.ptr(self.top), _lib.ptr(self.scratch),
+                                           _lib.stream_ptr(self.device)), "sap_real_reset")
         self.t_host = 0
 
     def step(self, actions, batch):
         actions = self._check_actions(actions)
         view = batch.kernel_view()
-        _lib.check(self.lib.sap_real_step(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios),
+        _lib.check(self.lib.sap_real_step(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
+                                          _lib.ptr(self.task_prios),
                                           _lib.ptr(self.T_trans), self.lambda_, actions.data_ptr(), _lib.ptr(self.k),
                                           _lib.ptr(self.prev), _lib.ptr(self.ep_return), _lib.ptr(self.counts), view,
                                           _lib.ptr(self.top), _lib.ptr(self.scratch), _lib.stream_ptr(self.device)),

@@ -103,6 +103,14 @@ class CudaVecRunner:
         self.mac.action_selector.envs = [self.get_env()]
         if hasattr(self.mac.action_selector, "bind_counters"):
             self.mac.action_selector.bind_counters(self.episode_ctr, self.env.k)
+        # fp32 staging of the agent network's input: the env kernel writes float(obs) of the new slot into it, so
+        # the per-step `batch["obs"][:, t].float()` conversion of basic_controller.py:82 disappears
+        self.agent_in = None
+        if getattr(self.args, "stage_agent_inputs", True) and hasattr(mac, "_build_inputs"):
+            row = self.env.obs_size
+            row += self.env.m if getattr(self.args, "obs_last_action", False) else 0
+            row += self.env.n if getattr(self.args, "obs_agent_id", False) else 0
+            self.agent_in = th.zeros(self.batch_size, self.env.n, row, dtype=th.float32, device=self.device)
 
     def get_env(self):
         return _EnvInfo(self.env)
@@ -129,7 +137,9 @@ class CudaVecRunner:
             self.batch.set_lazy_provider("beta", lambda _b, env=self.env, dtype=dtype: env.beta_field(dtype))
         if self.env.kind == "real":
             self.batch.top_agent_tasks = self.env.top
+        self.batch.agent_in = getattr(self, "agent_in", None)
         self.env.reset(self.batch, **reset_kwargs)
+        self.batch.agent_in_t = 0
         self.kernel_launches += 1
         self.t = 0
 
@@ -141,6 +151,7 @@ class CudaVecRunner:
             actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
             # fused env kernel: rewards/actions/terminated at slot t, obs/prev_assigns/filled at slot t+1
             self.env.step(actions, self.batch)
+            self.batch.agent_in_t = t + 1
             self.kernel_launches += 2
             self.t += 1
         self.episode_ctr += 1
