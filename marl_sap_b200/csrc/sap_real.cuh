@@ -18,6 +18,7 @@ struct RealParams {
   int32_t* top_out;
   double* scratch;  // [B,n,ms] when tot does not fit shared memory
   int is_reset;
+  int debug_skip_redo;  // timing experiments only (SAP_DEBUG_SKIP_REDO=1): accept uncertified lists
   int tot_in_smem;
   int ms;  // row stride of tot (odd -> conflict-free column walks)
 };
@@ -39,6 +40,34 @@ __device__ __forceinline__ void warp_select(int len, int count, bool idx_desc, i
       if (sap_better(v, j, bv, bi, idx_desc)) {
         bv = v;
         bi = j;
+      }
+    }
+    sap_warp_argbest(bv, bi, idx_desc);
+    lastv = bv;
+    lasti = bi;
+    if (lane == 0) put(r, bi);
+  }
+}
+
+// Same selection on values cached in registers: lane holds elements lane, lane + 32, ... (at most 16 of them).
+template <typename Put>
+__device__ __forceinline__ void warp_select_cached(int len, int count, bool idx_desc, int lane, const double (&vals)[16],
+                                                   Put put) {
+  double lastv = 0.0;
+  int lasti = -1;
+  for (int r = 0; r < count; ++r) {
+    double bv = 0.0;
+    int bi = -1;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int j = lane + 32 * c;
+      if (j < len) {
+        const double v = vals[c];
+        const bool taken = lasti >= 0 && !sap_better(lastv, lasti, v, j, idx_desc);
+        if (!taken && sap_better(v, j, bv, bi, idx_desc)) {
+          bv = v;
+          bi = j;
+        }
       }
     }
     sap_warp_argbest(bv, bi, idx_desc);

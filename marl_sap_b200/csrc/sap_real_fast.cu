@@ -36,7 +36,7 @@ constexpr size_t kMaxSmem = 227 * 1024 - 1024;
   }
 
 struct FastLayout {
-  size_t tile, k32, D, E, nbr, other, dmask, cnt, prios, red, queue, total;
+  size_t tile, k32, D, E, nbr, other, dmask, cnt, prios, red, queue, lut, total;
   int ms, mw, rows_per_pass;
 };
 
@@ -59,6 +59,7 @@ __host__ __device__ inline FastLayout fast_layout(const SapEnvDims& d, int out_e
   f.prios = off; off = up16(off + (prios ? sizeof(double) * (size_t)d.m : 0));
   f.red = off;   off = up16(off + sizeof(double) * 80);
   f.queue = off; off = up16(off + sizeof(int32_t) * (2 * (size_t)d.n + 4));
+  f.lut = off;   off = up16(off + sizeof(uint16_t) * (size_t)(d.M + d.N * d.M + d.N * H));
   f.total = off;
   const size_t row_bytes = (size_t)out_esz * (d.M * d.L + d.N * d.M * d.L + d.N * H * d.L + d.M);
   const size_t stage = sizeof(uint32_t) * (size_t)d.n * f.ms;
@@ -147,13 +148,11 @@ struct Cfg {
 };
 
 template <typename C>
-__global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p) {
+__device__ __forceinline__ void process_env(const RealParams& p, const int b, unsigned char* smem) {
   using OutT = typename C::OutT;
   using IdxT = typename C::IdxT;
   constexpr bool kPrios = C::kPrios;
-  extern __shared__ __align__(128) unsigned char smem[];
   const SapEnvDims d = p.d;
-  const int b = blockIdx.x;
   const int n = d.n, m = d.m, T = d.T;
   const int L = C::kCommon ? 3 : d.L, M = C::kCommon ? 10 : d.M, N = C::kCommon ? 10 : d.N;
   const int H = M / 2, K2 = M + H;
@@ -174,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
   double* sPrio = reinterpret_cast<double*>(smem + f.prios);
   double* sRed = reinterpret_cast<double*>(smem + f.red);
   int32_t* sQ = reinterpret_cast<int32_t*>(smem + f.queue);          // [0]=rows count, [1]=nbr count, then ids
+  uint16_t* sLut = reinterpret_cast<uint16_t*>(smem + f.lut);        // output pair -> (rival slot << 8 | column slot)
   int32_t* qRows = sQ + 4;
   int32_t* qNbr = sQ + 4 + n;
 
@@ -195,6 +195,13 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
   if (kPrios)
     for (int j = tid; j < m; j += kThreads) sPrio[j] = (double)p.prios[j];
   for (int j = tid; j < m; j += kThreads) sCnt[j] = 0;
+  for (int pp = tid; pp < npairs; pp += kThreads) {  // obs layout (:225): own | rivals on my tasks | rivals' other tasks
+    uint32_t code;
+    if (pp < M) code = (0xffu << 8) | pp;
+    else if (pp < M + N * M) code = (((pp - M) / M) << 8) | ((pp - M) % M);
+    else code = (((pp - M - N * M) / H) << 8) | (0x80u + (pp - M - N * M));
+    sLut[pp] = (uint16_t)code;
+  }
   __syncthreads();
 
   // ------------------------------------------------------------------ 1. rewards at the old window (:135-164)
@@ -370,12 +377,8 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
   const bool vec4 = (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(win) & 15) == 0);
   if (vec4) {
     const int m4 = m >> 2, total4 = nm >> 2;
-    for (int e4 = tid; e4 < total4; e4 += kThreads) {
-      const int i = e4 / m4, j = (e4 - i * m4) << 2;
-      float4 v[4];  // L <= 4
-#pragma unroll
-      for (int l = 0; l < 4; ++l)
-        if (l < Leff) v[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4 * 4);
+    // 4 adjacent tasks of one agent: L float4 in, 4 keys + L x 4 rounded benefits out
+    auto finish = [&](int e4, int i, int j, const float4 (&v)[4]) {
       double tot[4] = {0.0, 0.0, 0.0, 0.0};
       OutT o[4][4];
 #pragma unroll
@@ -412,6 +415,33 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&o[l][0]);
           }
         }
+    };
+    // (i, j/4) advance incrementally: no division in the loop; two groups per iteration keep 2L loads in flight
+    const int step_i = kThreads / m4, step_j = kThreads - step_i * m4;
+    int i0 = tid / m4, j0 = tid - i0 * m4;
+    for (int e4 = tid; e4 < total4; e4 += 2 * kThreads) {
+      int i1 = i0 + step_i, j1 = j0 + step_j;
+      if (j1 >= m4) {
+        j1 -= m4;
+        ++i1;
+      }
+      const int e4b = e4 + kThreads;
+      const bool has_b = e4b < total4;
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < Leff) va[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4 * 4);
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < Leff && has_b) vb[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4b * 4);
+      finish(e4, i0, j0 << 2, va);
+      if (has_b) finish(e4b, i1, j1 << 2, vb);
+      i0 = i1 + step_i;
+      j0 = j1 + step_j;
+      if (j0 >= m4) {
+        j0 -= m4;
+        ++i0;
+      }
     }
   } else {
     for (int i = warp; i < n; i += kWarps)
@@ -457,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
     uint32_t top[16];
     group_top16(live ? m : 0, s, [&](int e) { return (row[e] << ib) | (imask - (uint32_t)e); }, top);
     if (live && s == 0) {
-      if (!certified(top, K2, ib)) {
+      if (!certified(top, K2, ib) && !p.debug_skip_redo) {
         qRows[atomicAdd(&sQ[0], 1)] = i;
       } else {
         // D: first M entries as they are (ties are proven ties, already in index-ascending order)
@@ -513,8 +543,11 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
   // exact float64 redo of the lists that could not be certified (near-ties, negative benefits)
   for (int qi = warp; qi < sQ[0]; qi += kWarps) {
     const int i = qRows[qi];
-    warp_select(m, M, false, lane, [&](int j) { return tot64(i, j); }, [&](int r, int j) { sD[i * M + r] = (IdxT)j; });
-    warp_select(m, K2, true, lane, [&](int j) { return tot64(i, j); }, [&](int r, int j) { sE[i * K2 + r] = (IdxT)j; });
+    double vals[16];  // this lane's window sums (m <= 511 -> at most 16 per lane), fetched once from L2
+#pragma unroll
+    for (int c = 0; c < 16; ++c) vals[c] = (lane + 32 * c < m) ? tot64(i, lane + 32 * c) : 0.0;
+    warp_select_cached(m, M, false, lane, vals, [&](int r, int j) { sD[i * M + r] = (IdxT)j; });
+    warp_select_cached(m, K2, true, lane, vals, [&](int r, int j) { sE[i * K2 + r] = (IdxT)j; });
   }
   __syncthreads();
   for (int i = tid; i < n; i += kThreads) {  // membership mask of D[i], used to filter the rivals' lists
@@ -546,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
                 },
                 top);
     if (live && s == 0) {
-      if (!certified(top, N, ib)) {
+      if (!certified(top, N, ib) && !p.debug_skip_redo) {
         qNbr[atomicAdd(&sQ[1], 1)] = i;
       } else {
 #pragma unroll
@@ -558,14 +591,16 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
   __syncthreads();
   for (int qi = warp; qi < sQ[1]; qi += kWarps) {
     const int i = qNbr[qi];
-    warp_select(n, N, false, lane,
-                [&](int a) {
-                  if (a == i) return (double)-INFINITY;
-                  double best = -INFINITY;
-                  for (int q = 0; q < M; ++q) best = fmax(best, tot64(a, sD[i * M + q]));
-                  return best;
-                },
-                [&](int r, int a) { sNbr[i * N + r] = (IdxT)a; });
+    // exact scores once into scratch (the key tile is dead after the barrier above), then the exact selection
+    double* sc = reinterpret_cast<double*>(K32) + (size_t)warp * n;
+    for (int a = lane; a < n; a += 32) {
+      double best = -INFINITY;
+      for (int q = 0; q < M; ++q) best = fmax(best, tot64(a, sD[i * M + q]));
+      sc[a] = (a == i) ? -INFINITY : best;
+    }
+    __syncwarp();
+    warp_select(n, N, false, lane, [&](int a) { return sc[a]; }, [&](int r, int a) { sNbr[i * N + r] = (IdxT)a; });
+    __syncwarp();
   }
   __syncthreads();
 
@@ -592,6 +627,7 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
   unsigned char* stage = reinterpret_cast<unsigned char*>(K32);
   const size_t row_bytes = sizeof(OutT) * (size_t)obs_size;
   const int rpp = f.rows_per_pass;
+  const bool ain_flat = ain && ain_row == obs_size && ((reinterpret_cast<uintptr_t>(ain) & 15) == 0);
   for (int r0 = 0; r0 < n; r0 += rpp) {
     const int rows = min(rpp, n - r0);
     unsigned char* gdst = reinterpret_cast<unsigned char*>(obs_out) + (size_t)r0 * row_bytes;
@@ -599,27 +635,50 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
     if (warp < rows) {
       const int i = r0 + warp;
       OutT* srow = reinterpret_cast<OutT*>(stage + phase + (size_t)warp * row_bytes);
-      // (a) own benefits on the top-M tasks
-      for (int q = lane; q < M; q += 32) {
-        const OutT* src = tile + i * m + sD[i * M + q];
-        for (int l = 0; l < L; ++l) srow[q * L + l] = src[(size_t)l * nm];
+      const IdxT* myD = sD + i * M;
+      const IdxT* myN = sNbr + i * N;
+      const IdxT* myO = sOther + (size_t)i * N * H;
+      // one pair (agent a, task j) per lane and slot: L benefits each.  Branch-free decode through the LUT; kGB
+      // independent pairs per lane are loaded before any is stored so their shared-memory latencies overlap.
+      constexpr int kGB = 5;
+      for (int pp0 = lane; pp0 < npairs; pp0 += 32 * kGB) {
+        uint32_t code[kGB];
+#pragma unroll
+        for (int g = 0; g < kGB; ++g) code[g] = (pp0 + 32 * g < npairs) ? (uint32_t)sLut[pp0 + 32 * g] : 0xff00u;
+        int a_r[kGB], j_d[kGB], j_o[kGB];
+#pragma unroll
+        for (int g = 0; g < kGB; ++g) {
+          const uint32_t ps = code[g] >> 8, qs = code[g] & 0xffu;
+          a_r[g] = myN[min(ps, (uint32_t)(N - 1))];
+          j_d[g] = myD[min(qs, (uint32_t)(M - 1))];
+          j_o[g] = myO[min(qs & 0x7fu, (uint32_t)(N * H - 1))];
+        }
+        OutT val[kGB][4];
+#pragma unroll
+        for (int g = 0; g < kGB; ++g) {
+          const uint32_t ps = code[g] >> 8, qs = code[g] & 0xffu;
+          const int a = ps == 0xffu ? i : a_r[g];
+          const int j = (qs & 0x80u) ? j_o[g] : j_d[g];
+          const OutT* src = tile + a * m + j;
+#pragma unroll
+          for (int l = 0; l < 4; ++l)
+            if (l < L) val[g][l] = src[(size_t)l * nm];
+        }
+#pragma unroll
+        for (int g = 0; g < kGB; ++g) {
+          const int pp = pp0 + 32 * g;
+          if (pp < npairs) {
+            OutT* dst = srow + pp * L;
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+              if (l < L) dst[l] = val[g][l];
+          }
+        }
       }
-      // (b) rivals' benefits on the same tasks
-      for (int x = lane; x < N * M; x += 32) {
-        const int ps = x / M, q = x - ps * M;
-        const OutT* src = tile + (int)sNbr[i * N + ps] * m + sD[i * M + q];
-        for (int l = 0; l < L; ++l) srow[(M + x) * L + l] = src[(size_t)l * nm];
-      }
-      // (c) rivals' benefits on their other top tasks
-      for (int x = lane; x < N * H; x += 32) {
-        const int ps = x / H;
-        const OutT* src = tile + (int)sNbr[i * N + ps] * m + sOther[(size_t)i * N * H + x];
-        for (int l = 0; l < L; ++l) srow[(M + N * M + x) * L + l] = src[(size_t)l * nm];
-      }
-      // (d) "is my previous task among my top-M" flags (:222)
+      // "is my previous task among my top-M" flags (:222)
       const int pv = p.prev[(size_t)b * n + i];
       for (int q = lane; q < M; q += 32) {
-        const int j = sD[i * M + q];
+        const int j = myD[q];
         srow[npairs * L + q] = to_out_f<OutT>(j == pv ? 1.f : 0.f);
         if (p.top_out) p.top_out[((size_t)b * n + i) * M + q] = j;
       }
@@ -627,24 +686,55 @@ __global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p
     __syncthreads();
     const size_t bytes = (size_t)rows * row_bytes;
     const unsigned char* ssrc = stage + phase;
-    size_t head = (16 - phase) & 15;
-    if (head > bytes) head = bytes;
-    const size_t body = (bytes - head) & ~(size_t)15;
-    for (size_t o = tid * sizeof(OutT); o < head; o += kThreads * sizeof(OutT))
-      *reinterpret_cast<OutT*>(gdst + o) = *reinterpret_cast<const OutT*>(ssrc + o);
-    for (size_t o = head + (size_t)tid * 16; o < head + body; o += (size_t)kThreads * 16)
-      *reinterpret_cast<uint4*>(gdst + o) = *reinterpret_cast<const uint4*>(ssrc + o);
-    for (size_t o = head + body + tid * sizeof(OutT); o < bytes; o += kThreads * sizeof(OutT))
-      *reinterpret_cast<OutT*>(gdst + o) = *reinterpret_cast<const OutT*>(ssrc + o);
-    if (ain) {  // fp32 copy for the agent network: float(obs rounded to the buffer dtype)
-      for (int r = warp; r < rows; r += kWarps) {
-        const OutT* srow = reinterpret_cast<const OutT*>(ssrc + (size_t)r * row_bytes);
-        float* drow = ain + (int64_t)(r0 + r) * ain_row;
-        for (int c = lane; c < obs_size; c += 32) drow[c] = out_to_f(srow[c]);
+    if (phase == 0 && (bytes & 15) == 0 && (!ain || ain_flat)) {
+      // aligned block: 16 bytes per thread and iteration to the obs slot, plus its fp32 image for the agent network
+      float* adst = ain ? ain + (size_t)r0 * obs_size : nullptr;  // rows are contiguous when ain_row == obs_size
+      const int chunks = (int)(bytes >> 4);
+#pragma unroll 4
+      for (int c = tid; c < chunks; c += kThreads) {
+        const uint4 v = *reinterpret_cast<const uint4*>(ssrc + (size_t)c * 16);
+        *reinterpret_cast<uint4*>(gdst + (size_t)c * 16) = v;
+        if (adst) {
+          if (sizeof(OutT) == 2) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v);
+            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
+                         f3 = __half22float2(h[3]);
+            float4* o = reinterpret_cast<float4*>(adst + (size_t)c * 8);
+            o[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+            o[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+          } else {
+            *reinterpret_cast<uint4*>(adst + (size_t)c * 4) = v;
+          }
+        }
+      }
+    } else {
+      size_t head = (16 - phase) & 15;
+      if (head > bytes) head = bytes;
+      const size_t body = (bytes - head) & ~(size_t)15;
+      for (size_t o = tid * sizeof(OutT); o < head; o += kThreads * sizeof(OutT))
+        *reinterpret_cast<OutT*>(gdst + o) = *reinterpret_cast<const OutT*>(ssrc + o);
+      for (size_t o = head + (size_t)tid * 16; o < head + body; o += (size_t)kThreads * 16)
+        *reinterpret_cast<uint4*>(gdst + o) = *reinterpret_cast<const uint4*>(ssrc + o);
+      for (size_t o = head + body + tid * sizeof(OutT); o < bytes; o += kThreads * sizeof(OutT))
+        *reinterpret_cast<OutT*>(gdst + o) = *reinterpret_cast<const OutT*>(ssrc + o);
+      if (ain) {  // fp32 copy for the agent network: float(obs rounded to the buffer dtype)
+        for (int r = warp; r < rows; r += kWarps) {
+          const OutT* srow = reinterpret_cast<const OutT*>(ssrc + (size_t)r * row_bytes);
+          float* drow = ain + (int64_t)(r0 + r) * ain_row;
+          for (int c = lane; c < obs_size; c += 32) drow[c] = out_to_f(srow[c]);
+        }
       }
     }
     __syncthreads();
   }
+}
+
+// One CTA per environment; the hardware block scheduler balances the (slightly uneven) per-env durations better
+// than a static persistent partition did (measured: 0.95 ms vs 1.18 ms at 4096 x 100 x 100).
+template <typename C>
+__global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  process_env<C>(p, blockIdx.x, smem);
 }
 
 template <typename C>
@@ -674,11 +764,11 @@ int sap_real_fast_try(RealParams& p, void* stream, int* handled) {
   const bool half_out = p.view.obs.dtype == SAP_F16;
   // eligibility: lists fit the 16-wide networks, indices fit the packed words, tiles fit shared memory
   if (d.M + H + 1 > 16 || d.N + 1 > 16 || d.L > 4) return SAP_OK;
-  if (d.n > 511 || d.m > 511) return SAP_OK;
+  if (d.n > 511 || d.m > 511 || d.N * H > 127) return SAP_OK;
   const bool common = d.M == 10 && d.N == 10 && d.L == 3 && half_out && !p.prios;
   const bool idx8 = common && d.n <= 256 && d.m <= 256;
   const FastLayout f = fast_layout(d, half_out ? 2 : 4, idx8 ? 1 : 2, p.prios != nullptr);
-  if (f.total > kMaxSmem || f.rows_per_pass < 1) return SAP_OK;
+  if (f.total > kMaxSmem || f.rows_per_pass < 1 || f.ms * 4 < kWarps * 8) return SAP_OK;
   if (p.view.agent_in.ptr && p.view.agent_in.dtype != SAP_F32) {
     sap_set_error("sap_real: agent_in must be f32");
     return SAP_E_DTYPE;

@@ -60,6 +60,93 @@ struct SelParams {
   int64_t* out;
 };
 
+// Classic epsilon-greedy, batched 32 rows per warp: lane r draws the Philox uniforms of row (base + r) once, then
+// the warp walks the 32 rows, each a 128-bit coalesced read of the Q row and two warp-wide reductions
+// (max of order-preserving keys, then min index among the maxima = torch's first-index argmax).
+__device__ __forceinline__ uint32_t f32_ordered(float v) {
+  v += 0.0f;  // -0.0 -> +0.0 so that equal floats get equal keys
+  const uint32_t u = __float_as_uint(v);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kThreads) sap_select_classic_kernel(SelParams p, int vec4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)p.B * p.n;
+  const int64_t base = ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * 32;
+  if (base >= rows) return;
+  const int A = p.A;
+  const uint32_t ep_lo = p.episode_ctr ? (uint32_t)(*p.episode_ctr) : 0u;
+  const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+  // per-lane draws for row base + lane
+  float ue = 2.f, ua = 0.f;
+  {
+    const int64_t row = base + lane;
+    if (row < rows) {
+      if (p.u_explore) {
+        ue = p.u_explore[row];
+        ua = p.u_action[row];
+      } else {
+        const uint32_t step = p.k ? (uint32_t)p.k[row / p.n] : 0u;
+        const SapPhilox4 r = sap_philox4x32_10((uint32_t)row, ep_lo, step, 0u, k0, k1);
+        ue = sap_u01(r.x);
+        ua = sap_u01(r.y);
+      }
+    }
+  }
+  int my_action = 0;
+  const int nrows = (int)min((int64_t)32, rows - base);
+  for (int rr = 0; rr < nrows; ++rr) {
+    const int64_t row = base + rr;
+    const float* qr = p.q + row * A;
+    const uint8_t* av = p.avail ? p.avail + row * A : nullptr;
+    uint32_t bk = 0u;  // best ordered key of this lane (0 is below every real key, even -inf)
+    int bi = 0x7fffffff, n_avail = 0;
+    if (vec4) {
+      for (int j = lane * 4; j < A; j += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(qr + j);
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        uchar4 a4 = make_uchar4(1, 1, 1, 1);
+        if (av) a4 = *reinterpret_cast<const uchar4*>(av + j);
+        const uint8_t ok[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          n_avail += ok[c] != 0;
+          const uint32_t key = f32_ordered(ok[c] ? x[c] : -INFINITY);  // classic_selectors.py:46-47
+          if (key > bk) {
+            bk = key;
+            bi = j + c;
+          }
+        }
+      }
+    } else {
+      for (int j = lane; j < A; j += 32) {
+        const bool ok = av ? av[j] != 0 : true;
+        n_avail += ok;
+        const uint32_t key = f32_ordered(ok ? qr[j] : -INFINITY);
+        if (key > bk) {
+          bk = key;
+          bi = j;
+        }
+      }
+    }
+    const uint32_t gmax = __reduce_max_sync(SAP_FULL_MASK, bk);
+    int action = (int)__reduce_min_sync(SAP_FULL_MASK, (uint32_t)(bk == gmax ? bi : 0x7fffffff));
+    const float ue_r = __shfl_sync(SAP_FULL_MASK, ue, rr);
+    if (ue_r < p.eps) {  // warp-uniform: explore (:49-51)
+      if (av) n_avail = (int)__reduce_add_sync(SAP_FULL_MASK, (uint32_t)n_avail);
+      else n_avail = A;
+      if (n_avail > 0) {
+        const float ua_r = __shfl_sync(SAP_FULL_MASK, ua, rr);
+        int rank = (int)floorf(__fmul_rn(ua_r, (float)n_avail));
+        rank = min(rank, n_avail - 1);
+        action = av ? warp_rank_select(av, A, rank, lane) : rank;
+      }
+    }
+    if (lane == rr) my_action = action;
+  }
+  if (lane < nrows) p.out[base + lane] = (int64_t)my_action;
+}
+
 template <bool kFiltered>
 __global__ void __launch_bounds__(kThreads) sap_select_kernel(SelParams p) {
   const int lane = threadIdx.x & 31;
@@ -177,8 +264,10 @@ extern "C" int sap_select_epsilon_greedy(const float* q, const uint8_t* avail, i
   p.q = q; p.avail = avail; p.B = B; p.n = n; p.A = A; p.eps = eps; p.seed = seed;
   p.episode_ctr = episode_ctr; p.k = k; p.u_explore = u_explore; p.u_action = u_action; p.out = actions_out;
   const int64_t rows = (int64_t)B * n;
-  sap_select_kernel<false><<<(unsigned)((rows + kWarps - 1) / kWarps), kThreads, 0, (cudaStream_t)stream>>>(p);
-  SAP_CUDA_LAUNCH_CHECK("sap_select_kernel<classic>");
+  const int vec4 = (A % 4 == 0) && sap_aligned16(q) && (!avail || (reinterpret_cast<uintptr_t>(avail) & 3) == 0);
+  const int64_t warps = (rows + 31) / 32;
+  sap_select_classic_kernel<<<(unsigned)((warps + kWarps - 1) / kWarps), kThreads, 0, (cudaStream_t)stream>>>(p, vec4);
+  SAP_CUDA_LAUNCH_CHECK("sap_select_classic_kernel");
   return SAP_OK;
 }
 

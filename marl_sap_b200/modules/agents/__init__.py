@@ -1,6 +1,7 @@
 """Agent networks: plain torch modules, kept as in the reference (the only dense contraction on the path;
 north star: "the agent network forward stays the reference's torch module").
 /root/reference/src/modules/agents/rnn_agent.py:7-31, flat_const_agent.py:9-34."""
+import torch as th
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -19,14 +20,22 @@ class _FcAgent(nn.Module):
     def init_hidden(self):
         return self.fc1.weight.new(1, self.args.hidden_dim).zero_()
 
+    @staticmethod
+    def _linear(layer, x):
+        """layer(x) as one cuBLAS call with the bias as beta*C (same fp32 math as F.linear, bit-identical results,
+        without the separate bias-epilogue kernel cublasLt launches for these skinny fp32 GEMMs)."""
+        if x.is_cuda and x.dim() == 2 and layer.bias is not None:
+            return th.addmm(layer.bias, x, layer.weight.t())
+        return layer(x)
+
     def forward(self, inputs, hidden_state):
-        x = F.relu(self.fc1(inputs))
+        x = F.relu(self._linear(self.fc1, inputs))
         h_in = hidden_state.reshape(-1, self.args.hidden_dim)
         if self.args.use_rnn:
             h = self.rnn(x, h_in)
         else:
-            h = F.relu(self.rnn(x))
-        q = self.fc2(h)
+            h = F.relu(self._linear(self.rnn, x))
+        q = self._linear(self.fc2, h)
         return q, h
 
 
