@@ -46,10 +46,11 @@ def obs_size(w):
     return w["M"] * w["L"] + w["N"] * w["M"] * w["L"] + w["N"] * (w["M"] // 2) * w["L"] + w["M"]
 
 
-def algorithmic_bytes_per_env_step(w, e_obs):
-    """DESIGN.md section 4 / SURVEY.md 8(d): window read + obs write + per-agent scalars."""
+def algorithmic_bytes_per_env_step(w, e_obs, e_agent_in=4):
+    """DESIGN.md section 4 / SURVEY.md 8(d): window read + obs write (buffer dtype) + the fp32 copy of the obs the
+    agent network consumes (written by the same kernel) + per-agent scalars."""
     n, m, L = w["n"], w["m"], w["L"]
-    return n * m * L * 4 + n * obs_size(w) * e_obs + n * 16 + 16
+    return n * m * L * 4 + n * obs_size(w) * (e_obs + e_agent_in) + n * 16 + 16
 
 
 # ----------------------------------------------------------------------------------------------- CPU port
@@ -345,7 +346,8 @@ def gpu_arm(opts, w):
                    "parallelism": f"envs block-partitioned, {world} rank(s), no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "sap_real_kernel" if w["env"] == "real" else "sap_mock_kernel",
+                     "traffic": traffic, "kernel": "sap_real_fast_kernel" if w["env"] == "real" else "sap_mock_kernel",
+                     "algorithmic_bytes": "window read n*m*L*4 + obs write n*obs*(2 or 4) + agent-input write n*obs*4 + n*16+16 per env-step",
                      "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": kern_ms, "peak_source": peak_src,
                      "kernel_share_of_step": kern_ms * T / (ms / opts.steps)},
         "cpu_baseline": cpu, "wall_s": wall,

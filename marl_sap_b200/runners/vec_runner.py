@@ -143,6 +143,7 @@ class CudaVecRunner:
         self.kernel_launches += 1
         self.t = 0
 
+    @th.no_grad()
     def run(self, test_mode=False, **reset_kwargs):
         self.reset(**reset_kwargs)
         self.mac.init_hidden(batch_size=self.batch_size)
