@@ -35,8 +35,14 @@ constexpr size_t kMaxSmem = 227 * 1024 - 1024;
     a = hi__;                   \
   }
 
+// Shared-memory plan.  Two overlays share one region: while the lists are built it holds the key tile and the
+// scratch lists; for the gather it is refilled with the benefits (rounded to the obs dtype) and the staging rows.
+// At 100 x 100 (fp16 obs, 8-bit indices) that is 7.3 KB persistent + max(45 KB, 68 KB) = 75 KB: three CTAs per SM.
 struct FastLayout {
-  size_t tile, k32, D, E, nbr, other, dmask, cnt, prios, red, queue, lut, total;
+  size_t D, nbr, other, lut, prios;            // live through the whole kernel
+  size_t k32, E, dmask, cnt, red, queue;       // overlay 1: list building
+  size_t tile, stage;                          // overlay 2: gather
+  size_t total;
   int ms, mw, rows_per_pass;
 };
 
@@ -48,24 +54,26 @@ __host__ __device__ inline FastLayout fast_layout(const SapEnvDims& d, int out_e
   f.ms = (d.m + 3) & ~3;
   f.mw = (d.m + 31) / 32;
   size_t off = 0;
-  f.tile = off;  off = up16(off + (size_t)out_esz * d.L * d.n * d.m);
-  f.k32 = off;   off = up16(off + sizeof(uint32_t) * (size_t)d.n * f.ms + 16);  // +16: staging alignment shift
   f.D = off;     off = up16(off + (size_t)idx_esz * d.n * d.M);
-  f.E = off;     off = up16(off + (size_t)idx_esz * d.n * K2);
   f.nbr = off;   off = up16(off + (size_t)idx_esz * d.n * d.N);
   f.other = off; off = up16(off + (size_t)idx_esz * d.n * d.N * H);
+  f.lut = off;   off = up16(off + sizeof(uint16_t) * (size_t)(d.M + d.N * d.M + d.N * H));
+  f.prios = off; off = up16(off + (prios ? sizeof(double) * (size_t)d.m : 0));
+  const size_t base = off;
+  f.k32 = off;   off = up16(off + sizeof(uint32_t) * (size_t)d.n * f.ms);
+  f.E = off;     off = up16(off + (size_t)idx_esz * d.n * K2);
   f.dmask = off; off = up16(off + sizeof(uint32_t) * (size_t)d.n * f.mw);
   f.cnt = off;   off = up16(off + sizeof(int32_t) * (size_t)d.m);
-  f.prios = off; off = up16(off + (prios ? sizeof(double) * (size_t)d.m : 0));
   f.red = off;   off = up16(off + sizeof(double) * 80);
   f.queue = off; off = up16(off + sizeof(int32_t) * (2 * (size_t)d.n + 4));
-  f.lut = off;   off = up16(off + sizeof(uint16_t) * (size_t)(d.M + d.N * d.M + d.N * H));
-  f.total = off;
+  const size_t end1 = off;
   const size_t row_bytes = (size_t)out_esz * (d.M * d.L + d.N * d.M * d.L + d.N * H * d.L + d.M);
-  const size_t stage = sizeof(uint32_t) * (size_t)d.n * f.ms;
-  int rpp = (int)(stage / row_bytes);
-  if (rpp > kWarps) rpp = kWarps;
-  f.rows_per_pass = rpp;
+  f.rows_per_pass = kWarps;
+  off = base;
+  f.tile = off;  off = up16(off + (size_t)out_esz * d.L * d.n * d.m);
+  f.stage = off; off = up16(off + (size_t)kWarps * row_bytes + 16);  // +16: staging alignment shift
+  const size_t end2 = off;
+  f.total = end1 > end2 ? end1 : end2;
   return f;
 }
 
@@ -380,23 +388,12 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     // 4 adjacent tasks of one agent: L float4 in, 4 keys + L x 4 rounded benefits out
     auto finish = [&](int e4, int i, int j, const float4 (&v)[4]) {
       double tot[4] = {0.0, 0.0, 0.0, 0.0};
-      OutT o[4][4];
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
-        if (l < L) {
-          const float x[4] = {l < Leff ? v[l].x : 0.f, l < Leff ? v[l].y : 0.f, l < Leff ? v[l].z : 0.f,
-                              l < Leff ? v[l].w : 0.f};
+        if (l < Leff) {
+          const float x[4] = {v[l].x, v[l].y, v[l].z, v[l].w};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (kPrios) {
-              const double bv = (double)x[c] * sPrio[j + c];
-              tot[c] += bv;
-              o[l][c] = to_out<OutT>(bv);
-            } else {
-              tot[c] += (double)x[c];
-              o[l][c] = to_out_f<OutT>(x[c]);
-            }
-          }
+          for (int c = 0; c < 4; ++c) tot[c] += kPrios ? (double)x[c] * sPrio[j + c] : (double)x[c];
         }
       }
       uint4 kk;
@@ -405,16 +402,6 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
       kk.z = make_key(tot[2]);
       kk.w = make_key(tot[3]);
       *reinterpret_cast<uint4*>(K32 + i * ms + j) = kk;
-#pragma unroll
-      for (int l = 0; l < 4; ++l)
-        if (l < L) {
-          OutT* dst = tile + (size_t)l * nm + (size_t)e4 * 4;
-          if (sizeof(OutT) == 2) {
-            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(&o[l][0]);
-          } else {
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&o[l][0]);
-          }
-        }
     };
     // (i, j/4) advance incrementally: no division in the loop; two groups per iteration keep 2L loads in flight
     const int step_i = kThreads / m4, step_j = kThreads - step_i * m4;
@@ -448,11 +435,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
       for (int j = lane; j < m; j += 32) {
         const double pr = kPrios ? sPrio[j] : 1.0;
         double tot = 0.0;
-        for (int l = 0; l < L; ++l) {
-          const double bv = l < Leff ? (double)win[(size_t)l * nm + i * m + j] * pr : 0.0;
-          tot += bv;
-          tile[(size_t)l * nm + i * m + j] = to_out<OutT>(bv);
-        }
+        for (int l = 0; l < Leff; ++l) tot += (double)win[(size_t)l * nm + i * m + j] * pr;
         K32[i * ms + j] = make_key(tot);
       }
   }
@@ -559,7 +542,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   }
 
   // ------------------------------------------------------------------ 6. rivals (:203-206)
-  for (int base = 0; base < n * TPL; base += kThreads) {
+  for (int base = 0; base < n * TPL && !(p.debug_skip_redo & 4); base += kThreads) {
     const int g = base + tid;
     const int i = g / TPL, s = g % TPL;
     const bool live = i < n;
@@ -607,7 +590,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   // ------------------------------------------------------------------ 7. rivals' other top tasks (:212-217)
   // The M/2 best tasks of rival r outside D[i] under (value desc, idx desc) are the first M/2 entries of E[r]
   // not in D[i]; the reference lists them ascending, so they are stored reversed.
-  for (int it = tid; it < n * N; it += kThreads) {
+  for (int it = tid; it < n * N && !(p.debug_skip_redo & 64); it += kThreads) {
     const int i = it / N;
     const int r = sNbr[it];
     int c = 0;
@@ -621,10 +604,62 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   }
   __syncthreads();
 
-  // ------------------------------------------------------------------ 8. gather rows into shared memory, store 128-bit
+  // ------------------------------------------------------------------ 8a. benefits of the window -> shared memory
+  // Second read of the window (it is L2-resident: this CTA streamed it a few microseconds ago).  It lands over
+  // the key tile and the scratch lists, which are dead now, already rounded to the obs dtype (:199-219 gathers).
+  if (p.debug_skip_redo & 32) {
+  } else if (vec4) {
+    const int total4 = nm >> 2;
+    auto put4 = [&](int l, int e4, const float4& v) {
+      OutT o[4];
+      if (kPrios) {
+        const int j = (e4 * 4) % m;
+        o[0] = to_out<OutT>((double)v.x * sPrio[j]);
+        o[1] = to_out<OutT>((double)v.y * sPrio[j + 1]);
+        o[2] = to_out<OutT>((double)v.z * sPrio[j + 2]);
+        o[3] = to_out<OutT>((double)v.w * sPrio[j + 3]);
+      } else {
+        o[0] = to_out_f<OutT>(v.x);
+        o[1] = to_out_f<OutT>(v.y);
+        o[2] = to_out_f<OutT>(v.z);
+        o[3] = to_out_f<OutT>(v.w);
+      }
+      OutT* dst = tile + (size_t)l * nm + (size_t)e4 * 4;
+      if (sizeof(OutT) == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(&o[0]);
+      else *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&o[0]);
+    };
+    // 2 x L independent 128-bit loads in flight per thread
+    for (int e4 = tid; e4 < total4; e4 += 2 * kThreads) {
+      const int e4b = e4 + kThreads;
+      const bool has_b = e4b < total4;
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        va[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[l] = va[l];
+        if (l < Leff) va[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4 * 4);
+        if (l < Leff && has_b) vb[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4b * 4);
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < L) {
+          put4(l, e4, va[l]);
+          if (has_b) put4(l, e4b, vb[l]);
+        }
+    }
+  } else {
+    for (int e = tid; e < L * nm; e += kThreads) {
+      const int l = e / nm, x = e - l * nm;
+      const double pr = kPrios ? sPrio[x % m] : 1.0;
+      tile[e] = to_out<OutT>(l < Leff ? (double)win[e] * pr : 0.0);
+    }
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ 8b. gather rows into shared memory, store 128-bit
   // The key tile is dead now; it becomes the staging area.  Rows are staged at the same 16-byte phase as their
   // global destination so the aligned interior goes out as uint4.
-  unsigned char* stage = reinterpret_cast<unsigned char*>(K32);
+  unsigned char* stage = smem + f.stage;
   const size_t row_bytes = sizeof(OutT) * (size_t)obs_size;
   const int rpp = f.rows_per_pass;
   const bool ain_flat = ain && ain_row == obs_size && ((reinterpret_cast<uintptr_t>(ain) & 15) == 0);
@@ -632,7 +667,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     const int rows = min(rpp, n - r0);
     unsigned char* gdst = reinterpret_cast<unsigned char*>(obs_out) + (size_t)r0 * row_bytes;
     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15);
-    if (warp < rows) {
+    if (warp < rows && !(p.debug_skip_redo & 8)) {
       const int i = r0 + warp;
       OutT* srow = reinterpret_cast<OutT*>(stage + phase + (size_t)warp * row_bytes);
       const IdxT* myD = sD + i * M;
@@ -684,7 +719,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
       }
     }
     __syncthreads();
-    const size_t bytes = (size_t)rows * row_bytes;
+    const size_t bytes = (p.debug_skip_redo & 16) ? 0 : (size_t)rows * row_bytes;
     const unsigned char* ssrc = stage + phase;
     if (phase == 0 && (bytes & 15) == 0 && (!ain || ain_flat)) {
       // aligned block: 16 bytes per thread and iteration to the obs slot, plus its fp32 image for the agent network
@@ -732,7 +767,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
 // One CTA per environment; the hardware block scheduler balances the (slightly uneven) per-env durations better
 // than a static persistent partition did (measured: 0.95 ms vs 1.18 ms at 4096 x 100 x 100).
 template <typename C>
-__global__ void __launch_bounds__(kThreads, 2) sap_real_fast_kernel(RealParams p) {
+__global__ void __launch_bounds__(kThreads, 3) sap_real_fast_kernel(RealParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   process_env<C>(p, blockIdx.x, smem);
 }
@@ -768,7 +803,7 @@ int sap_real_fast_try(RealParams& p, void* stream, int* handled) {
   const bool common = d.M == 10 && d.N == 10 && d.L == 3 && half_out && !p.prios;
   const bool idx8 = common && d.n <= 256 && d.m <= 256;
   const FastLayout f = fast_layout(d, half_out ? 2 : 4, idx8 ? 1 : 2, p.prios != nullptr);
-  if (f.total > kMaxSmem || f.rows_per_pass < 1 || f.ms * 4 < kWarps * 8) return SAP_OK;
+  if (f.total > kMaxSmem || f.ms * 4 < kWarps * 8) return SAP_OK;
   if (p.view.agent_in.ptr && p.view.agent_in.dtype != SAP_F32) {
     sap_set_error("sap_real: agent_in must be f32");
     return SAP_E_DTYPE;
