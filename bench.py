@@ -228,6 +228,7 @@ def build_runner(w, rank_seed, planes):
     mac.agent.load_state_dict({k: th.tensor(v) for k, v in weights.items()})
     mac.cuda()
     runner.setup(scheme=env.scheme, groups=groups, preprocess=env.preprocess, mac=mac)
+    runner.attach_replay(buffer)  # episodes are rolled out in the replay ring's own rows (no insert-time copy)
     return runner, buffer, weights
 
 
@@ -342,7 +343,7 @@ def gpu_arm(opts, w):
                    "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch",
                    "inputs": f"benefit planes {planes.numel() * 4 / 2 ** 30:.1f} GiB per GPU (> 126 MB L2), distinct per env",
                    "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
-                   "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy",
+                   "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy; episodes rolled out in place in the replay ring",
                    "parallelism": f"envs block-partitioned, {world} rank(s), no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

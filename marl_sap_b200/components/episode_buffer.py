@@ -270,10 +270,35 @@ class ReplayBuffer(EpisodeBatch):
         self.episodes_in_buffer = 0
 
     # ------------------------------------------------------------------ ring insert (:244-259)
+    def view_next(self, n_new):
+        """An EpisodeBatch whose tensors ALIAS the next ``n_new`` ring rows, for runners that roll out straight into
+        the replay buffer (no episode-sized copy at insert time).  ``None`` when the rows would wrap.  Rolling into
+        a used slot is safe because the env kernels rewrite every slot they own each episode and the slots they
+        never write (actions/rewards/terminated at t = T) are zero from allocation."""
+        if n_new > self.buffer_size or self.buffer_index + n_new > self.buffer_size:
+            return None
+        sl = slice(self.buffer_index, self.buffer_index + n_new)
+        data = self._new_data_sn()
+        for k, v in self.data.transition_data.items():
+            data.transition_data[k] = v[sl]
+        for k, v in self.data.episode_data.items():
+            data.episode_data[k] = v[sl]
+        view = EpisodeBatch(self.scheme, self.groups, n_new, self.max_seq_length, data=data, device=self.device,
+                            lazy=self.lazy)
+        view.preprocess = self.preprocess
+        view._ring_owner, view._ring_start = self, self.buffer_index
+        return view
+
     def insert_episode_batch(self, ep_batch):
         n_new = ep_batch.batch_size
         if n_new > self.buffer_size:
             raise ValueError(f"episode batch of {n_new} does not fit a replay buffer of {self.buffer_size}")
+        if getattr(ep_batch, "_ring_owner", None) is self and ep_batch._ring_start == self.buffer_index:
+            # the episode was rolled out in place (view_next): only the ring bookkeeping moves
+            end = self.buffer_index + n_new
+            self.episodes_in_buffer = max(self.episodes_in_buffer, end)
+            self.buffer_index = end % self.buffer_size
+            return
         if self._device_rows_ok(ep_batch):
             lib = _lib.load()
             stream = _lib.stream_ptr(self.data.transition_data["filled"].device)

@@ -124,8 +124,18 @@ class CudaVecRunner:
     def close_env(self):
         return None
 
+    def attach_replay(self, buffer):
+        """Opt-in: roll episodes out directly into ``buffer``'s next ring rows (``ReplayBuffer.view_next``), so the
+        following ``buffer.insert_episode_batch(batch)`` is bookkeeping only.  Falls back to a private batch when
+        the rows would wrap."""
+        self._replay = buffer
+
     def reset(self, **reset_kwargs):
-        if self.reuse_batch and self._batch is not None:
+        ring = getattr(self, "_replay", None)
+        view = ring.view_next(self.batch_size) if ring is not None else None
+        if view is not None:
+            self.batch = view
+        elif self.reuse_batch and self._batch is not None:
             self.batch = self._batch
             for v in self.batch.data.transition_data.values():
                 v.zero_()

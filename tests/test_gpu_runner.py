@@ -188,3 +188,26 @@ def test_product_path_has_no_oracle_import():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_rollout_in_place_into_replay_ring():
+    """runner.attach_replay: episodes land in the ring rows directly and equal a copy-inserted rollout."""
+    rng = np.random.default_rng(31)
+    B, n, m, T = 4, 8, 12, 5
+    S = O.gen_dense(rng, B, n, m, T)
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=3, M=4, L=3, lambda_=0.5, sat_prox_mat=S, graphs=1)
+    res = []
+    for in_place in (False, True):
+        args = make_args("real_constellation_env", env_args, B, epsilon_start=0.4, epsilon_finish=0.4)
+        runner, mac, buffer, logger = build(args)  # ring of 2B + 1 rows
+        if in_place:
+            runner.attach_replay(buffer)
+        for ep in range(3):  # third episode would wrap -> falls back to a private batch + copy insert
+            batch = runner.run()
+            if in_place and ep < 2:
+                assert batch["obs"].data_ptr() == buffer["obs"][ep * B:].data_ptr()
+            buffer.insert_episode_batch(batch)
+        assert buffer.episodes_in_buffer == 2 * B + 1 and buffer.buffer_index == (3 * B) % (2 * B + 1)
+        res.append({k: v.clone() for k, v in buffer.data.transition_data.items()})
+    for k in res[0]:
+        assert th.equal(res[0][k], res[1][k]), k
