@@ -190,7 +190,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def build_runner(w, rank_seed, planes):
+def build_runner(w, rank_seed, planes, use_graph=False):
     import torch as th
 
     from marl_sap_b200.components.episode_buffer import ReplayBuffer
@@ -213,7 +213,8 @@ def build_runner(w, rank_seed, planes):
                            epsilon_anneal_time=1, evaluation_epsilon=0.0, agent="rnn", hidden_dim=64, use_rnn=False,
                            obs_agent_id=False, obs_last_action=False, agent_output_type="q", test_nepisode=w["B"],
                            runner_log_interval=10 ** 12, seed=rank_seed, use_mps_action_selection=True,
-                           lazy_buffer_fields=("beta", "avail_actions", "actions_onehot"), reuse_episode_batch=True)
+                           lazy_buffer_fields=("beta", "avail_actions", "actions_onehot"), reuse_episode_batch=True,
+                           use_cuda_graph=bool(use_graph))
     logger = Logger()
     runner = r_REGISTRY["parallel"](args=args, logger=logger)
     runner.env.set_planes(planes, shared=False)
@@ -248,7 +249,7 @@ def gpu_arm(opts, w):
     # synthetic benefits, U(0,1), distinct per env and per rank, generated straight in the device layout
     g = th.Generator(device=dev).manual_seed(1234 + rank)
     planes = th.rand(B, T, n, m, device=dev, generator=g)
-    runner, buffer, weights = build_runner(w, 1 + rank, planes)
+    runner, buffer, weights = build_runner(w, 1 + rank, planes, opts.graph)
     n_fields = len(buffer.data.transition_data)
 
     # per-launch event pairs around the fused env kernel
@@ -297,6 +298,15 @@ def gpu_arm(opts, w):
     barrier()
     timed_step.enabled = False
     clocks = sampler.stop() if rank == 0 else None
+    if opts.graph:
+        # the timed region replayed captured CUDA graphs (no per-launch events possible): take the per-launch
+        # durations from one extra eager episode right after it
+        runner.args.use_cuda_graph = False
+        timed_step.enabled = True
+        step()
+        th.cuda.synchronize()
+        timed_step.enabled = False
+        runner.args.use_cuda_graph = True
     ms = e0.elapsed_time(e1)
     kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(len(ev_pairs), 1)
     launches = runner.kernel_launches - launches0 + opts.steps * n_fields
@@ -340,7 +350,7 @@ def gpu_arm(opts, w):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{opts.workload}: {w['desc']}, T={T}, L={w['L']}, M={w['M']}, N={w['N']}, {w['env']} env, "
                                "epsilon_greedy + fc agent(hidden 64)",
-                   "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch",
+                   "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch", "cuda_graph": bool(opts.graph),
                    "inputs": f"benefit planes {planes.numel() * 4 / 2 ** 30:.1f} GiB per GPU (> 126 MB L2), distinct per env",
                    "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
                    "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy; episodes rolled out in place in the replay ring",
@@ -474,6 +484,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--graph", action="store_true", help="replay the T-step loop of every episode as one CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -148,12 +148,14 @@ int sap_mock_step(const SapEnvDims* dims, const float* planes, const float* T_tr
  * sap_select_filtered_epsilon_greedy = FilteredEpsilonGreedyActionSelector.select_action
  *   (action_selectors/filtered_classic_selectors.py:17-63); `top` replaces its th.topk(beta.sum(-1)).
  * Random draws: injected uniforms (u_* non-null, fp32 in [0,1)) or Philox4x32-10 keyed by
- *   (seed; b*n+i, *episode_ctr, k[b], draw id).  avail null = everything available. */
+ *   (seed; b*n+i, *episode_ctr, k[b], draw id).  avail null = everything available.
+ * eps_dev (nullable): device scalar that overrides `eps`, so a captured CUDA graph follows the schedule. */
 int sap_select_epsilon_greedy(const float* q, const uint8_t* avail, int32_t B, int32_t n, int32_t A, float eps,
+                              const float* eps_dev,
                               uint64_t seed, const uint64_t* episode_ctr, const int32_t* k, const float* u_explore,
                               const float* u_action, int64_t* actions_out, void* stream);
 int sap_select_filtered_epsilon_greedy(const float* q, const int32_t* top, const uint8_t* avail, int32_t B, int32_t n,
-                                       int32_t m, int32_t M, float eps, uint64_t seed, const uint64_t* episode_ctr,
+                                       int32_t m, int32_t M, float eps, const float* eps_dev, uint64_t seed, const uint64_t* episode_ctr,
                                        const int32_t* k, const float* u_tie, const float* u_explore,
                                        const float* u_action, int64_t* actions_out, void* stream);
 /* top-M task indices from a beta tensor [B,n,m,L] (dtype f32|f16), stable (value desc, index asc);

@@ -58,8 +58,8 @@ SIGNATURES = {
     "sap_real_scratch_doubles": (C.c_int64, [_DIMS]),
     "sap_mock_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _VIEW, _P]),
     "sap_mock_step": (C.c_int, [_DIMS, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P]),
-    "sap_select_epsilon_greedy": (C.c_int, [_P, _P, _I32, _I32, _I32, _F32, _U64, _P, _P, _P, _P, _P, _P]),
-    "sap_select_filtered_epsilon_greedy": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _F32, _U64, _P, _P, _P, _P,
+    "sap_select_epsilon_greedy": (C.c_int, [_P, _P, _I32, _I32, _I32, _F32, _P, _U64, _P, _P, _P, _P, _P, _P]),
+    "sap_select_filtered_epsilon_greedy": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _F32, _P, _U64, _P, _P, _P, _P,
                                                      _P, _P, _P]),
     "sap_topm_from_beta": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "sap_buffer_insert": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P]),

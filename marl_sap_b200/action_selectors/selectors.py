@@ -35,6 +35,29 @@ class _KernelSelectorBase:
         launch stays CUDA-graph capturable."""
         self.episode_ctr, self.step_k = episode_ctr, step_k
 
+    def use_device_epsilon(self, enabled=True):
+        """Keep epsilon in a device scalar the kernels read (needed when select_action is captured in a CUDA graph:
+        the schedule keeps moving between replays).  ``set_device_epsilon`` refreshes it outside the graph."""
+        self._eps_dev_enabled = bool(enabled)
+
+    def _eps_tensor(self, device):
+        # allocated once: captured graphs keep its address
+        if getattr(self, "_eps_dev", None) is None:
+            self._eps_dev = th.zeros(1, dtype=th.float32, device=device)
+        return self._eps_dev
+
+    def set_device_epsilon(self, t_env, test_mode, device):
+        eps = self._eps(t_env, test_mode)
+        self._eps_tensor(device).fill_(eps)
+        return eps
+
+    def _eps_ptr(self, eps, device):
+        if not getattr(self, "_eps_dev_enabled", False):
+            return None
+        if getattr(self, "_eps_dev", None) is None:
+            self._eps_tensor(device).fill_(eps)
+        return self._eps_dev.data_ptr()
+
     def inject_draws(self, **draws):
         """Parity hook: u_explore/u_action[/u_tie] fp32 tensors consumed by the next select_action call."""
         self._injected = draws
@@ -89,7 +112,8 @@ class EpsilonGreedyActionSelector(_KernelSelectorBase):
         if k is not None and k.numel() != B:
             k = None
         lib = _lib.load()
-        _lib.check(lib.sap_select_epsilon_greedy(q.data_ptr(), _lib.ptr(av), B, n, A, eps, self.seed, _lib.ptr(ctr),
+        _lib.check(lib.sap_select_epsilon_greedy(q.data_ptr(), _lib.ptr(av), B, n, A, eps, self._eps_ptr(eps, q.device),
+                                                 self.seed, _lib.ptr(ctr),
                                                  _lib.ptr(k), _lib.ptr(ue), _lib.ptr(ua), out.data_ptr(),
                                                  _lib.stream_ptr(q.device)), "sap_select_epsilon_greedy")
         return out
@@ -138,7 +162,7 @@ class FilteredEpsilonGreedyActionSelector(_KernelSelectorBase):
         if k is not None and k.numel() != B:
             k = None
         _lib.check(lib.sap_select_filtered_epsilon_greedy(q.data_ptr(), top.data_ptr(), _lib.ptr(av), B, n, m, M, eps,
-                                                          self.seed, _lib.ptr(ctr), _lib.ptr(k), _lib.ptr(ut), _lib.ptr(ue),
+                                                          self._eps_ptr(eps, q.device), self.seed, _lib.ptr(ctr), _lib.ptr(k), _lib.ptr(ut), _lib.ptr(ue),
                                                           _lib.ptr(ua), out.data_ptr(), stream),
                    "sap_select_filtered_epsilon_greedy")
         return out

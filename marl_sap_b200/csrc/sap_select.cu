@@ -51,6 +51,7 @@ struct SelParams {
   const uint8_t* avail;  // nullable
   int B, n, A, m, M;
   float eps;
+  const float* eps_dev;  // when non-null the kernel reads epsilon from device memory (CUDA-graph replays)
   uint64_t seed;
   const uint64_t* episode_ctr;
   const int32_t* k;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(kThreads) sap_select_classic_kernel(SelParams 
   const int64_t base = ((int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * 32;
   if (base >= rows) return;
   const int A = p.A;
+  const float eps = p.eps_dev ? *p.eps_dev : p.eps;
   const uint32_t ep_lo = p.episode_ctr ? (uint32_t)(*p.episode_ctr) : 0u;
   const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
   // per-lane draws for row base + lane
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) sap_select_classic_kernel(SelParams 
     const uint32_t gmax = __reduce_max_sync(SAP_FULL_MASK, bk);
     int action = (int)__reduce_min_sync(SAP_FULL_MASK, (uint32_t)(bk == gmax ? bi : 0x7fffffff));
     const float ue_r = __shfl_sync(SAP_FULL_MASK, ue, rr);
-    if (ue_r < p.eps) {  // warp-uniform: explore (:49-51)
+    if (ue_r < eps) {  // warp-uniform: explore (:49-51)
       if (av) n_avail = (int)__reduce_add_sync(SAP_FULL_MASK, (uint32_t)n_avail);
       else n_avail = A;
       if (n_avail > 0) {
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) sap_select_kernel(SelParams p) {
     ua = sap_u01(r.y);
   }
   int action = bi;
-  if (ue < p.eps && n_avail > 0) {  // :49-50 ; Categorical over the 0/1 mask = uniform over available
+  if (ue < (p.eps_dev ? *p.eps_dev : p.eps) && n_avail > 0) {  // :49-50 ; Categorical over the 0/1 mask = uniform over available
     int rank = (int)floorf(__fmul_rn(ua, (float)n_avail));
     rank = min(rank, n_avail - 1);
     action = warp_rank_select(av, A, rank, lane);
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(kThreads) sap_topm_kernel(const TB* beta, int6
 }  // namespace
 
 extern "C" int sap_select_epsilon_greedy(const float* q, const uint8_t* avail, int32_t B, int32_t n, int32_t A, float eps,
+                                         const float* eps_dev,
                                          uint64_t seed, const uint64_t* episode_ctr, const int32_t* k,
                                          const float* u_explore, const float* u_action, int64_t* actions_out,
                                          void* stream) {
@@ -261,7 +264,7 @@ extern "C" int sap_select_epsilon_greedy(const float* q, const uint8_t* avail, i
   SAP_REQUIRE((u_explore == nullptr) == (u_action == nullptr), SAP_E_NULL,
               "sap_select_epsilon_greedy: u_explore and u_action must be given together");
   SelParams p{};
-  p.q = q; p.avail = avail; p.B = B; p.n = n; p.A = A; p.eps = eps; p.seed = seed;
+  p.q = q; p.avail = avail; p.B = B; p.n = n; p.A = A; p.eps = eps; p.eps_dev = eps_dev; p.seed = seed;
   p.episode_ctr = episode_ctr; p.k = k; p.u_explore = u_explore; p.u_action = u_action; p.out = actions_out;
   const int64_t rows = (int64_t)B * n;
   const int vec4 = (A % 4 == 0) && sap_aligned16(q) && (!avail || (reinterpret_cast<uintptr_t>(avail) & 3) == 0);
@@ -272,7 +275,8 @@ extern "C" int sap_select_epsilon_greedy(const float* q, const uint8_t* avail, i
 }
 
 extern "C" int sap_select_filtered_epsilon_greedy(const float* q, const int32_t* top, const uint8_t* avail, int32_t B,
-                                                  int32_t n, int32_t m, int32_t M, float eps, uint64_t seed,
+                                                  int32_t n, int32_t m, int32_t M, float eps, const float* eps_dev,
+                                                  uint64_t seed,
                                                   const uint64_t* episode_ctr, const int32_t* k, const float* u_tie,
                                                   const float* u_explore, const float* u_action, int64_t* actions_out,
                                                   void* stream) {
@@ -282,7 +286,7 @@ extern "C" int sap_select_filtered_epsilon_greedy(const float* q, const int32_t*
   SAP_REQUIRE((u_explore == nullptr) == (u_action == nullptr), SAP_E_NULL,
               "sap_select_filtered_epsilon_greedy: u_explore and u_action must be given together");
   SelParams p{};
-  p.q = q; p.top = top; p.avail = avail; p.B = B; p.n = n; p.m = m; p.M = M; p.eps = eps; p.seed = seed;
+  p.q = q; p.top = top; p.avail = avail; p.B = B; p.n = n; p.m = m; p.M = M; p.eps = eps; p.eps_dev = eps_dev; p.seed = seed;
   p.episode_ctr = episode_ctr; p.k = k; p.u_tie = u_tie; p.u_explore = u_explore; p.u_action = u_action;
   p.out = actions_out;
   const int64_t rows = (int64_t)B * n;

@@ -153,9 +153,7 @@ class CudaVecRunner:
         self.kernel_launches += 1
         self.t = 0
 
-    @th.no_grad()
-    def run(self, test_mode=False, **reset_kwargs):
-        self.reset(**reset_kwargs)
+    def _rollout_loop(self, test_mode):
         self.mac.init_hidden(batch_size=self.batch_size)
         for t in range(self.T):
             # agent forward (torch) + selection kernel; obs / avail / beta for slot t were written by the env kernel
@@ -163,9 +161,47 @@ class CudaVecRunner:
             # fused env kernel: rewards/actions/terminated at slot t, obs/prev_assigns/filled at slot t+1
             self.env.step(actions, self.batch)
             self.batch.agent_in_t = t + 1
-            self.kernel_launches += 2
             self.t += 1
         self.episode_ctr += 1
+
+    def _rollout_graph(self, test_mode):
+        """Replay the T-step loop as one CUDA graph (``args.use_cuda_graph``).  Every launch reads its step counter,
+        episode counter and epsilon from device memory, so one capture serves all later episodes that use the same
+        buffers.  The first episode runs eagerly (lazy initialisation), the second is captured."""
+        sel = self.mac.action_selector
+        if not hasattr(sel, "use_device_epsilon"):
+            return False
+        sel.use_device_epsilon(True)
+        sel.set_device_epsilon(self.t_env, test_mode, self.device)
+        td = self.batch.data.transition_data
+        key = (td["obs"].data_ptr(), td["filled"].data_ptr(), self.env.planes.data_ptr(),
+               0 if self.env.plane_stats is None else self.env.plane_stats.data_ptr(), bool(test_mode))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            if not self.__dict__.get("_graph_warm", False) or len(graphs) >= 8:
+                self._graph_warm = True
+                return False
+            g = th.cuda.CUDAGraph()
+            th.cuda.synchronize(self.device)
+            t_host = self.env.t_host
+            with th.cuda.graph(g):
+                self._rollout_loop(test_mode)
+            self.env.t_host = t_host  # capture only recorded the launches
+            self.t = 0
+            graphs[key] = g
+        g.replay()
+        self.env.t_host += self.T
+        self.t = self.T
+        self.batch.agent_in_t = self.T
+        return True
+
+    @th.no_grad()
+    def run(self, test_mode=False, **reset_kwargs):
+        self.reset(**reset_kwargs)
+        if not (getattr(self.args, "use_cuda_graph", False) and self._rollout_graph(test_mode)):
+            self._rollout_loop(test_mode)
+        self.kernel_launches += 2 * self.T
         self.last_episode_returns = self.env.ep_return.clone()
         self._finish_run(test_mode)
         return self.batch

@@ -70,7 +70,7 @@ def test_argument_validation_without_gpu():
     assert b"m >= n" in lib.sap_last_error()
     dims = _lib.SapEnvDims(2, 4, 9, 5, 3, 3, 2, 0)  # odd M
     assert lib.sap_real_reset(dims, None, None, None, None, None, None, view, None, None, None) == -3
-    assert lib.sap_select_epsilon_greedy(None, None, 1, 1, 1, 0.1, 0, None, None, None, None, None, None) == -1
+    assert lib.sap_select_epsilon_greedy(None, None, 1, 1, 1, 0.1, None, 0, None, None, None, None, None, None) == -1
     assert lib.sap_buffer_insert(None, None, 16, 4, 0, 0, 1, None) == -1
     assert lib.sap_benefit_ingest(None, None, 1, 1, 1, 1, None) == -1
     with pytest.raises(RuntimeError, match="failed"):

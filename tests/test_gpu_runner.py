@@ -211,3 +211,35 @@ def test_rollout_in_place_into_replay_ring():
         res.append({k: v.clone() for k, v in buffer.data.transition_data.items()})
     for k in res[0]:
         assert th.equal(res[0][k], res[1][k]), k
+
+
+@pytest.mark.parametrize("env_name", ["real_constellation_env", "mock_constellation_env"])
+def test_cuda_graph_rollout_equals_eager(env_name):
+    """args.use_cuda_graph: the captured T-step loop reproduces the eager rollout bit for bit, episode after episode,
+    while epsilon keeps following its schedule (device scalar)."""
+    rng = np.random.default_rng(37)
+    B, n, m, T = 6, 10, 12, 6
+    S = O.gen_dense(rng, B, n, m, T)
+    if env_name == "real_constellation_env":
+        env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=3, M=4, L=3, lambda_=0.5, sat_prox_mat=S, graphs=1)
+        kw = {}
+    else:
+        env_args = dict(n=n, m=m, T=T, L=3, lambda_=0.5, sat_prox_mat=S)
+        kw = {"prev0": np.tile(np.arange(n), (B, 1))}
+    outs = []
+    for use_graph in (False, True):
+        args = make_args(env_name, env_args, B, epsilon_anneal_time=200, reuse_episode_batch=True, use_cuda_graph=use_graph)
+        runner, mac, buffer, logger = build(args)
+        eps_seen, acts = [], []
+        for ep in range(5):
+            batch = runner.run(**kw)
+            eps_seen.append(mac.action_selector.epsilon)
+            acts.append(batch["actions"].clone())
+            acts.append(batch["obs"].clone())
+            acts.append(batch["rewards"].clone())
+        if use_graph:
+            assert len(runner._graphs) == 1
+        outs.append((eps_seen, acts))
+    assert outs[0][0] == outs[1][0] and outs[0][0][0] > outs[0][0][-1]  # epsilon annealed identically
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert th.equal(a, b)
