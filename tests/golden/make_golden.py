@@ -303,10 +303,87 @@ def main():
     golden_mock(R)
     golden_selectors(R)
     golden_buffer(R)
+    golden_runner(R)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--runner-only" not in sys.argv:
     main()
+
+
+def golden_runner(R):
+    """The reference's EpisodeRunner + BasicMAC + RNNAgent + epsilon_greedy end to end (runners/episode_runner.py:60-127),
+    with injected selector draws.  Seeds are retried until every greedy decision has a top-2 Q gap > 1e-3, so that
+    fp32 GEMM rounding differences between the reference's CPU agent and a GPU agent cannot flip an argmax."""
+    import torch as th
+    from types import SimpleNamespace as SN
+
+    class Log:
+        def __init__(self):
+            self.stats = {}
+
+        def log_stat(self, k, v, t):
+            self.stats.setdefault(k, []).append((t, float(v)))
+
+    for name, env_name, n, m, T, extra in [("runner_mock", "mock_constellation_env", 10, 10, 20, {}),
+                                           ("runner_real", "real_constellation_env", 8, 12, 10, dict(M=4, N=3))]:
+        for seed in range(100):
+            rng = np.random.default_rng(1000 + seed)
+            S = O.gen_dense(rng, 1, n, m, T)[0]
+            if env_name == "mock_constellation_env":
+                env_args = dict(n=n, m=m, T=T, L=3, lambda_=0.5, sat_prox_mat=S.astype(np.float64), seed=0)
+            else:
+                env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, L=3, lambda_=0.5, N=extra["N"], M=extra["M"],
+                                sat_prox_mat=S.astype(np.float64), graphs=1, seed=0)
+            args = SN(env=env_name, env_args=env_args, batch_size_run=1, use_mps_action_selection=True, device="cpu",
+                      mac="basic_mac", render=False, test_nepisode=1, runner_log_interval=1, agent="rnn", hidden_dim=64,
+                      use_rnn=False, agent_output_type="q", action_selector="epsilon_greedy", epsilon_start=0.4,
+                      epsilon_finish=0.4, epsilon_anneal_time=1, evaluation_epsilon=0.0, obs_agent_id=True,
+                      obs_last_action=True, n=n, m=m, T=T)
+            log = Log()
+            runner = R.episode_runner.EpisodeRunner(args, log)
+            env = runner.get_env()
+            groups = {"agents": n}
+            buffer = R.episode_buffer.ReplayBuffer(env.scheme, groups, 2, T + 1, preprocess=env.preprocess, device="cpu")
+            th.manual_seed(seed)
+            mac = R.basic_controller.BasicMAC(buffer.scheme, groups, args)
+            runner.setup(scheme=env.scheme, groups=groups, preprocess=env.preprocess, mac=mac)
+            u_explore = rng.random((T, 1, n), dtype=np.float32)
+            u_action = rng.random((T, 1, n), dtype=np.float32)
+            gaps = []
+            sel = mac.action_selector
+            orig = sel.select_action
+            step = [0]
+
+            def wrapped(agent_inputs, avail_actions, t_env, test_mode=False, beta=None):
+                top2 = th.topk(agent_inputs, 2, dim=-1).values
+                gaps.append(float((top2[..., 0] - top2[..., 1]).min()))
+                with _inject(th, R, [u_explore[step[0]]], u_action[step[0]]):
+                    a = orig(agent_inputs, avail_actions, t_env, test_mode=test_mode, beta=beta)
+                step[0] += 1
+                return a
+
+            sel.select_action = wrapped
+            np.random.seed(seed)
+            with th.no_grad():
+                batch = runner.run(test_mode=False)
+            if min(gaps) > 1e-3:
+                break
+        else:
+            raise RuntimeError("no seed with a safe Q gap")
+        out = {f"td_{k}": v.numpy().copy() for k, v in batch.data.transition_data.items()}
+        out.update({f"w_{k}": v.numpy().copy() for k, v in mac.agent.state_dict().items()})
+        prev0 = out["td_obs"][0, 0] * 0  # placeholder keeps key order stable
+        extra_out = {}
+        if env_name == "mock_constellation_env":
+            np.random.seed(seed)
+            extra_out["prev0"] = np.random.choice(m, n, replace=False)  # what env.reset drew (mock_constellation_env.py:105)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), S=S, n=n, m=m, T=T, L=3, lambda_=0.5, M=extra.get("M", 0),
+                            N=extra.get("N", 0), u_explore=u_explore, u_action=u_action, eps=0.4, min_gap=min(gaps),
+                            t_env_after=runner.t_env, return_mean=log.stats["return_mean"][-1][1], **extra_out, **out)
+
+
+if __name__ == "__main__" and "--runner-only" in sys.argv:
+    golden_runner(ref_import.ref_modules())

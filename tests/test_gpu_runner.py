@@ -243,3 +243,34 @@ def test_cuda_graph_rollout_equals_eager(env_name):
     assert outs[0][0] == outs[1][0] and outs[0][0][0] > outs[0][0][-1]  # epsilon annealed identically
     for a, b in zip(outs[0][1], outs[1][1]):
         assert th.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["runner_mock", "runner_real"])
+def test_episode_runner_matches_reference_runner_golden(name):
+    """REGISTRY["episode"] runner + BasicMAC vs the EpisodeBatch produced by the UNMODIFIED reference EpisodeRunner +
+    BasicMAC + RNNAgent + epsilon_greedy (tests/golden/make_golden.py: golden_runner), same weights, same injected
+    draws, obs_last_action and obs_agent_id on.  Every buffer field must be identical."""
+    import os
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")))
+    n, m, T = int(g["n"]), int(g["m"]), int(g["T"])
+    if name == "runner_mock":
+        env_name = "mock_constellation_env"
+        env_args = dict(n=n, m=m, T=T, L=3, lambda_=0.5, sat_prox_mat=g["S"])
+        kw = {"prev0": g["prev0"][None]}
+    else:
+        env_name = "real_constellation_env"
+        env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, L=3, lambda_=0.5, N=int(g["N"]), M=int(g["M"]),
+                        sat_prox_mat=g["S"], graphs=1)
+        kw = {}
+    args = make_args(env_name, env_args, 1, runner="episode", epsilon_start=0.4, epsilon_finish=0.4, epsilon_anneal_time=1,
+                     obs_agent_id=True, obs_last_action=True)
+    runner, mac, buffer, logger = build(args)
+    mac.agent.load_state_dict({k[2:]: th.tensor(v) for k, v in g.items() if k.startswith("w_")})
+    DrawInjector(mac.action_selector, {"u_explore": g["u_explore"], "u_action": g["u_action"]})
+    batch = runner.run(test_mode=False, **kw)
+    for k, v in batch.data.transition_data.items():
+        want = th.tensor(g["td_" + k])
+        assert th.equal(v.cpu(), want), f"field {k} differs from the reference runner's batch"
+    assert runner.t_env == int(g["t_env_after"])
+    assert logger.stats["return_mean"][-1][1] == pytest.approx(float(g["return_mean"]), rel=1e-3)  # fp16 rewards in the log sum
