@@ -139,6 +139,32 @@ __device__ __forceinline__ __half to_out_f<__half>(float v) { return __float2hal
 __device__ __forceinline__ float out_to_f(float v) { return v; }
 __device__ __forceinline__ float out_to_f(__half v) { return __half2float(v); }
 
+// L2 residency control: the window is read twice by the same CTA a few microseconds apart (keys, then gather
+// tile), while the obs / agent-input stores in between are never re-read by this kernel.  First read = evict_last,
+// second read and all bulk stores = evict_first, so the re-read hits L2 instead of going back to HBM.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_hint4(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void stg_hint4(void* p, const uint4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+               "l"(pol)
+               : "memory");
+}
+
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
@@ -185,6 +211,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   int32_t* qRows = sQ + 4;
   int32_t* qNbr = sQ + 4 + n;
 
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
   const size_t env_plane0 = d.shared_planes ? (size_t)0 : (size_t)b * T;
   const float* env_planes = p.planes + env_plane0 * nm;
   const SapBatchView& vw = p.view;
@@ -417,10 +444,10 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
       float4 va[4], vb[4];
 #pragma unroll
       for (int l = 0; l < 4; ++l)
-        if (l < Leff) va[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4 * 4);
+        if (l < Leff) va[l] = ldg_hint4(win + (size_t)l * nm + (size_t)e4 * 4, pol_keep);
 #pragma unroll
       for (int l = 0; l < 4; ++l)
-        if (l < Leff && has_b) vb[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4b * 4);
+        if (l < Leff && has_b) vb[l] = ldg_hint4(win + (size_t)l * nm + (size_t)e4b * 4, pol_keep);
       finish(e4, i0, j0 << 2, va);
       if (has_b) finish(e4b, i1, j1 << 2, vb);
       i0 = i1 + step_i;
@@ -637,8 +664,8 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
       for (int l = 0; l < 4; ++l) {
         va[l] = make_float4(0.f, 0.f, 0.f, 0.f);
         vb[l] = va[l];
-        if (l < Leff) va[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4 * 4);
-        if (l < Leff && has_b) vb[l] = ldg_stream4(win + (size_t)l * nm + (size_t)e4b * 4);
+        if (l < Leff) va[l] = ldg_hint4(win + (size_t)l * nm + (size_t)e4 * 4, pol_drop);
+        if (l < Leff && has_b) vb[l] = ldg_hint4(win + (size_t)l * nm + (size_t)e4b * 4, pol_drop);
       }
 #pragma unroll
       for (int l = 0; l < 4; ++l)
@@ -728,17 +755,18 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
 #pragma unroll 4
       for (int c = tid; c < chunks; c += kThreads) {
         const uint4 v = *reinterpret_cast<const uint4*>(ssrc + (size_t)c * 16);
-        *reinterpret_cast<uint4*>(gdst + (size_t)c * 16) = v;
+        stg_hint4(gdst + (size_t)c * 16, v, pol_drop);
         if (adst) {
           if (sizeof(OutT) == 2) {
             const __half2* h = reinterpret_cast<const __half2*>(&v);
             const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
                          f3 = __half22float2(h[3]);
-            float4* o = reinterpret_cast<float4*>(adst + (size_t)c * 8);
-            o[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
-            o[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+            float* o = adst + (size_t)c * 8;
+            const float4 lo4 = make_float4(f0.x, f0.y, f1.x, f1.y), hi4 = make_float4(f2.x, f2.y, f3.x, f3.y);
+            stg_hint4(o, *reinterpret_cast<const uint4*>(&lo4), pol_drop);
+            stg_hint4(o + 4, *reinterpret_cast<const uint4*>(&hi4), pol_drop);
           } else {
-            *reinterpret_cast<uint4*>(adst + (size_t)c * 4) = v;
+            stg_hint4(adst + (size_t)c * 4, v, pol_drop);
           }
         }
       }
