@@ -280,7 +280,7 @@ def gpu_arm(opts, w):
 
     for _ in range(opts.warmup):
         step()
-    launches0 = runner.kernel_launches
+    launches0 = runner.kernel_launches + buffer.kernel_launches
     sampler = ClockSampler(local_rank)
     barrier()
     th.cuda.synchronize()
@@ -309,7 +309,7 @@ def gpu_arm(opts, w):
         runner.args.use_cuda_graph = True
     ms = e0.elapsed_time(e1)
     kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(len(ev_pairs), 1)
-    launches = runner.kernel_launches - launches0 + opts.steps * n_fields
+    launches = runner.kernel_launches + buffer.kernel_launches - launches0  # selector + env kernels (+ replay copies, if any)
     t = th.tensor([ms, kern_ms], dtype=th.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,7 +341,7 @@ def gpu_arm(opts, w):
     except Exception:
         pass
     cpu = None
-    if not opts.no_cpu:
+    if not opts.no_cpu and world == 1:
         v, cores, sample, _ = cpu_port_throughput(w, weights, target_seconds=opts.cpu_seconds)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
     line = {
@@ -379,17 +379,19 @@ def e2e_leg(opts, w, runner, buffer, planes, dev, rank, world):
     from marl_sap_b200 import _lib
 
     B, n, m, T = w["B"], w["n"], w["m"], w["T"]
-    bytes_in = B * n * m * T * 4
+    per_env = n * m * T * 4
+    bytes_in = B * per_env
+    chunk = max(1, min(B, (256 << 20) // per_env))           # envs per H2D request
+    host_envs = min(B, max(chunk, ((2 << 30) // per_env) // chunk * chunk))  # pinned pool: <= 2 GiB per rank, cycled
     free_host = psutil.virtual_memory().available
     free_dev, _ = th.cuda.mem_get_info(dev)
-    if bytes_in * 1.5 > free_host or bytes_in * 1.3 > free_dev:
+    if host_envs * per_env * world * 2 > free_host or bytes_in * 1.3 > free_dev:
         return {"value": None, "unit": "agent-steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 0,
                 "skipped": f"not enough memory (host free {free_host >> 30} GiB, device free {free_dev >> 30} GiB)"}
     lib = _lib.load()
-    host = th.empty(B, n, m, T, dtype=th.float32, pin_memory=True)
-    chunk = max(1, min(B, (256 << 20) // (n * m * T * 4)))
-    for b0 in range(0, B, chunk):  # fill the pinned buffer with distinct synthetic values
-        b1 = min(B, b0 + chunk)
+    host = th.empty(host_envs, n, m, T, dtype=th.float32, pin_memory=True)
+    for b0 in range(0, host_envs, chunk):  # fill the pinned pool with distinct synthetic values
+        b1 = min(host_envs, b0 + chunk)
         host[b0:b1].copy_(th.rand(b1 - b0, n, m, T, device=dev))
     planes2 = th.empty_like(planes)
     staging = [th.empty(chunk * n * m * T, dtype=th.float32, device=dev) for _ in range(2)]
@@ -407,7 +409,8 @@ def e2e_leg(opts, w, runner, buffer, planes, dev, rank, world):
             copy_stream.wait_event(consumed[slot])  # the rollout that read this buffer has finished
             for i, b0 in enumerate(range(0, B, chunk)):
                 b1 = min(B, b0 + chunk)
-                _lib.check(lib.sap_benefit_upload_host(host[b0:b1].data_ptr(), staging[i % 2].data_ptr(), dst[b0:b1].data_ptr(),
+                h0 = b0 % host_envs  # the pinned pool is cycled when it is smaller than the batch
+                _lib.check(lib.sap_benefit_upload_host(host[h0:h0 + (b1 - b0)].data_ptr(), staging[i % 2].data_ptr(), dst[b0:b1].data_ptr(),
                                                        b1 - b0, n, m, T, copy_stream.cuda_stream), "sap_benefit_upload_host")
             ready[slot].record(copy_stream)
 
@@ -445,7 +448,8 @@ def e2e_leg(opts, w, runner, buffer, planes, dev, rank, world):
     val = world * B * n * T * steps / (ms.item() * 1e-3)
     return {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
             "steps": steps, "ms_per_step": ms.item() / steps,
-            "note": "benefit upload of episode e+1 overlaps the rollout of episode e (copy stream)"}
+            "note": "benefit upload of episode e+1 overlaps the rollout of episode e (copy stream); every episode uploads "
+                    f"all {B} envs' benefits from a pinned pool of {host_envs} envs ({host_envs * per_env >> 20} MiB, cycled)"}
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -457,7 +461,8 @@ def reference_arm(opts, w):
     weights = default_agent_weights(w)
     vals = []
     for i in range(opts.warmup + opts.steps):
-        v, cores, sample, wall = cpu_port_throughput(w, weights, target_seconds=opts.cpu_seconds / 2)
+        per_step = min(opts.cpu_seconds / 2, 150.0 / max(1, opts.warmup + opts.steps))  # whole run within a few minutes
+        v, cores, sample, wall = cpu_port_throughput(w, weights, target_seconds=per_step)
         if i >= opts.warmup:
             vals.append((v, wall))
     vals.sort()

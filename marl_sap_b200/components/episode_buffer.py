@@ -268,6 +268,7 @@ class ReplayBuffer(EpisodeBatch):
         self.buffer_size = buffer_size
         self.buffer_index = 0
         self.episodes_in_buffer = 0
+        self.kernel_launches = 0  # sap_buffer_insert / sap_buffer_gather launches issued so far
 
     # ------------------------------------------------------------------ ring insert (:244-259)
     def view_next(self, n_new):
@@ -309,6 +310,7 @@ class ReplayBuffer(EpisodeBatch):
                     row_bytes = dst[0].numel() * dst.element_size()
                     _lib.check(lib.sap_buffer_insert(dst.data_ptr(), src.data_ptr(), row_bytes, self.buffer_size,
                                                      self.buffer_index, 0, n_new, stream), "sap_buffer_insert")
+                    self.kernel_launches += 1
             end = self.buffer_index + n_new
             self.episodes_in_buffer = max(self.episodes_in_buffer, min(end, self.buffer_size))
             self.buffer_index = end % self.buffer_size
@@ -369,6 +371,7 @@ class ReplayBuffer(EpisodeBatch):
                 row_bytes = src[0].numel() * src.element_size()
                 _lib.check(lib.sap_buffer_gather(dst.data_ptr(), src.data_ptr(), ids.data_ptr(), row_bytes, count, stream),
                            "sap_buffer_gather")
+                self.kernel_launches += 1
                 getattr(new_data, store_name)[k] = dst
         ret = EpisodeBatch(self.scheme, self.groups, count, self.max_seq_length, data=new_data, device=self.device,
                            lazy=self.lazy)

@@ -303,3 +303,83 @@ def test_single_env_facade_kat1():
     assert env3.n == 4 and env3._impl is None
     bh = env.beta_hat(g["beta"][0], np.arange(4))
     np.testing.assert_allclose(bh[..., 0], g["beta"][0][..., 0] - 0.5 * (1 - np.eye(4)) * (g["beta"][0].sum(-1) > 1e-12))
+
+
+def test_real_env_full_size_fast_equals_generic(monkeypatch):
+    """BASELINE shape 100 x 100 (M = N = 10, L = 3, fp16 scheme) at a few hundred envs: the shared-memory fast kernel and
+    the generic float64 kernel must produce identical bytes (obs, rewards, top-M, agent input) step after step."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    B, n, m, T, L, M, N = 296, 100, 100, 6, 3, 10, 10
+    g = th.Generator().manual_seed(3)
+    S = th.rand(B, n, m, T, generator=g)
+    S[:, :, ::7] = 0.0            # inactive tasks: exact zero ties
+    S[:40] = (S[:40] * 8).round() / 8  # coarse grid: duplicate sums above zero
+    acts = [th.randint(0, m, (B, n), generator=g).cuda() for _ in range(T)]
+    outs = []
+    for generic in ("1", "0"):
+        monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
+        env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S.cuda())
+        batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
+        batch.agent_in = th.zeros(B, n, env.obs_size, device="cuda")
+        env.reset(batch)
+        ain = [batch.agent_in.clone()]
+        tops = [env.top.clone()]
+        for t in range(T):
+            env.step(acts[t], batch)
+            ain.append(batch.agent_in.clone())
+            tops.append(env.top.clone())
+        outs.append((batch["obs"].clone(), batch["rewards"].clone(), th.stack(ain), th.stack(tops[:-1]), env.ep_return.clone()))
+    for a, b in zip(*outs):
+        assert th.equal(a, b)
+    obs, _, ain, _, _ = outs[1]
+    assert th.equal(ain, obs.permute(1, 0, 2, 3).float())  # agent_in == float(obs[:, t]) for every t
+
+
+def test_real_env_constellation_scale_matches_oracle():
+    """324 agents x 450 tasks (real_constellation_env.yaml): too large for the shared-memory path, runs the generic kernel."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    rng = np.random.default_rng(11)
+    B, n, m, T, L, M, N = 2, 324, 450, 3, 3, 10, 10
+    S = O.gen_ref_like(rng, B, n, m, T, p_active=0.05)
+    acts = rng.integers(0, m, size=(T, B, n))
+    st = O.RealState(S.astype(np.float64), L, M, N, 0.5)
+    want = O.rollout(st, lambda t, pre: acts[t], "real")
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S)
+    assert env.scratch is not None  # float64 sums live in an L2-resident scratch buffer at this size
+    batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
+    env.reset(batch)
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+    assert th.equal(batch["obs"].cpu(), _cast(want["obs"], th.float16))
+    assert th.equal(batch["rewards"].cpu(), _cast(want["rewards"], th.float16))
+    assert th.equal(batch["prev_assigns"].cpu(), _cast(want["prev_assigns"], th.int16))
+
+
+def test_real_env_bench_batch_properties():
+    """The bench configuration itself (4096 envs x 100 x 100): conflict histogram, sorted top-M, determinism."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    B, n, m, T, L, M, N = 4096, 100, 100, 3, 3, 10, 10
+    g = th.Generator(device="cuda").manual_seed(5)
+    planes = th.rand(B, T, n, m, device="cuda", generator=g)
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5)
+    env.set_planes(planes)
+    batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
+    acts = [th.randint(0, m, (B, n), device="cuda", generator=g) for _ in range(T)]
+    sums = []
+    for rep in range(2):
+        env.reset(batch)
+        for t in range(T):
+            env.step(acts[t], batch)
+            if rep == 0 and t + 1 < T:
+                tot = planes[:, t + 1:t + 1 + L].double().sum(1)
+                tv = tot.gather(2, env.top.long())
+                assert bool((tv[..., :-1] >= tv[..., 1:]).all())
+                assert bool((tot.scatter(2, env.top.long(), float("-inf")).max(-1).values <= tv[..., -1]).all())
+                want_cnt = th.zeros(B, m, dtype=th.int32, device="cuda").scatter_add_(1, acts[t], th.ones_like(acts[t], dtype=th.int32))
+                assert th.equal(env.counts, want_cnt)
+        sums.append((batch["obs"].float().sum(dtype=th.float64).item(), batch["rewards"].float().sum(dtype=th.float64).item(),
+                     batch["obs"].clone()))
+    assert sums[0][0] == sums[1][0] and sums[0][1] == sums[1][1] and th.equal(sums[0][2], sums[1][2])
