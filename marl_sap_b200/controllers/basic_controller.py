@@ -1,8 +1,15 @@
-"""Shared-parameter multi-agent controller (mirror of /root/reference/src/controllers/basic_controller.py:7-101).
+"""Shared-parameter multi-agent controller: glue between the episode batch, the torch agent and the kernel selector.
 
-Glue only: build inputs -> torch agent forward -> kernel selector.  A single on-device agent is used for both
-training and selection (the reference's CPU "selector_agent" copy, :69-75, is what
-``use_mps_action_selection=True`` disables); ``update_action_selector_agent`` is kept as a no-op.
+Keeps the interface of /root/reference/src/controllers/basic_controller.py:7-101 (``select_actions``, ``forward``,
+``init_hidden``, ``parameters``, ``load_state``, ``cuda``, ``save_models``, ``load_models``,
+``update_action_selector_agent``, ``_build_inputs``, ``_get_input_shape``; attributes ``agent``, ``action_selector``,
+``hidden_states``), with two differences that matter on a GPU:
+
+  * one device-resident agent serves training and action selection (the reference keeps a second CPU
+    "selector_agent" unless ``use_mps_action_selection`` is set, :69-75); ``update_action_selector_agent`` is a no-op;
+  * when the runner provides ``batch.agent_in`` (fp32 staging rows the env kernel already filled with
+    ``float(obs[:, t])``), the per-step ``obs[:, t].float()`` / ``cat`` of :77-92 is skipped and only the optional
+    last-action / agent-id columns are written.
 """
 import torch as th
 
@@ -10,37 +17,82 @@ from ..action_selectors import REGISTRY as action_REGISTRY
 from ..modules.agents import REGISTRY as agent_REGISTRY
 
 
+def _obs_width(scheme):
+    v = scheme["obs"]["vshape"]
+    return v if isinstance(v, int) else v[0]
+
+
 class BasicMAC:
     def __init__(self, scheme, groups, args):
-        self.n = args.n
         self.args = args
-        input_shape = self._get_input_shape(scheme)
-        self._build_agents(input_shape)
+        self.n = args.n
         self.agent_output_type = args.agent_output_type
+        self.agent = agent_REGISTRY[args.agent](self._get_input_shape(scheme), args)
+        self.selector_agent = self.agent
         self.action_selector = action_REGISTRY[args.action_selector](args)
         self.hidden_states = None
+        self._filtered = type(self.action_selector).__name__.startswith("Filtered")
 
+    # ------------------------------------------------------------------ acting
     def select_actions(self, ep_batch, t_ep, t_env, bs=slice(None), test_mode=False):
-        agent_outputs = self.forward(ep_batch, t_ep, test_mode=test_mode, action_selection_mode=True)
-        avail_actions = ep_batch["avail_actions"][:, t_ep]
-        top = getattr(ep_batch, "top_agent_tasks", None)
-        if top is not None and hasattr(self.action_selector, "select_action") and \
-                self.action_selector.__class__.__name__.startswith("Filtered"):
-            return self.action_selector.select_action(agent_outputs[bs], avail_actions[bs], t_env, test_mode=test_mode,
-                                                      top=top[bs])
-        beta = ep_batch["beta"][bs, t_ep] if self.action_selector.__class__.__name__.startswith("Filtered") else None
-        return self.action_selector.select_action(agent_outputs[bs], avail_actions[bs], t_env, test_mode=test_mode, beta=beta)
+        q = self.forward(ep_batch, t_ep, test_mode=test_mode, action_selection_mode=True)[bs]
+        avail = ep_batch["avail_actions"][:, t_ep][bs]
+        if not self._filtered:
+            return self.action_selector.select_action(q, avail, t_env, test_mode=test_mode, beta=None)
+        top = getattr(ep_batch, "top_agent_tasks", None)  # the env's own top-M task indices (computed once)
+        if top is not None:
+            return self.action_selector.select_action(q, avail, t_env, test_mode=test_mode, top=top[bs])
+        return self.action_selector.select_action(q, avail, t_env, test_mode=test_mode, beta=ep_batch["beta"][bs, t_ep])
 
     def forward(self, ep_batch, t, test_mode=False, action_selection_mode=False):
-        agent_inputs = self._build_inputs(ep_batch, t)
-        agent_outs, self.hidden_states = self.agent(agent_inputs, self.hidden_states)
+        outs, self.hidden_states = self.agent(self._build_inputs(ep_batch, t), self.hidden_states)
         if self.agent_output_type == "pi_logits":
-            agent_outs = th.nn.functional.softmax(agent_outs, dim=-1)
-        return agent_outs.view(ep_batch.batch_size, self.n, -1)
+            outs = th.softmax(outs, dim=-1)
+        return outs.view(ep_batch.batch_size, self.n, -1)
 
     def init_hidden(self, batch_size):
-        self.hidden_states = self.agent.init_hidden().unsqueeze(0).expand(batch_size, self.n, -1)
+        h0 = self.agent.init_hidden()  # [1, hidden]
+        self.hidden_states = h0.unsqueeze(0).expand(batch_size, self.n, -1)
 
+    # ------------------------------------------------------------------ agent inputs
+    def _get_input_shape(self, scheme):
+        width = _obs_width(scheme)
+        if self.args.obs_last_action:
+            width += scheme["actions_onehot"]["vshape"][0]
+        if self.args.obs_agent_id:
+            width += self.n
+        return width
+
+    def _build_inputs(self, batch, t):
+        staged = getattr(batch, "agent_in", None)
+        if staged is not None and getattr(batch, "agent_in_t", None) == t:
+            return self._finish_staged_inputs(batch, t, staged)
+        rows = batch.batch_size * self.n
+        parts = [batch["obs"][:, t].float().reshape(rows, -1)]
+        if self.args.obs_last_action:
+            prev = batch["actions_onehot"][:, t - 1] if t > 0 else th.zeros_like(batch["actions_onehot"][:, 0])
+            parts.append(prev.reshape(rows, -1))
+        if self.args.obs_agent_id:
+            eye = th.eye(self.n, device=batch.device)
+            parts.append(eye.unsqueeze(0).expand(batch.batch_size, -1, -1).reshape(rows, -1))
+        return parts[0] if len(parts) == 1 else th.cat(parts, dim=1)
+
+    def _finish_staged_inputs(self, batch, t, staged):
+        """Columns [0, obs) already hold float(obs[:, t]) (written by the env kernel); fill the optional rest."""
+        col = _obs_width(batch.scheme)
+        if self.args.obs_last_action:
+            m = batch.scheme["actions_onehot"]["vshape"][0]
+            block = staged[:, :, col:col + m]
+            block.zero_()
+            if t > 0:
+                block.scatter_(2, batch["actions"][:, t - 1].long(), 1.0)
+            col += m
+        if self.args.obs_agent_id and not getattr(batch, "agent_in_has_ids", False):
+            staged[:, :, col:col + self.n] = th.eye(self.n, device=staged.device)
+            batch.agent_in_has_ids = True
+        return staged.view(batch.batch_size * self.n, -1)
+
+    # ------------------------------------------------------------------ parameters / checkpoints (agent.th, :62-67)
     def parameters(self):
         return self.agent.parameters()
 
@@ -54,49 +106,9 @@ class BasicMAC:
         th.save(self.agent.state_dict(), "{}/agent.th".format(path))
 
     def load_models(self, path):
-        self.agent.load_state_dict(th.load("{}/agent.th".format(path), map_location=lambda storage, loc: storage))
+        state = th.load("{}/agent.th".format(path), map_location=lambda storage, loc: storage)
+        self.agent.load_state_dict(state)
         self.update_action_selector_agent()
 
-    def _build_agents(self, input_shape):
-        self.agent = agent_REGISTRY[self.args.agent](input_shape, self.args)
-        self.selector_agent = self.agent  # one device-resident agent serves both roles
-
     def update_action_selector_agent(self):
-        return None
-
-    def _build_inputs(self, batch, t):
-        bs = batch.batch_size
-        staged = getattr(batch, "agent_in", None)
-        if staged is not None and getattr(batch, "agent_in_t", None) == t:
-            # the env kernel already wrote float(obs[:, t]) into columns [0, obs_size) of the staging rows
-            o = batch.scheme["obs"]["vshape"]
-            o = o if isinstance(o, int) else o[0]
-            if self.args.obs_last_action:
-                m = batch.scheme["actions_onehot"]["vshape"][0]
-                staged[:, :, o:o + m] = 0
-                if t > 0:
-                    staged[:, :, o:o + m].scatter_(2, batch["actions"][:, t - 1].long(), 1.0)
-                o += m
-            if self.args.obs_agent_id and getattr(batch, "agent_in_eye_t", None) is None:
-                staged[:, :, o:o + self.n] = th.eye(self.n, device=staged.device)
-                batch.agent_in_eye_t = True
-            return staged.view(bs * self.n, -1)
-        inputs = [batch["obs"][:, t].float()]
-        if self.args.obs_last_action:
-            if t == 0:
-                inputs.append(th.zeros_like(batch["actions_onehot"][:, t]))
-            else:
-                inputs.append(batch["actions_onehot"][:, t - 1])
-        if self.args.obs_agent_id:
-            inputs.append(th.eye(self.n, device=batch.device).unsqueeze(0).expand(bs, -1, -1))
-        if len(inputs) == 1:
-            return inputs[0].reshape(bs * self.n, -1)
-        return th.cat([x.reshape(bs * self.n, -1) for x in inputs], dim=1)
-
-    def _get_input_shape(self, scheme):
-        input_shape = scheme["obs"]["vshape"]
-        if self.args.obs_last_action:
-            input_shape += scheme["actions_onehot"]["vshape"][0]
-        if self.args.obs_agent_id:
-            input_shape += self.n
-        return input_shape
+        return None  # single agent: nothing to synchronise
