@@ -745,31 +745,39 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
         if (p.top_out) p.top_out[((size_t)b * n + i) * M + q] = j;
       }
     }
+    // generic-proxy writes of the staged rows must be visible to the async proxy (TMA) before the barrier
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const size_t bytes = (p.debug_skip_redo & 16) ? 0 : (size_t)rows * row_bytes;
     const unsigned char* ssrc = stage + phase;
     if (phase == 0 && (bytes & 15) == 0 && (!ain || ain_flat)) {
-      // aligned block: 16 bytes per thread and iteration to the obs slot, plus its fp32 image for the agent network
+      // aligned block.  The obs rows leave shared memory with ONE TMA bulk store (cp.async.bulk.global.shared::cta)
+      // issued by thread 0; meanwhile all threads widen the same rows to fp32 for the agent network (128-bit stores).
+      if (tid == 0 && bytes > 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                     "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"((uint32_t)bytes), "l"(pol_drop)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       float* adst = ain ? ain + (size_t)r0 * obs_size : nullptr;  // rows are contiguous when ain_row == obs_size
-      const int chunks = (int)(bytes >> 4);
+      const int chunks = adst ? (int)(bytes >> 4) : 0;
 #pragma unroll 4
       for (int c = tid; c < chunks; c += kThreads) {
         const uint4 v = *reinterpret_cast<const uint4*>(ssrc + (size_t)c * 16);
-        stg_hint4(gdst + (size_t)c * 16, v, pol_drop);
-        if (adst) {
-          if (sizeof(OutT) == 2) {
-            const __half2* h = reinterpret_cast<const __half2*>(&v);
-            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
-                         f3 = __half22float2(h[3]);
-            float* o = adst + (size_t)c * 8;
-            const float4 lo4 = make_float4(f0.x, f0.y, f1.x, f1.y), hi4 = make_float4(f2.x, f2.y, f3.x, f3.y);
-            stg_hint4(o, *reinterpret_cast<const uint4*>(&lo4), pol_drop);
-            stg_hint4(o + 4, *reinterpret_cast<const uint4*>(&hi4), pol_drop);
-          } else {
-            stg_hint4(adst + (size_t)c * 4, v, pol_drop);
-          }
+        if (sizeof(OutT) == 2) {
+          const __half2* h = reinterpret_cast<const __half2*>(&v);
+          const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]),
+                       f3 = __half22float2(h[3]);
+          float* o = adst + (size_t)c * 8;
+          const float4 lo4 = make_float4(f0.x, f0.y, f1.x, f1.y), hi4 = make_float4(f2.x, f2.y, f3.x, f3.y);
+          stg_hint4(o, *reinterpret_cast<const uint4*>(&lo4), pol_drop);
+          stg_hint4(o + 4, *reinterpret_cast<const uint4*>(&hi4), pol_drop);
+        } else {
+          stg_hint4(adst + (size_t)c * 4, v, pol_drop);
         }
       }
+      // the staging rows may be overwritten once the bulk store has finished READING them
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     } else {
       size_t head = (16 - phase) & 15;
       if (head > bytes) head = bytes;
@@ -790,6 +798,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     }
     __syncthreads();
   }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores complete before exit
 }
 
 // One CTA per environment; the hardware block scheduler balances the (slightly uneven) per-env durations better
