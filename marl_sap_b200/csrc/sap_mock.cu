@@ -136,25 +136,44 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
   if (p.vec4) {
     // obs row i = (L+1) segments of m floats = (L+1)*m/4 float4; all rows of the env are contiguous.
     float* out = reinterpret_cast<float*>(vw.obs.ptr) + obs_base;
+    // Warp per agent row, lane per 4 tasks: no index arithmetic beyond adds, up to 4 independent 128-bit loads in
+    // flight per lane, every segment of a row leaves as one contiguous run.
     const int m4 = m >> 2, row4 = (L + 1) * m4;
-    const int total4 = n * row4;
-    for (int e = tid; e < total4; e += kThreads) {
-      const int i = e / row4, r = e - i * row4;
-      const int seg = r / m4, j4 = r - seg * m4;
-      float4 v;
-      if (seg == 0) {
-        const int a = act[i] - (j4 << 2);
-        v = make_float4(a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f, a == 3 ? 1.f : 0.f);
-      } else if (k_new + seg - 1 < T) {
-        v = ldg_stream4(reinterpret_cast<const float4*>(env_planes + ((size_t)(k_new + seg - 1) * n + i) * m) + j4);
-      } else {
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      stg_stream4(reinterpret_cast<float4*>(out) + e, v);
-      if (ain) {
-        float* dst = ain + i * ain_row + (r << 2);
-        if (p.ain_vec4) stg_stream4(reinterpret_cast<float4*>(dst), v);
-        else { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+    for (int i = warp; i < n; i += kWarps) {
+      float4* orow = reinterpret_cast<float4*>(out) + (size_t)i * row4;
+      float* arow = ain ? ain + i * ain_row : nullptr;
+      const int ai = act[i];
+      for (int j4 = lane; j4 < m4; j4 += 32) {
+        const int a = ai - (j4 << 2);
+        const float4 hot = make_float4(a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f, a == 3 ? 1.f : 0.f);
+        stg_stream4(orow + j4, hot);  // :107, :147  curr_assignment
+        if (arow) {
+          float* dst = arow + (j4 << 2);
+          if (p.ain_vec4) stg_stream4(reinterpret_cast<float4*>(dst), hot);
+          else { dst[0] = hot.x; dst[1] = hot.y; dst[2] = hot.z; dst[3] = hot.w; }
+        }
+        for (int seg0 = 1; seg0 <= L; seg0 += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int seg = seg0 + u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (seg <= L && k_new + seg - 1 < T)  // :108-112  zero rows past T
+              v[u] = ldg_stream4(reinterpret_cast<const float4*>(env_planes + ((size_t)(k_new + seg - 1) * n + i) * m) + j4);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int seg = seg0 + u;
+            if (seg <= L) {
+              stg_stream4(orow + seg * m4 + j4, v[u]);
+              if (arow) {
+                float* dst = arow + ((seg * m4 + j4) << 2);
+                if (p.ain_vec4) stg_stream4(reinterpret_cast<float4*>(dst), v[u]);
+                else { dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w; }
+              }
+            }
+          }
+        }
       }
     }
   } else {
