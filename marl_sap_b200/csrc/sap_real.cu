@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int obs_size = M * L + N * M * L + N * H * L + M;
   Smem s;
-  smem_layout(d, p.ms, p.tot_in_smem, &s, smem_raw);
-  double* tot = p.tot_in_smem ? s.tot : p.scratch + (size_t)b * n * p.ms;
+  smem_layout(d, p.ms, true, &s, smem_raw);
+  double* tot = s.tot;
   const int ms = p.ms;
   const float* env_planes = p.planes + (d.shared_planes ? (size_t)0 : (size_t)b * T * n * m);
   const SapBatchView& vw = p.view;
@@ -295,9 +295,10 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 int launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
-  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: exercise the generic kernel on small shapes
+  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: "1" generic kernel, "2" multi-CTA large path
   const char* skip = getenv("SAP_DEBUG_SKIP_REDO");
   p.debug_skip_redo = skip ? atoi(skip) : 0;  // bit 0: accept uncertified lists; other bits: timing ablations
+  if (force && force[0] == '2') return sap_real_large_launch(p, stream);
   if (!(force && force[0] == '1')) {
     int handled = 0;
     const int rc = sap_real_fast_try(p, stream, &handled);
@@ -306,11 +307,8 @@ int launch(RealParams& p, void* stream) {
   p.ms = (d.m & 1) ? d.m : d.m + 1;
   size_t with_tot = smem_layout(d, p.ms, true, nullptr, nullptr);
   p.tot_in_smem = with_tot <= kMaxSmem;
-  size_t bytes = p.tot_in_smem ? with_tot : smem_layout(d, p.ms, false, nullptr, nullptr);
-  SAP_REQUIRE(bytes <= kMaxSmem, SAP_E_SMEM, "sap_real: index lists need %zu bytes of shared memory (> %zu)", bytes,
-              kMaxSmem);
-  SAP_REQUIRE(p.tot_in_smem || p.scratch, SAP_E_SMEM,
-              "sap_real: n*m too large for shared memory; pass scratch of sap_real_scratch_doubles() doubles");
+  if (!p.tot_in_smem) return sap_real_large_launch(p, stream);  // one env over many CTAs (sap_real_large.cu)
+  const size_t bytes = with_tot;
   static thread_local size_t configured = 0;
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(sap_real_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
@@ -329,9 +327,11 @@ int launch(RealParams& p, void* stream) {
 
 extern "C" int64_t sap_real_scratch_doubles(const SapEnvDims* d) {
   if (!d) return 0;
+  const char* force = getenv("SAP_REAL_FORCE_GENERIC");
+  if (force && force[0] == '2') return sap_real_large_scratch_doubles(*d);
   int ms = (d->m & 1) ? d->m : d->m + 1;
   if (smem_layout(*d, ms, true, nullptr, nullptr) <= kMaxSmem) return 0;
-  return (int64_t)d->B * d->n * ms;
+  return sap_real_large_scratch_doubles(*d);
 }
 
 extern "C" int sap_real_reset(const SapEnvDims* dims, const float* planes, const float* plane_stats,

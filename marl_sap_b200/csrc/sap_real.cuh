@@ -16,7 +16,7 @@ struct RealParams {
   int32_t* counts_out;
   SapBatchView view;
   int32_t* top_out;
-  double* scratch;  // [B,n,ms] when tot does not fit shared memory
+  double* scratch;  // sap_real_scratch_doubles() doubles when tot does not fit shared memory (sap_real_large.cu)
   int is_reset;
   int debug_skip_redo;  // timing experiments only (SAP_DEBUG_SKIP_REDO=1): accept uncertified lists
   int tot_in_smem;
@@ -80,3 +80,7 @@ __device__ __forceinline__ void warp_select_cached(int len, int count, bool idx_
 // Launches the shared-memory-resident fast kernel when the problem fits it.
 // Returns SAP_OK / error like every entry point; *handled = 0 means "not eligible, use the generic kernel".
 int sap_real_fast_try(RealParams& p, void* stream, int* handled);
+
+// One environment spread over many CTAs, for shapes whose window sums do not fit shared memory (sap_real_large.cu).
+int sap_real_large_launch(RealParams& p, void* stream);
+int64_t sap_real_large_scratch_doubles(const SapEnvDims& d);

@@ -40,11 +40,12 @@ def _cast(x64, dtype):
 @pytest.mark.parametrize("name", REAL)
 @pytest.mark.parametrize("real_dtype", [th.float16, th.float32])
 @pytest.mark.parametrize("shared", [True, False])
-@pytest.mark.parametrize("generic", ["0", "1"])
+@pytest.mark.parametrize("generic", ["0", "1", "2"])
 def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, monkeypatch):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
-    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)  # "1": generic kernel, "0": shared-memory fast path
+    # "0": shared-memory fast path, "1": generic one-CTA-per-env kernel, "2": multi-CTA path of the large shapes
+    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
 
     g = _load(name)
     B = 3
@@ -89,7 +90,7 @@ def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, mo
     dict(B=2, n=16, m=16, T=3, L=1, M=10, N=10, gen="dense", seed=7),
     dict(B=2, n=12, m=200, T=3, L=3, M=10, N=10, gen="const", seed=8),
 ])
-@pytest.mark.parametrize("generic", ["0", "1"])
+@pytest.mark.parametrize("generic", ["0", "1", "2"])
 def test_real_env_matches_oracle(cfg, generic, monkeypatch):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
@@ -306,8 +307,8 @@ def test_single_env_facade_kat1():
 
 
 def test_real_env_full_size_fast_equals_generic(monkeypatch):
-    """BASELINE shape 100 x 100 (M = N = 10, L = 3, fp16 scheme) at a few hundred envs: the shared-memory fast kernel and
-    the generic float64 kernel must produce identical bytes (obs, rewards, top-M, agent input) step after step."""
+    """BASELINE shape 100 x 100 (M = N = 10, L = 3, fp16 scheme) at a few hundred envs: the shared-memory fast kernel, the
+    generic float64 kernel and the multi-CTA large-shape path must produce identical bytes (obs, rewards, top-M, agent input) step after step."""
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
     B, n, m, T, L, M, N = 296, 100, 100, 6, 3, 10, 10
@@ -317,7 +318,7 @@ def test_real_env_full_size_fast_equals_generic(monkeypatch):
     S[:40] = (S[:40] * 8).round() / 8  # coarse grid: duplicate sums above zero
     acts = [th.randint(0, m, (B, n), generator=g).cuda() for _ in range(T)]
     outs = []
-    for generic in ("1", "0"):
+    for generic in ("1", "2", "0"):
         monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
         env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S.cuda())
         batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
@@ -330,14 +331,14 @@ def test_real_env_full_size_fast_equals_generic(monkeypatch):
             ain.append(batch.agent_in.clone())
             tops.append(env.top.clone())
         outs.append((batch["obs"].clone(), batch["rewards"].clone(), th.stack(ain), th.stack(tops[:-1]), env.ep_return.clone()))
-    for a, b in zip(*outs):
-        assert th.equal(a, b)
-    obs, _, ain, _, _ = outs[1]
+    for a, b, c in zip(*outs):
+        assert th.equal(a, b) and th.equal(a, c)
+    obs, _, ain, _, _ = outs[2]
     assert th.equal(ain, obs.permute(1, 0, 2, 3).float())  # agent_in == float(obs[:, t]) for every t
 
 
 def test_real_env_constellation_scale_matches_oracle():
-    """324 agents x 450 tasks (real_constellation_env.yaml): too large for the shared-memory path, runs the generic kernel."""
+    """324 agents x 450 tasks (real_constellation_env.yaml): too large for one SM: runs the multi-CTA path."""
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
     rng = np.random.default_rng(11)
