@@ -216,12 +216,25 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   const float* env_planes = p.planes + env_plane0 * nm;
   const SapBatchView& vw = p.view;
 
+  // The reward phase is a chain of dependent global loads (k -> actions -> chosen benefits -> ...); everything that
+  // does not depend on an earlier load is issued up front so the chain costs two DRAM round trips, not five.
+  int a_mine = 0, pv_mine = 0;  // action / previous task of agent `tid`
+  if (!p.is_reset && tid < n) {
+    a_mine = min(max((int)p.actions[(size_t)b * n + tid], 0), m - 1);
+    pv_mine = p.prev[(size_t)b * n + tid];
+  }
   const int k_old = p.is_reset ? -1 : p.k[b];
   if (!p.is_reset && k_old >= T) return;
   const int k_new = k_old + 1;
   const bool done = k_new >= T;
   const int Leff = done ? 0 : min(L, T - k_new);
   const float* win = env_planes + (size_t)k_new * nm;
+  // per-plane {min, max} of the new window, also requested now (used by step 3 after the reward phase)
+  const bool own_scale = p.plane_stats && !kPrios && (reinterpret_cast<uintptr_t>(p.plane_stats) & 7) == 0;
+  float2 pst[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l)
+    if (own_scale && l < Leff) pst[l] = __ldg(reinterpret_cast<const float2*>(p.plane_stats) + (env_plane0 + k_new + l));
 
   if (tid == 0) {
     sQ[0] = 0;
@@ -241,22 +254,27 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
 
   // ------------------------------------------------------------------ 1. rewards at the old window (:135-164)
   if (!p.is_reset) {
+    float mine[4] = {0.f, 0.f, 0.f, 0.f};  // chosen benefits of agent `tid` over the old window, loaded before the barrier
+    if (tid < n) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        if (l < L && k_old + l < T) mine[l] = __ldg(env_planes + ((size_t)(k_old + l) * n + tid) * m + a_mine);
+    }
     for (int i = tid; i < n; i += kThreads) {
-      int a = (int)p.actions[(size_t)b * n + i];
-      a = min(max(a, 0), m - 1);
+      const int a = i == tid ? a_mine : min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
       atomicAdd(&sCnt[a], 1);
     }
     __syncthreads();
     double local_ret = 0.0;
     for (int i = tid; i < n; i += kThreads) {
-      int a = (int)p.actions[(size_t)b * n + i];
-      a = min(max(a, 0), m - 1);
-      const int pv = p.prev[(size_t)b * n + i];
+      const int a = i == tid ? a_mine : min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
+      const int pv = i == tid ? pv_mine : p.prev[(size_t)b * n + i];
       const double pr = kPrios ? sPrio[a] : 1.0;
       double sum = 0.0, b0 = 0.0;
-      for (int l = 0; l < L; ++l) {
-        if (k_old + l < T) {
-          const double v = (double)env_planes[((size_t)(k_old + l) * n + i) * m + a] * pr;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        if (l < L && k_old + l < T) {
+          const double v = (double)(i == tid ? mine[l] : env_planes[((size_t)(k_old + l) * n + i) * m + a]) * pr;
           if (l == 0) b0 = v;
           sum += v;
         }
@@ -287,7 +305,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     if (tid == 0) {
       double t = 0.0;
       for (int w = 0; w < kWarps; ++w) t += sRed[w];
-      p.ep_return[b] += t;
+      atomicAdd(&p.ep_return[b], t);  // one add per env and launch: same result as +=, without waiting for the load
       p.k[b] = k_new;
       if (vw.terminated.ptr)
         sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, done);
@@ -307,7 +325,8 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   if (vw.prev_assigns.ptr) {
     const int64_t base = sap_field_off(vw.prev_assigns, b, t_slot);
     for (int i = tid; i < n; i += kThreads)
-      sap_store_int(vw.prev_assigns.ptr, base + i, vw.prev_assigns.dtype, p.prev[(size_t)b * n + i]);
+      sap_store_int(vw.prev_assigns.ptr, base + i, vw.prev_assigns.dtype,
+                    p.is_reset ? i : (i == tid ? a_mine : p.prev[(size_t)b * n + i]));
   }
   if (vw.avail_actions.ptr) {
     const int64_t base = sap_field_off(vw.avail_actions, b, t_slot);
@@ -329,7 +348,32 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   }
 
   // ------------------------------------------------------------------ 3. bounds of the window sums -> key scale
-  {
+  // origin, power-of-two scale and sign class of the keys from (lo, sum of max |value|, max |prio|, any prio < 0)
+  auto key_scale = [&](double lo, double habs, double pabs, bool pneg, double& o_lo, double& o_scale, bool& o_nonneg) {
+    const bool nonneg = lo >= 0.0 && !pneg;
+    const double hi = habs * pabs * 1.0000001;  // >= every |window sum| (margin covers fp64 rounding)
+    int e2 = 0;
+    if (hi > 0.0) (void)frexp(hi, &e2);  // hi < 2^e2
+    const int ib0 = 32 - __clz(max(n, m));  // max(n, m) <= 2^ib - 1: index code 0 is never a real element
+    const int vb1 = 31 - ib0;               // bits of the fixed-point part
+    o_lo = nonneg ? 0.0 : -ldexp(1.0, e2);                               // origin
+    o_scale = hi > 0.0 ? ldexp(1.0, vb1 - e2 - (nonneg ? 0 : 1)) : 1.0;  // scale (power of two)
+    o_nonneg = nonneg;
+  };
+  double k_lo, k_scale;
+  bool k_nonneg;
+  if (own_scale) {
+    // common case: every thread derives the scale from the per-plane {min, max} metadata itself (L broadcast loads):
+    // no serial section, no barrier
+    float vmin = INFINITY, vabs = 0.f;
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (l < Leff) {
+        vmin = fminf(vmin, pst[l].x);
+        vabs += fmaxf(fabsf(pst[l].x), fabsf(pst[l].y));
+      }
+    key_scale((double)vmin, (double)vabs, 1.0, false, k_lo, k_scale, k_nonneg);
+  } else {
     float vmin = INFINITY, vabs = 0.f;  // per thread: min value and sum over planes of max |value|
     if (p.plane_stats) {
       if (tid == 0) {
@@ -378,29 +422,32 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
           pneg = pneg || sPrio[j] < 0.0;
         }
       }
-      const bool nonneg = sRed[64] >= 0.0 && !pneg;
-      const double hi = sRed[65] * pabs * 1.0000001;  // >= every |window sum| (margin covers fp64 rounding)
-      int e2 = 0;
-      if (hi > 0.0) (void)frexp(hi, &e2);  // hi < 2^e2
-      const int ib0 = 32 - __clz(max(n, m));  // max(n, m) <= 2^ib - 1: index code 0 is never a real element
-      const int vb1 = 31 - ib0;               // bits of the fixed-point part
-      sRed[66] = nonneg ? 0.0 : -ldexp(1.0, e2);                        // origin
-      sRed[67] = hi > 0.0 ? ldexp(1.0, vb1 - e2 - (nonneg ? 0 : 1)) : 1.0;  // scale (power of two)
-      sRed[68] = nonneg ? 1.0 : 0.0;
+      double o_lo, o_scale;
+      bool o_nonneg;
+      key_scale(sRed[64], sRed[65], pabs, pneg, o_lo, o_scale, o_nonneg);
+      sRed[66] = o_lo;
+      sRed[67] = o_scale;
+      sRed[68] = o_nonneg ? 1.0 : 0.0;
     }
     __syncthreads();
+    k_lo = sRed[66];
+    k_scale = sRed[67];
+    k_nonneg = sRed[68] != 0.0;
   }
   const int ib = 32 - __clz(max(n, m));
   const uint32_t imask = (1u << ib) - 1u;
   const uint32_t fixed_max = (1u << (31 - ib)) - 1u;
-  const double k_lo = sRed[66], k_scale = sRed[67];
-  const bool k_nonneg = sRed[68] != 0.0;
 
   // key of a float64 window sum: monotone; bit 0 = "conversion was not exact"
   auto make_key = [&](double tot) -> uint32_t {
+    // floor(y) for y >= 0 without float<->int conversion instructions (they run at a quarter of the fp64 rate and
+    // used to bound this pass): adding 2^52 rounds to the nearest integer, one compare turns that into the floor.
+    // (Floor, not nearest: an inexact key must mean "strictly between fx and fx + 1" for the certificates.)
     const double y = (tot - k_lo) * k_scale;  // exact when k_lo == 0 (power-of-two scale)
-    uint32_t fx = __double2uint_rz(y);
-    bool inexact = !k_nonneg || ((double)fx != y);
+    const double t = y + 4503599627370496.0;
+    const double r = t - 4503599627370496.0;
+    uint32_t fx = (uint32_t)__double2loint(t) - (r > y ? 1u : 0u);
+    bool inexact = !k_nonneg || (r != y);
     if (fx > fixed_max) {
       fx = fixed_max;
       inexact = true;
@@ -478,6 +525,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   }
   __syncthreads();
 
+  if (p.debug_skip_redo & 256) return;  // timing ablation: stop after the key pass
   // exact float64 window sum (the reference's beta.sum(-1), :190) straight from global memory: only the rare
   // lists that cannot be certified use it
   auto tot64 = [&](int a, int j) {
@@ -568,6 +616,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     }
   }
 
+  if (p.debug_skip_redo & 512) return;  // timing ablation: stop after the task lists
   // ------------------------------------------------------------------ 6. rivals (:203-206)
   for (int base = 0; base < n * TPL && !(p.debug_skip_redo & 4); base += kThreads) {
     const int g = base + tid;
@@ -614,6 +663,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   }
   __syncthreads();
 
+  if (p.debug_skip_redo & 128) return;  // timing ablation: stop after the rival lists
   // ------------------------------------------------------------------ 7. rivals' other top tasks (:212-217)
   // The M/2 best tasks of rival r outside D[i] under (value desc, idx desc) are the first M/2 entries of E[r]
   // not in D[i]; the reference lists them ascending, so they are stored reversed.
