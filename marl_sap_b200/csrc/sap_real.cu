@@ -295,10 +295,10 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 int launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
-  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: "1" generic kernel, "2" multi-CTA large path
+  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: "1" generic kernel, "2" / "3" multi-CTA large path (keyed / exact)
   const char* skip = getenv("SAP_DEBUG_SKIP_REDO");
   p.debug_skip_redo = skip ? atoi(skip) : 0;  // bit 0: accept uncertified lists; other bits: timing ablations
-  if (force && force[0] == '2') return sap_real_large_launch(p, stream);
+  if (force && (force[0] == '2' || force[0] == '3')) return sap_real_large_launch(p, stream);
   if (!(force && force[0] == '1')) {
     int handled = 0;
     const int rc = sap_real_fast_try(p, stream, &handled);
@@ -328,7 +328,7 @@ int launch(RealParams& p, void* stream) {
 extern "C" int64_t sap_real_scratch_doubles(const SapEnvDims* d) {
   if (!d) return 0;
   const char* force = getenv("SAP_REAL_FORCE_GENERIC");
-  if (force && force[0] == '2') return sap_real_large_scratch_doubles(*d);
+  if (force && (force[0] == '2' || force[0] == '3')) return sap_real_large_scratch_doubles(*d);
   int ms = (d->m & 1) ? d->m : d->m + 1;
   if (smem_layout(*d, ms, true, nullptr, nullptr) <= kMaxSmem) return 0;
   return sap_real_large_scratch_doubles(*d);

@@ -365,25 +365,27 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   if (own_scale) {
     // common case: every thread derives the scale from the per-plane {min, max} metadata itself (L broadcast loads):
     // no serial section, no barrier
-    float vmin = INFINITY, vabs = 0.f;
+    float vmin = INFINITY;
+    double vabs = 0.0;  // float64: a true bound of the sum of the per-plane maxima
 #pragma unroll
     for (int l = 0; l < 4; ++l)
       if (l < Leff) {
         vmin = fminf(vmin, pst[l].x);
-        vabs += fmaxf(fabsf(pst[l].x), fabsf(pst[l].y));
+        vabs += (double)fmaxf(fabsf(pst[l].x), fabsf(pst[l].y));
       }
-    key_scale((double)vmin, (double)vabs, 1.0, false, k_lo, k_scale, k_nonneg);
+    key_scale((double)vmin, vabs, 1.0, false, k_lo, k_scale, k_nonneg);
   } else {
-    float vmin = INFINITY, vabs = 0.f;  // per thread: min value and sum over planes of max |value|
+    float vmin = INFINITY;
+    double vabs = 0.0;  // min value and sum over planes of max |value| (float64: a true bound)
     if (p.plane_stats) {
       if (tid == 0) {
         for (int l = 0; l < Leff; ++l) {
           const float lo = p.plane_stats[2 * (env_plane0 + k_new + l)], hi = p.plane_stats[2 * (env_plane0 + k_new + l) + 1];
           vmin = fminf(vmin, lo);
-          vabs += fmaxf(fabsf(lo), fabsf(hi));
+          vabs += (double)fmaxf(fabsf(lo), fabsf(hi));
         }
         sRed[64] = (double)vmin;
-        sRed[65] = (double)vabs;
+        sRed[65] = vabs;
       }
     } else {  // no metadata: one extra read of the window
       float amax = 0.f;

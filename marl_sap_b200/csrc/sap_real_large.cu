@@ -3,64 +3,216 @@
 // sap_real.cu / sap_real_fast.cu (reference: real_constellation_env.py step :135-175, beta_hat :282-328,
 // _build_obs :177-230), decomposed so that one environment is spread over many CTAs:
 //
-//   K1 sap_real_large_tot    grid (tiles, B)   float64 window sums -> L2-resident scratch in BOTH layouts
-//                                              tot[b][agent][task] and totT[b][task][agent]; snapshot of k[b]
-//   K2 sap_real_large_lists  grid (n/8, B)     warp per agent: exact top-M (idx asc) and top-(M+M/2) (idx desc)
-//                                              lists of its row -> scratch
-//   K3 sap_real_large_main   grid (n/8, B)     warp per agent: rival scores from coalesced totT rows, exact top-N,
-//                                              rivals' other tasks, gather, obs / agent-input rows;
+//   K0 sap_real_large_prep   grid (B)          snapshot of k[b]; origin / power-of-two scale of the selection keys
+//   K1 sap_real_large_keys   grid (tiles, B)   float64 window sums -> L2-resident scratch in BOTH layouts,
+//                                              [agent][task] and [task][agent]
+//   K2 sap_real_large_lists  grid (n/64, B)    per agent: top-M (idx asc) and top-(M+M/2) (idx desc) task lists
+//   K3 sap_real_large_main   grid (n/8, B)     warp per agent: rival scores from coalesced [task][agent] rows,
+//                                              top-N rivals, rivals' other tasks, gather, obs / agent-input rows;
 //                                              chunk 0 also does the reward phase and advances k, prev
 //
-// Every selection is the exact float64 warp selection (values cached in registers), so there is no certificate /
-// redo logic here.  Float64 semantics as in the other kernels.
+// Two modes.  Keyed (used when the lists fit the 16-wide networks, like the fast kernel): the scratch holds 32-bit
+// fixed-point keys of the float64 sums (+ an "inexact" bit); lists come from sorting networks on packed
+// (key | index) words (K2) or from N+1 rounds of redux.max over register-resident packed scores (K3), and are
+// accepted only when PROVABLY equal to the float64 answer under the stable tie rules (strictly decreasing keys or
+// ties between exact keys); anything else is redone by the exact float64 warp selection.  Exact (any M, N): the
+// scratch holds the float64 sums and every selection is the exact warp selection.
+#include <stdlib.h>
+
 #include "sap_real.cuh"
+#include "sap_sortnet.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kMaxRowsPerCta = kThreads / 4;  // K2: 4 or 8 lanes per task list -> 64 or 32 lists per CTA
+constexpr int kES = 16;                       // stride of an E row (uint16 entries; K2 <= 15 in keyed mode)
+
+#define SAP_CE(a, b)            \
+  {                             \
+    uint32_t hi__ = max(a, b);  \
+    b = min(a, b);              \
+    a = hi__;                   \
+  }
 
 struct LargeScratch {
-  double* tot;      // [B][n][m]
-  double* totT;     // [B][m][n]
-  uint16_t* D;      // [B][n][M]
-  uint16_t* E;      // [B][n][K2]
+  double* scale;    // [B][4]  k_lo, k_scale, nonneg, -
   int32_t* ksnap;   // [B]
+  uint16_t* D;      // [B][n][M]
+  uint16_t* E;      // [B][n][es]  es = 16 in keyed mode (aligned 32-byte rows), K2 otherwise
+  uint32_t* K;      // keyed: [B][n][m]
+  uint32_t* KT;     // keyed: [B][m][n]
+  double* tot;      // exact: [B][n][m]
+  double* totT;     // exact: [B][m][n]
 };
 
 __host__ __device__ inline size_t dbl_of_bytes(size_t bytes) { return (bytes + 7) / 8; }
 
+__host__ __device__ inline bool large_keyed(const SapEnvDims& d) {
+  return d.M + d.M / 2 + 1 <= 16 && d.N + 1 <= 16 && d.n <= 511 && d.m <= 511;
+}
+
+// sized for the exact mode (float64 sums); the keyed mode uses half of the two big arrays
+__host__ __device__ inline int e_stride(const SapEnvDims& d) { return large_keyed(d) ? kES : d.M + d.M / 2; }
+
 __host__ __device__ inline size_t large_layout(const SapEnvDims& d, LargeScratch* s, double* base) {
-  const int K2 = d.M + d.M / 2;
+  const int K2 = e_stride(d);
   size_t off = 0;
-  const size_t o_tot = off;  off += (size_t)d.B * d.n * d.m;
-  const size_t o_totT = off; off += (size_t)d.B * d.m * d.n;
-  const size_t o_D = off;    off += dbl_of_bytes(sizeof(uint16_t) * (size_t)d.B * d.n * d.M);
-  const size_t o_E = off;    off += dbl_of_bytes(sizeof(uint16_t) * (size_t)d.B * d.n * K2);
-  const size_t o_k = off;    off += dbl_of_bytes(sizeof(int32_t) * (size_t)d.B);
+  const size_t o_scale = off; off += (size_t)d.B * 4;
+  const size_t o_k = off;     off += dbl_of_bytes(sizeof(int32_t) * (size_t)d.B);
+  const size_t o_D = off;     off += dbl_of_bytes(sizeof(uint16_t) * (size_t)d.B * d.n * d.M);
+  off = (off + 1) & ~(size_t)1;  // E rows 16-byte aligned
+  const size_t o_E = off;     off += dbl_of_bytes(sizeof(uint16_t) * (size_t)d.B * d.n * K2);
+  const size_t nm = (size_t)d.B * d.n * d.m;
+  const size_t o_a = off;     off += nm;
+  const size_t o_b = off;     off += nm;
   if (s) {
-    s->tot = base + o_tot;
-    s->totT = base + o_totT;
+    s->scale = base + o_scale;
+    s->ksnap = reinterpret_cast<int32_t*>(base + o_k);
     s->D = reinterpret_cast<uint16_t*>(base + o_D);
     s->E = reinterpret_cast<uint16_t*>(base + o_E);
-    s->ksnap = reinterpret_cast<int32_t*>(base + o_k);
+    s->K = reinterpret_cast<uint32_t*>(base + o_a);
+    s->KT = reinterpret_cast<uint32_t*>(base + o_b);
+    s->tot = base + o_a;
+    s->totT = base + o_b;
   }
   return off;
 }
 
-__device__ __forceinline__ int new_step(const RealParams& p, const int32_t* ksnap, int b) {
-  return p.is_reset ? 0 : ksnap[b] + 1;
+// exact float64 window sum (the reference's beta.sum(-1), :190) straight from the planes
+__device__ __forceinline__ double tot64(const RealParams& p, const float* win, int Leff, int a, int j) {
+  const double pr = p.prios ? (double)p.prios[j] : 1.0;
+  const size_t nm = (size_t)p.d.n * p.d.m;
+  double s = 0.0;
+  for (int l = 0; l < Leff; ++l) s += (double)win[(size_t)l * nm + (size_t)a * p.d.m + j] * pr;
+  return s;
 }
 
-// ---------------------------------------------------------------------------------------------------- K1
-__global__ void __launch_bounds__(kThreads) sap_real_large_tot(RealParams p) {
-  __shared__ double tile[32][33];
+// top-16 of a list under the packed order, kTPL adjacent lanes per list (same scheme as sap_real_fast.cu)
+template <int kTPL, typename KeyFn>
+__device__ __forceinline__ void group_top16(int len, int s, KeyFn key, uint32_t (&top)[16]) {
+  const int per = (len + kTPL - 1) / kTPL;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int e = s + kTPL * c;
+    top[c] = (e < len) ? key(e) : 0u;
+  }
+  SAP_SORT16(top);
+  for (int base = 16; base < per; base += 16) {
+    uint32_t ch[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int e = s + kTPL * (base + c);
+      ch[c] = (e < len) ? key(e) : 0u;
+    }
+    SAP_SORT16(ch);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) top[c] = max(top[c], ch[15 - c]);
+    SAP_BITONIC_MERGE16(top);
+  }
+#pragma unroll
+  for (int stride = 1; stride < kTPL; stride <<= 1) {
+    uint32_t ot[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) ot[c] = __shfl_xor_sync(SAP_FULL_MASK, top[15 - c], stride);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) top[c] = max(top[c], ot[c]);
+    SAP_BITONIC_MERGE16(top);
+  }
+}
+
+// env index of a CTA: grid = (chunks, min(B, 32768), ceil(B / 32768))
+constexpr int kEnvFold = 32768;
+__device__ __forceinline__ int env_of_block() { return (int)(blockIdx.z * kEnvFold + blockIdx.y); }
+
+// adjacent keys strictly decreasing, or ties between two EXACT keys (bit 0 clear): then the order is proven
+__device__ __forceinline__ bool pair_ok(uint32_t a, uint32_t b) { return a > b || (a == b && !(a & 1u)); }
+
+// ---------------------------------------------------------------------------------------------------- K0
+__global__ void __launch_bounds__(kThreads) sap_real_large_prep(RealParams p, int keyed) {
+  __shared__ double sv[4][kWarps];
   const SapEnvDims d = p.d;
-  const int b = blockIdx.y, n = d.n, m = d.m, T = d.T, L = d.L;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   LargeScratch s;
   large_layout(d, &s, p.scratch);
   const int k_old = p.is_reset ? -1 : p.k[b];
-  if (blockIdx.x == 0 && threadIdx.x == 0) s.ksnap[b] = k_old;
+  if (tid == 0) s.ksnap[b] = k_old;
+  const int k_new = k_old + 1;
+  if (!keyed || k_new >= d.T || k_old >= d.T) return;
+  const int Leff = min(d.L, d.T - k_new);
+  const size_t nm = (size_t)d.n * d.m;
+  const size_t plane0 = (d.shared_planes ? (size_t)0 : (size_t)b * d.T) + k_new;
+  float vmin = INFINITY;
+  double vabs = 0.0;  // sum over planes of max |value|, in float64 so that it is a true bound
+  if (p.plane_stats) {
+    for (int l = 0; l < Leff; ++l) {
+      const float lo = p.plane_stats[2 * (plane0 + l)], hi = p.plane_stats[2 * (plane0 + l) + 1];
+      vmin = fminf(vmin, lo);
+      vabs += (double)fmaxf(fabsf(lo), fabsf(hi));
+    }
+  } else {  // no metadata: one extra read of the window
+    const float* win = p.planes + plane0 * nm;
+    float amax = 0.f;
+    for (size_t e = tid; e < (size_t)Leff * nm; e += kThreads) {
+      const float v = win[e];
+      vmin = fminf(vmin, v);
+      amax = fmaxf(amax, fabsf(v));
+    }
+    vabs = (double)amax * Leff;
+  }
+  float pabs = 1.f, pneg = 0.f;
+  if (p.prios) {
+    pabs = 0.f;
+    for (int j = tid; j < d.m; j += kThreads) {
+      pabs = fmaxf(pabs, fabsf(p.prios[j]));
+      if (p.prios[j] < 0.f) pneg = 1.f;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    vmin = fminf(vmin, __shfl_xor_sync(SAP_FULL_MASK, vmin, off));
+    vabs = fmax(vabs, __shfl_xor_sync(SAP_FULL_MASK, vabs, off));
+    pabs = fmaxf(pabs, __shfl_xor_sync(SAP_FULL_MASK, pabs, off));
+    pneg = fmaxf(pneg, __shfl_xor_sync(SAP_FULL_MASK, pneg, off));
+  }
+  if (lane == 0) {
+    sv[0][warp] = vmin;
+    sv[1][warp] = vabs;
+    sv[2][warp] = pabs;
+    sv[3][warp] = pneg;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kWarps; ++w) {
+      vmin = fminf(vmin, (float)sv[0][w]);
+      vabs = fmax(vabs, sv[1][w]);
+      pabs = fmaxf(pabs, (float)sv[2][w]);
+      pneg = fmaxf(pneg, (float)sv[3][w]);
+    }
+    const bool nonneg = vmin >= 0.f && pneg == 0.f;
+    const double hi = vabs * (double)pabs * 1.0000001;  // >= every |window sum|
+    int e2 = 0;
+    if (hi > 0.0) (void)frexp(hi, &e2);  // hi < 2^e2
+    const int ib = 32 - __clz(max(d.n, d.m));
+    const int vb1 = 31 - ib;  // bits of the fixed-point part
+    s.scale[4 * b + 0] = nonneg ? 0.0 : -ldexp(1.0, e2);
+    s.scale[4 * b + 1] = hi > 0.0 ? ldexp(1.0, vb1 - e2 - (nonneg ? 0 : 1)) : 1.0;
+    s.scale[4 * b + 2] = nonneg ? 1.0 : 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- K1
+template <bool kKeyed>
+__global__ void __launch_bounds__(kThreads) sap_real_large_keys(RealParams p) {
+  __shared__ double tile_d[kKeyed ? 1 : 32][kKeyed ? 1 : 33];
+  __shared__ uint32_t tile_k[kKeyed ? 32 : 1][kKeyed ? 33 : 1];
+  const SapEnvDims d = p.d;
+  const int b = env_of_block(), n = d.n, m = d.m, T = d.T, L = d.L;
+  if (b >= d.B) return;
+  LargeScratch s;
+  large_layout(d, &s, p.scratch);
+  const int k_old = s.ksnap[b];
   const int k_new = k_old + 1;
   if (k_new >= T || k_old >= T) return;  // done: no window
   const int Leff = min(L, T - k_new);
@@ -68,46 +220,185 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_tot(RealParams p) {
   const int tiles_j = (m + 31) / 32;
   const int ti = blockIdx.x / tiles_j, tj = blockIdx.x - ti * tiles_j;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int ib = 32 - __clz(max(n, m));
+  const uint32_t fixed_max = (1u << (31 - ib)) - 1u;
+  const double k_lo = kKeyed ? s.scale[4 * b] : 0.0, k_scale = kKeyed ? s.scale[4 * b + 1] : 1.0;
+  const bool k_nonneg = kKeyed ? s.scale[4 * b + 2] != 0.0 : true;
   for (int r = ty; r < 32; r += kWarps) {
     const int i = ti * 32 + r, j = tj * 32 + tx;
     if (i < n && j < m) {
       const double pr = p.prios ? (double)p.prios[j] : 1.0;
       double sum = 0.0;
       for (int l = 0; l < Leff; ++l) sum += (double)win[((size_t)l * n + i) * m + j] * pr;  // :167-170, :190
-      s.tot[((size_t)b * n + i) * m + j] = sum;
-      tile[r][tx] = sum;
+      if (kKeyed) {
+        // monotone 32-bit image of the float64 sum: floor(sum * 2^s) and an "inexact" bit (see sap_real_fast.cu)
+        const double y = (sum - k_lo) * k_scale;
+        const double t = y + 4503599627370496.0, rr = t - 4503599627370496.0;
+        uint32_t fx = (uint32_t)__double2loint(t) - (rr > y ? 1u : 0u);
+        bool inexact = !k_nonneg || (rr != y);
+        if (fx > fixed_max) {
+          fx = fixed_max;
+          inexact = true;
+        }
+        const uint32_t key = (fx << 1) | (inexact ? 1u : 0u);
+        s.K[((size_t)b * n + i) * m + j] = key;
+        tile_k[r][tx] = key;
+      } else {
+        s.tot[((size_t)b * n + i) * m + j] = sum;
+        tile_d[r][tx] = sum;
+      }
     }
   }
   __syncthreads();
   for (int r = ty; r < 32; r += kWarps) {
     const int j = tj * 32 + r, i = ti * 32 + tx;
-    if (i < n && j < m) s.totT[((size_t)b * m + j) * n + i] = tile[tx][r];
+    if (i < n && j < m) {
+      if (kKeyed) s.KT[((size_t)b * m + j) * n + i] = tile_k[tx][r];
+      else s.totT[((size_t)b * m + j) * n + i] = tile_d[tx][r];
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------- K2
+template <bool kKeyed, int kTPL>
 __global__ void __launch_bounds__(kThreads) sap_real_large_lists(RealParams p) {
+  constexpr int kRowsPerCta = kThreads / kTPL;
+  __shared__ int32_t q_cnt;
+  __shared__ int32_t q_rows[kMaxRowsPerCta];
   const SapEnvDims d = p.d;
-  const int b = blockIdx.y, n = d.n, m = d.m, M = d.M, K2 = d.M + d.M / 2;
-  const int lane = threadIdx.x & 31, i = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int b = env_of_block(), n = d.n, m = d.m, M = d.M, K2 = d.M + d.M / 2;
+  if (b >= d.B) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   LargeScratch s;
   large_layout(d, &s, p.scratch);
-  if (i >= n || new_step(p, s.ksnap, b) >= d.T || (!p.is_reset && s.ksnap[b] >= d.T)) return;
-  const double* row = s.tot + ((size_t)b * n + i) * m;
+  const int k_old = s.ksnap[b], k_new = k_old + 1;
+  if (k_new >= d.T || k_old >= d.T) return;
+  const int Leff = min(d.L, d.T - k_new);
+  const float* win = p.planes + ((d.shared_planes ? (size_t)0 : (size_t)b * d.T) + k_new) * n * m;
+  const int row0 = blockIdx.x * kRowsPerCta, es = e_stride(d);
+  if (tid == 0) q_cnt = 0;
+  __syncthreads();
+  if (kKeyed) {
+    const int ib = 32 - __clz(max(n, m));
+    const uint32_t imask = (1u << ib) - 1u;
+    const int i = row0 + tid / kTPL, sl = tid % kTPL;
+    const bool live = i < n;
+    const uint32_t* row = s.K + ((size_t)b * n + (live ? i : 0)) * m;
+    uint32_t top[16];
+    group_top16<kTPL>(live ? m : 0, sl, [&](int e) { return (row[e] << ib) | (imask - (uint32_t)e); }, top);
+    if (live && sl == 0) {
+      bool ok = true;
+#pragma unroll
+      for (int t = 0; t < 15; ++t)
+        if (t < K2) ok = ok && pair_ok(top[t] >> ib, top[t + 1] >> ib);
+      if (!ok) {
+        q_rows[atomicAdd(&q_cnt, 1)] = i;
+      } else {
+        uint16_t* Dr = s.D + ((size_t)b * n + i) * M;
+        uint16_t* Er = s.E + ((size_t)b * n + i) * es;
+        // D (:198): first M entries as they are (ties are proven ties, already in index-ascending order)
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t < M) Dr[t] = (uint16_t)(imask - (top[t] & imask));
+        // E (:217): same values, ties in index-DESCENDING order and, when the tie group of the K2-th entry extends
+        // past the cut, its LARGEST indices
+        uint32_t kk[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) kk[t] = top[t] >> ib;
+        bool ties = false, ext = false;
+        uint32_t vstar = 0u;
+        int pfx = K2;
+#pragma unroll
+        for (int t = 0; t < 15; ++t) {
+          if (t < K2 - 1) ties = ties || (kk[t] == kk[t + 1]);
+          if (t == K2 - 1) {
+            ext = kk[t] == kk[t + 1];
+            vstar = kk[t];
+          }
+        }
+        if (ext) {
+          pfx = 0;
+#pragma unroll
+          for (int t = 0; t < 16; ++t)
+            if (t < K2 && kk[t] > vstar) pfx = t + 1;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t < pfx) Er[t] = (uint16_t)(imask - (top[t] & imask));
+        if (ties) {  // reverse every run of equal keys inside the prefix
+          int rs = 0;
+          while (rs < pfx) {
+            int re = rs + 1;
+            const uint32_t kv = row[Er[rs]];
+            while (re < pfx && row[Er[re]] == kv) ++re;
+            for (int x = rs, y = re - 1; x < y; ++x, --y) {
+              const uint16_t tmp = Er[x];
+              Er[x] = Er[y];
+              Er[y] = tmp;
+            }
+            rs = re;
+          }
+        }
+        if (ext)
+          for (int j = m - 1; j >= 0 && pfx < K2; --j)
+            if (row[j] == vstar) Er[pfx++] = (uint16_t)j;
+      }
+    }
+    __syncthreads();
+  }
+  // exact float64 warp selection: every row in exact mode, the uncertified rows in keyed mode
+  const int todo = kKeyed ? q_cnt : min(kRowsPerCta, n - row0);
+  for (int qi = warp; qi < todo; qi += kWarps) {
+    const int i = kKeyed ? q_rows[qi] : row0 + qi;
+    double vals[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int j = lane + 32 * c;
+      vals[c] = j < m ? (kKeyed ? tot64(p, win, Leff, i, j) : s.tot[((size_t)b * n + i) * m + j]) : 0.0;
+    }
+    uint16_t* Dr = s.D + ((size_t)b * n + i) * M;
+    uint16_t* Er = s.E + ((size_t)b * n + i) * es;
+    warp_select_cached(m, M, false, lane, vals, [&](int r, int j) { Dr[r] = (uint16_t)j; });   // :198
+    warp_select_cached(m, K2, true, lane, vals, [&](int r, int j) { Er[r] = (uint16_t)j; });   // :217 (pre-masking)
+  }
+}
+
+// exact float64 rival scores and selection of agent i (whole warp): every agent in exact mode, the rare uncertified
+// ones in keyed mode.  Kept out of line so that its 16 doubles per lane do not weigh on K3's register budget.
+// (Plain arguments, not the parameter struct: a struct reference would force a local-memory copy of it.)
+__device__ __noinline__ void exact_rivals(const float* win, const float* prios, const double* totT_env, int n, int m, int M,
+                                          int N, int Leff, int i, int lane, const uint16_t* wD, uint16_t* wN) {
   double vals[16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) vals[c] = (lane + 32 * c < m) ? row[lane + 32 * c] : 0.0;
-  uint16_t* Dr = s.D + ((size_t)b * n + i) * M;
-  uint16_t* Er = s.E + ((size_t)b * n + i) * K2;
-  warp_select_cached(m, M, false, lane, vals, [&](int r, int j) { Dr[r] = (uint16_t)j; });   // :198
-  warp_select_cached(m, K2, true, lane, vals, [&](int r, int j) { Er[r] = (uint16_t)j; });   // :217 (pre-masking)
+  for (int c = 0; c < 16; ++c) {
+    const int a = lane + 32 * c;
+    double best = -INFINITY;
+    if (a < n && a != i) {
+      for (int q = 0; q < M; ++q) {
+        const int j = wD[q];
+        double v;
+        if (totT_env) {
+          v = totT_env[(size_t)j * n + a];
+        } else {  // the reference's beta.sum(-1) (:190) straight from the planes
+          const double pr = prios ? (double)prios[j] : 1.0;
+          v = 0.0;
+          for (int l = 0; l < Leff; ++l) v += (double)win[((size_t)l * n + a) * m + j] * pr;
+        }
+        best = fmax(best, v);
+      }
+    }
+    vals[c] = best;
+  }
+  warp_select_cached(n, N, false, lane, vals, [&](int r, int a) { wN[r] = (uint16_t)a; });
 }
 
 // ---------------------------------------------------------------------------------------------------- K3
-__global__ void __launch_bounds__(kThreads) sap_real_large_main(RealParams p) {
+template <bool kKeyed>
+__global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SapEnvDims d = p.d;
-  const int b = blockIdx.y;
+  const int b = env_of_block();
+  if (b >= d.B) return;
   const int n = d.n, m = d.m, T = d.T, L = d.L, M = d.M, N = d.N, H = d.M / 2, K2 = d.M + d.M / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int obs_size = M * L + N * M * L + N * H * L + M;
@@ -229,55 +520,129 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_main(RealParams p) {
   const uint16_t* Dg = s.D + ((size_t)b * n + i) * M;
   for (int q = lane; q < M; q += 32) wD[q] = Dg[q];
   __syncwarp();
-  // rivals: score[a] = max_q tot[a, D_i[q]], read as M coalesced rows of totT (:203-206)
-  double vals[16];
+
+  // rivals (:203-206): score[a] = max_q tot[a, D_i[q]], read as M coalesced [task][agent] rows
+  bool need_exact = !kKeyed;
+  if (kKeyed) {
+    const int ib = 32 - __clz(max(n, m));
+    const uint32_t imask = (1u << ib) - 1u;
+    uint32_t pk[16];  // packed (score key | ~agent) of agents lane, lane + 32, ...
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int a = lane + 32 * c;
-    double best = -INFINITY;
-    if (a < n) {
-      for (int q = 0; q < M; ++q) best = fmax(best, s.totT[((size_t)b * m + wD[q]) * n + a]);
-      if (a == i) best = -INFINITY;
+    for (int c = 0; c < 16; ++c) pk[c] = 0u;
+    const uint32_t* kt = s.KT + (size_t)b * m * n;
+    for (int q = 0; q < M; ++q) {
+      const uint32_t* col = kt + (size_t)wD[q] * n;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int a = lane + 32 * c;
+        if (a < n) pk[c] = max(pk[c], __ldg(col + a));
+      }
     }
-    vals[c] = best;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int a = lane + 32 * c;
+      pk[c] = (a < n && a != i) ? (pk[c] << ib) | (imask - (uint32_t)a) : 0u;
+    }
+    // N + 1 rounds of "largest remaining packed word" (redux.max); equal keys come out in index-ascending order
+    uint32_t prevw = 0u;
+    bool ok = true;
+    for (int r = 0; r <= N; ++r) {
+      uint32_t loc = 0u;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) loc = max(loc, pk[c]);
+      const uint32_t w = __reduce_max_sync(SAP_FULL_MASK, loc);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) pk[c] = pk[c] == w ? 0u : pk[c];
+      if (r > 0) ok = ok && pair_ok(prevw >> ib, w >> ib);
+      if (r < N && lane == 0) wN[r] = (uint16_t)(imask - (w & imask));
+      prevw = w;
+    }
+    need_exact = !ok;
+    __syncwarp();
   }
-  warp_select_cached(n, N, false, lane, vals, [&](int r, int a) { wN[r] = (uint16_t)a; });
-  __syncwarp();
+  if (need_exact) {
+    exact_rivals(win, p.prios, kKeyed ? nullptr : s.totT + (size_t)b * m * n, n, m, M, N, Leff, i, lane, wD, wN);
+    __syncwarp();
+  }
   // rivals' other top tasks (:212-217): first M/2 entries of E[r] outside D[i], stored ascending
-  for (int ps = lane; ps < N; ps += 32) {
-    const uint16_t* Er = s.E + ((size_t)b * n + wN[ps]) * K2;
-    int c = 0;
-    for (int e = 0; e < K2 && c < H; ++e) {
-      const uint16_t j = Er[e];
-      bool in_top = false;
-      for (int q = 0; q < M; ++q) in_top |= (wD[q] == j);
-      if (!in_top) {
-        wO[ps * H + (H - 1 - c)] = j;
-        ++c;
+  if (kKeyed) {
+    for (int ps = lane; ps < N; ps += 32) {
+      const uint4* Er4 = reinterpret_cast<const uint4*>(s.E + ((size_t)b * n + wN[ps]) * kES);
+      const uint4 e0 = __ldg(Er4), e1 = __ldg(Er4 + 1);  // the whole list in two 128-bit loads
+      const uint32_t ew[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      int c = 0;
+#pragma unroll
+      for (int e = 0; e < 15; ++e) {
+        const uint32_t j = (ew[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+        bool in_top = false;
+        for (int q = 0; q < M; ++q) in_top |= (wD[q] == j);
+        if (e < K2 && c < H && !in_top) {
+          wO[ps * H + (H - 1 - c)] = (uint16_t)j;
+          ++c;
+        }
+      }
+    }
+  } else {
+    for (int ps = lane; ps < N; ps += 32) {
+      const uint16_t* Er = s.E + ((size_t)b * n + wN[ps]) * e_stride(d);
+      int c = 0;
+      for (int e = 0; e < K2 && c < H; ++e) {
+        const uint16_t j = Er[e];
+        bool in_top = false;
+        for (int q = 0; q < M; ++q) in_top |= (wD[q] == j);
+        if (!in_top) {
+          wO[ps * H + (H - 1 - c)] = j;
+          ++c;
+        }
       }
     }
   }
   __syncwarp();
-  // gather + store (:199-225)
-  for (int pp = lane; pp < npairs; pp += 32) {
-    int a, j;
-    if (pp < M) {
-      a = i;
-      j = wD[pp];
-    } else if (pp < M + N * M) {
-      const int x = pp - M;
-      a = wN[x / M];
-      j = wD[x % M];
-    } else {
-      const int x = pp - M - N * M;
-      a = wN[x / H];
-      j = wO[x];
+  // gather + store (:199-225): 4 (agent, task) pairs per lane in flight
+  const bool f16 = vw.obs.dtype == SAP_F16;
+  for (int pp0 = lane; pp0 < npairs; pp0 += 128) {
+    float v[4][4];
+    int jj[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int pp = pp0 + 32 * g;
+      int a = i, j = 0;
+      if (pp < M) {
+        j = wD[pp];
+      } else if (pp < M + N * M) {
+        const int x = pp - M;
+        a = wN[x / M];
+        j = wD[x % M];
+      } else if (pp < npairs) {
+        const int x = pp - M - N * M;
+        a = wN[x / H];
+        j = wO[x];
+      }
+      jj[g] = j;
+#pragma unroll
+      for (int l = 0; l < 4; ++l)
+        v[g][l] = (pp < npairs && l < Leff) ? __ldg(win + ((size_t)l * n + a) * m + j) : 0.f;
     }
-    const double pr = p.prios ? (double)p.prios[j] : 1.0;
-    for (int l = 0; l < L; ++l) {
-      const double v = l < Leff ? (double)win[((size_t)l * n + a) * m + j] * pr : 0.0;
-      sap_store_real(vw.obs.ptr, out + (int64_t)pp * L + l, vw.obs.dtype, v);
-      if (arow) arow[pp * L + l] = sap_round_real(vw.obs.dtype, v);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int pp = pp0 + 32 * g;
+      if (pp < npairs) {
+        const double pr = p.prios ? (double)p.prios[jj[g]] : 1.0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (l < L) {
+            const double x = (double)v[g][l] * pr;
+            const int64_t o = out + (int64_t)pp * L + l;
+            if (f16) {
+              const __half h = __double2half(x);
+              reinterpret_cast<__half*>(vw.obs.ptr)[o] = h;
+              if (arow) arow[pp * L + l] = __half2float(h);
+            } else {
+              reinterpret_cast<float*>(vw.obs.ptr)[o] = (float)x;
+              if (arow) arow[pp * L + l] = (float)x;
+            }
+          }
+      }
     }
   }
   const int pv = p.is_reset ? i : min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);  // the NEW prev_assigns
@@ -289,6 +654,29 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_main(RealParams p) {
   }
 }
 
+template <bool kKeyed>
+int launch_mode(RealParams& p, cudaStream_t st) {
+  const SapEnvDims& d = p.d;
+  const int H = d.M / 2;
+  const unsigned gy = (unsigned)min(d.B, kEnvFold), gz = (unsigned)((d.B + kEnvFold - 1) / kEnvFold);
+  const dim3 g1(((d.n + 31) / 32) * ((d.m + 31) / 32), gy, gz);
+  // 8 lanes per list when there are too few lists to fill the GPU with 4 (e.g. 64 envs x 324 agents)
+  const bool wide = (int64_t)d.B * ((d.n + 63) / 64) < 8 * 148;
+  const int rows_per_cta = kThreads / (wide ? 8 : 4);
+  const dim3 g2((d.n + rows_per_cta - 1) / rows_per_cta, gy, gz), g3((d.n + kWarps - 1) / kWarps, gy, gz);
+  sap_real_large_prep<<<d.B, kThreads, 0, st>>>(p, kKeyed ? 1 : 0);
+  SAP_CUDA_LAUNCH_CHECK("sap_real_large_prep");
+  sap_real_large_keys<kKeyed><<<g1, kThreads, 0, st>>>(p);
+  SAP_CUDA_LAUNCH_CHECK("sap_real_large_keys");
+  if (wide) sap_real_large_lists<kKeyed, 8><<<g2, kThreads, 0, st>>>(p);
+  else sap_real_large_lists<kKeyed, 4><<<g2, kThreads, 0, st>>>(p);
+  SAP_CUDA_LAUNCH_CHECK("sap_real_large_lists");
+  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(int32_t) * (size_t)d.m;
+  sap_real_large_main<kKeyed><<<g3, kThreads, smem, st>>>(p);
+  SAP_CUDA_LAUNCH_CHECK("sap_real_large_main");
+  return SAP_OK;
+}
+
 }  // namespace
 
 int64_t sap_real_large_scratch_doubles(const SapEnvDims& d) { return (int64_t)large_layout(d, nullptr, nullptr); }
@@ -297,16 +685,7 @@ int sap_real_large_launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
   SAP_REQUIRE(p.scratch, SAP_E_SMEM, "sap_real: this problem size needs scratch of sap_real_scratch_doubles() doubles");
   SAP_REQUIRE(d.n <= 512 && d.m <= 512, SAP_E_DIMS, "sap_real (large path): n, m must be <= 512");
-  SAP_REQUIRE(d.B <= 65535, SAP_E_DIMS, "sap_real (large path): B must be <= 65535");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int H = d.M / 2;
-  const dim3 g1(((d.n + 31) / 32) * ((d.m + 31) / 32), d.B), g2((d.n + kWarps - 1) / kWarps, d.B);
-  sap_real_large_tot<<<g1, kThreads, 0, st>>>(p);
-  SAP_CUDA_LAUNCH_CHECK("sap_real_large_tot");
-  sap_real_large_lists<<<g2, kThreads, 0, st>>>(p);
-  SAP_CUDA_LAUNCH_CHECK("sap_real_large_lists");
-  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(int32_t) * (size_t)d.m;
-  sap_real_large_main<<<g2, kThreads, smem, st>>>(p);
-  SAP_CUDA_LAUNCH_CHECK("sap_real_large_main");
-  return SAP_OK;
+  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: "3" = exact mode on keyed-eligible shapes
+  if (large_keyed(d) && !(force && force[0] == '3')) return launch_mode<true>(p, (cudaStream_t)stream);
+  return launch_mode<false>(p, (cudaStream_t)stream);
 }

@@ -40,11 +40,12 @@ def _cast(x64, dtype):
 @pytest.mark.parametrize("name", REAL)
 @pytest.mark.parametrize("real_dtype", [th.float16, th.float32])
 @pytest.mark.parametrize("shared", [True, False])
-@pytest.mark.parametrize("generic", ["0", "1", "2"])
+@pytest.mark.parametrize("generic", ["0", "1", "2", "3"])
 def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, monkeypatch):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
-    # "0": shared-memory fast path, "1": generic one-CTA-per-env kernel, "2": multi-CTA path of the large shapes
+    # "0": shared-memory fast path, "1": generic one-CTA-per-env kernel, "2" / "3": multi-CTA path of the large shapes
+    # (keyed lists with certificates / exact float64 selection)
     monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
 
     g = _load(name)
@@ -90,7 +91,7 @@ def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, mo
     dict(B=2, n=16, m=16, T=3, L=1, M=10, N=10, gen="dense", seed=7),
     dict(B=2, n=12, m=200, T=3, L=3, M=10, N=10, gen="const", seed=8),
 ])
-@pytest.mark.parametrize("generic", ["0", "1", "2"])
+@pytest.mark.parametrize("generic", ["0", "1", "2", "3"])
 def test_real_env_matches_oracle(cfg, generic, monkeypatch):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
@@ -318,7 +319,7 @@ def test_real_env_full_size_fast_equals_generic(monkeypatch):
     S[:40] = (S[:40] * 8).round() / 8  # coarse grid: duplicate sums above zero
     acts = [th.randint(0, m, (B, n), generator=g).cuda() for _ in range(T)]
     outs = []
-    for generic in ("1", "2", "0"):
+    for generic in ("1", "2", "3", "0"):
         monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
         env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S.cuda())
         batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
@@ -331,9 +332,9 @@ def test_real_env_full_size_fast_equals_generic(monkeypatch):
             ain.append(batch.agent_in.clone())
             tops.append(env.top.clone())
         outs.append((batch["obs"].clone(), batch["rewards"].clone(), th.stack(ain), th.stack(tops[:-1]), env.ep_return.clone()))
-    for a, b, c in zip(*outs):
-        assert th.equal(a, b) and th.equal(a, c)
-    obs, _, ain, _, _ = outs[2]
+    for a, b, c, e in zip(*outs):
+        assert th.equal(a, b) and th.equal(a, c) and th.equal(a, e)
+    obs, _, ain, _, _ = outs[3]
     assert th.equal(ain, obs.permute(1, 0, 2, 3).float())  # agent_in == float(obs[:, t]) for every t
 
 
