@@ -370,25 +370,30 @@ __device__ __noinline__ void exact_rivals(const float* win, const float* prios, 
                                           int N, int Leff, int i, int lane, const uint16_t* wD, uint16_t* wN) {
   double vals[16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int a = lane + 32 * c;
-    double best = -INFINITY;
-    if (a < n && a != i) {
-      for (int q = 0; q < M; ++q) {
-        const int j = wD[q];
-        double v;
-        if (totT_env) {
-          v = totT_env[(size_t)j * n + a];
-        } else {  // the reference's beta.sum(-1) (:190) straight from the planes
-          const double pr = prios ? (double)prios[j] : 1.0;
-          v = 0.0;
-          for (int l = 0; l < Leff; ++l) v += (double)win[((size_t)l * n + a) * m + j] * pr;
-        }
-        best = fmax(best, v);
+  for (int c = 0; c < 16; ++c) vals[c] = -INFINITY;
+  for (int q = 0; q < M; ++q) {
+    const int j = wD[q];
+    double v[16];  // 16 independent agents per lane: their loads overlap
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.0;
+    if (totT_env) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (lane + 32 * c < n) v[c] = totT_env[(size_t)j * n + lane + 32 * c];
+    } else {  // the reference's beta.sum(-1) (:190) straight from the planes
+      const double pr = prios ? (double)prios[j] : 1.0;
+      for (int l = 0; l < Leff; ++l) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (lane + 32 * c < n) v[c] += (double)win[((size_t)l * n + lane + 32 * c) * m + j] * pr;
       }
     }
-    vals[c] = best;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) vals[c] = fmax(vals[c], v[c]);
   }
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+    if (lane + 32 * c >= n || lane + 32 * c == i) vals[c] = -INFINITY;
   warp_select_cached(n, N, false, lane, vals, [&](int r, int a) { wN[r] = (uint16_t)a; });
 }
 
@@ -415,7 +420,9 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   uint16_t* wD = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * (M + N + N * H);
   uint16_t* wN = wD + M;
   uint16_t* wO = wN + N;
-  int32_t* cnt = reinterpret_cast<int32_t*>(smem_raw + sizeof(uint16_t) * (size_t)kWarps * (M + N + N * H) + 16);
+  const size_t cnt_off = (sizeof(uint16_t) * (size_t)kWarps * (M + N + N * H) + 15) & ~(size_t)15;
+  const size_t mask_off = cnt_off + ((sizeof(int32_t) * (size_t)m + 15) & ~(size_t)15);
+  int32_t* cnt = reinterpret_cast<int32_t*>(smem_raw + cnt_off);
   __shared__ double red[kWarps];
 
   // ------------------------------------------------------------------ chunk 0: rewards at the old window
@@ -566,6 +573,11 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   }
   // rivals' other top tasks (:212-217): first M/2 entries of E[r] outside D[i], stored ascending
   if (kKeyed) {
+    uint32_t* wMask = reinterpret_cast<uint32_t*>(smem_raw + mask_off) + warp * 16;  // membership bits of D[i] (m <= 511)
+    if (lane < 16) wMask[lane] = 0u;
+    __syncwarp();
+    if (lane < M) atomicOr(&wMask[wD[lane] >> 5], 1u << (wD[lane] & 31));
+    __syncwarp();
     for (int ps = lane; ps < N; ps += 32) {
       const uint4* Er4 = reinterpret_cast<const uint4*>(s.E + ((size_t)b * n + wN[ps]) * kES);
       const uint4 e0 = __ldg(Er4), e1 = __ldg(Er4 + 1);  // the whole list in two 128-bit loads
@@ -574,8 +586,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
 #pragma unroll
       for (int e = 0; e < 15; ++e) {
         const uint32_t j = (ew[e >> 1] >> (16 * (e & 1))) & 0xffffu;
-        bool in_top = false;
-        for (int q = 0; q < M; ++q) in_top |= (wD[q] == j);
+        const bool in_top = (wMask[(j >> 5) & 15] >> (j & 31)) & 1u;
         if (e < K2 && c < H && !in_top) {
           wO[ps * H + (H - 1 - c)] = (uint16_t)j;
           ++c;
@@ -671,7 +682,8 @@ int launch_mode(RealParams& p, cudaStream_t st) {
   if (wide) sap_real_large_lists<kKeyed, 8><<<g2, kThreads, 0, st>>>(p);
   else sap_real_large_lists<kKeyed, 4><<<g2, kThreads, 0, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_lists");
-  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(int32_t) * (size_t)d.m;
+  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 32 + sizeof(int32_t) * (size_t)d.m + 16 +
+                      sizeof(uint32_t) * 16 * kWarps;
   sap_real_large_main<kKeyed><<<g3, kThreads, smem, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_main");
   return SAP_OK;
