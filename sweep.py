@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--ns", type=str, default=None, help="comma list of n = m values (default: the C5 grid)")
+    ap.add_argument("--Bs", type=str, default=None, help="comma list of env counts (default: the C5 grid)")
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--mem-gb", type=float, default=80.0)
     opts = ap.parse_args()
@@ -195,6 +197,10 @@ def main():
     peak, peak_src = hbm_peak()
     Bs = [256, 4096] if opts.quick else [256, 1024, 4096, 16384, 65536]
     ns = [10, 100] if opts.quick else [10, 50, 100, 200, 500]
+    if opts.ns:
+        ns = [int(x) for x in opts.ns.split(",")]
+    if opts.Bs:
+        Bs = [int(x) for x in opts.Bs.split(",")]
     recs = []
     cpu = {n: cpu_point(n) for n in ns} if opts.cpu else {}
     for n in ns:
