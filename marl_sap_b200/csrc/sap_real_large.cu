@@ -45,12 +45,13 @@ struct LargeScratch {
   uint32_t* KT;     // keyed: [B][m][n]
   double* tot;      // exact: [B][n][m]
   double* totT;     // exact: [B][m][n]
+  void* G;          // keyed: [B][n][m][4] benefits of the window in the obs dtype (one 8/16-byte read per gathered pair)
 };
 
 __host__ __device__ inline size_t dbl_of_bytes(size_t bytes) { return (bytes + 7) / 8; }
 
 __host__ __device__ inline bool large_keyed(const SapEnvDims& d) {
-  return d.M + d.M / 2 + 1 <= 16 && d.N + 1 <= 16 && d.n <= 511 && d.m <= 511;
+  return d.M + d.M / 2 + 1 <= 16 && d.N + 1 <= 16 && d.n <= 511 && d.m <= 511 && d.L <= 4;
 }
 
 // sized for the exact mode (float64 sums); the keyed mode uses half of the two big arrays
@@ -67,7 +68,10 @@ __host__ __device__ inline size_t large_layout(const SapEnvDims& d, LargeScratch
   const size_t nm = (size_t)d.B * d.n * d.m;
   const size_t o_a = off;     off += nm;
   const size_t o_b = off;     off += nm;
+  off = (off + 1) & ~(size_t)1;  // 16-byte aligned
+  const size_t o_g = off;     off += large_keyed(d) ? 2 * nm : 0;
   if (s) {
+    s->G = base + o_g;
     s->scale = base + o_scale;
     s->ksnap = reinterpret_cast<int32_t*>(base + o_k);
     s->D = reinterpret_cast<uint16_t*>(base + o_D);
@@ -229,7 +233,27 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_keys(RealParams p) {
     if (i < n && j < m) {
       const double pr = p.prios ? (double)p.prios[j] : 1.0;
       double sum = 0.0;
-      for (int l = 0; l < Leff; ++l) sum += (double)win[((size_t)l * n + i) * m + j] * pr;  // :167-170, :190
+      double x[4] = {0.0, 0.0, 0.0, 0.0};
+      if (kKeyed) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (l < Leff) {
+            x[l] = (double)win[((size_t)l * n + i) * m + j] * pr;
+            sum += x[l];
+          }
+        // the L benefits of this (agent, task), rounded once to the obs dtype, side by side: K3 gathers a pair with
+        // ONE 8- or 16-byte read instead of L reads in L different planes
+        const size_t e = ((size_t)b * n + i) * m + j;
+        if (p.view.obs.dtype == SAP_F16) {
+          const __half2 h01 = __halves2half2(__double2half(x[0]), __double2half(x[1]));
+          const __half2 h23 = __halves2half2(__double2half(x[2]), __double2half(x[3]));
+          reinterpret_cast<uint2*>(s.G)[e] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+        } else {
+          reinterpret_cast<float4*>(s.G)[e] = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
+        }
+      } else {
+        for (int l = 0; l < Leff; ++l) sum += (double)win[((size_t)l * n + i) * m + j] * pr;  // :167-170, :190
+      }
       if (kKeyed) {
         // monotone 32-bit image of the float64 sum: floor(sum * 2^s) and an "inexact" bit (see sap_real_fast.cu)
         const double y = (sum - k_lo) * k_scale;
@@ -619,50 +643,78 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
     }
   }
   __syncwarp();
-  // gather + store (:199-225): 4 (agent, task) pairs per lane in flight
-  const bool f16 = vw.obs.dtype == SAP_F16;
-  for (int pp0 = lane; pp0 < npairs; pp0 += 128) {
-    float v[4][4];
-    int jj[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int pp = pp0 + 32 * g;
-      int a = i, j = 0;
-      if (pp < M) {
-        j = wD[pp];
-      } else if (pp < M + N * M) {
-        const int x = pp - M;
-        a = wN[x / M];
-        j = wD[x % M];
-      } else if (pp < npairs) {
-        const int x = pp - M - N * M;
-        a = wN[x / H];
-        j = wO[x];
-      }
-      jj[g] = j;
-#pragma unroll
-      for (int l = 0; l < 4; ++l)
-        v[g][l] = (pp < npairs && l < Leff) ? __ldg(win + ((size_t)l * n + a) * m + j) : 0.f;
+  // gather + store (:199-225)
+  auto pair_of = [&](int pp, int& a, int& j) {
+    a = i;
+    j = 0;
+    if (pp < M) {
+      j = wD[pp];
+    } else if (pp < M + N * M) {
+      const int x = pp - M;
+      a = wN[x / M];
+      j = wD[x % M];
+    } else if (pp < npairs) {
+      const int x = pp - M - N * M;
+      a = wN[x / H];
+      j = wO[x];
     }
+  };
+  if (kKeyed) {  // one read per pair from the K1 image (already in the obs dtype), 4 pairs per lane in flight
+    const bool f16 = vw.obs.dtype == SAP_F16;
+    const size_t row0 = (size_t)b * n;
+    for (int pp0 = lane; pp0 < npairs; pp0 += 128) {
+      uint4 raw[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int pp = pp0 + 32 * g;
-      if (pp < npairs) {
-        const double pr = p.prios ? (double)p.prios[jj[g]] : 1.0;
-#pragma unroll
-        for (int l = 0; l < 4; ++l)
-          if (l < L) {
-            const double x = (double)v[g][l] * pr;
-            const int64_t o = out + (int64_t)pp * L + l;
-            if (f16) {
-              const __half h = __double2half(x);
-              reinterpret_cast<__half*>(vw.obs.ptr)[o] = h;
-              if (arow) arow[pp * L + l] = __half2float(h);
-            } else {
-              reinterpret_cast<float*>(vw.obs.ptr)[o] = (float)x;
-              if (arow) arow[pp * L + l] = (float)x;
-            }
+      for (int g = 0; g < 4; ++g) {
+        const int pp = pp0 + 32 * g;
+        int a, j;
+        pair_of(pp, a, j);
+        const size_t e = (row0 + a) * m + j;
+        raw[g] = make_uint4(0u, 0u, 0u, 0u);
+        if (pp < npairs) {
+          if (f16) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(s.G) + e);
+            raw[g].x = t.x;
+            raw[g].y = t.y;
+          } else {
+            raw[g] = __ldg(reinterpret_cast<const uint4*>(s.G) + e);
           }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int pp = pp0 + 32 * g;
+        if (pp < npairs) {
+          const int64_t o = out + (int64_t)pp * L;
+          if (f16) {
+            const __half* h = reinterpret_cast<const __half*>(&raw[g]);
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+              if (l < L) {
+                reinterpret_cast<__half*>(vw.obs.ptr)[o + l] = h[l];
+                if (arow) arow[pp * L + l] = __half2float(h[l]);
+              }
+          } else {
+            const float* f = reinterpret_cast<const float*>(&raw[g]);
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+              if (l < L) {
+                reinterpret_cast<float*>(vw.obs.ptr)[o + l] = f[l];
+                if (arow) arow[pp * L + l] = f[l];
+              }
+          }
+        }
+      }
+    }
+  } else {
+    for (int pp = lane; pp < npairs; pp += 32) {
+      int a, j;
+      pair_of(pp, a, j);
+      const double pr = p.prios ? (double)p.prios[j] : 1.0;
+      for (int l = 0; l < L; ++l) {
+        const double v = l < Leff ? (double)win[((size_t)l * n + a) * m + j] * pr : 0.0;
+        sap_store_real(vw.obs.ptr, out + (int64_t)pp * L + l, vw.obs.dtype, v);
+        if (arow) arow[pp * L + l] = sap_round_real(vw.obs.dtype, v);
       }
     }
   }
