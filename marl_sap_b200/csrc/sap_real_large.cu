@@ -483,6 +483,46 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_lists(RealParams p) {
   }
 }
 
+// Keyed rival selection of agent i (whole warp): kC register slots per lane cover the n <= 32 kC candidate agents.
+// Returns whether the N winners are provably the float64 answer.
+template <int kC>
+__device__ __forceinline__ bool keyed_rivals(const uint32_t* kt, const uint16_t* wD, uint16_t* wN, int n, int m, int M, int N,
+                                             int i, int lane) {
+  const int ib = 32 - __clz(max(n, m));
+  const uint32_t imask = (1u << ib) - 1u;
+  uint32_t pk[kC];  // packed (score key | ~agent) of agents lane, lane + 32, ...
+#pragma unroll
+  for (int c = 0; c < kC; ++c) pk[c] = 0u;
+  for (int q = 0; q < M; ++q) {  // score[a] = max_q key[a, D_i[q]] (:203-206): M coalesced [task][agent] rows
+    const uint32_t* col = kt + (size_t)wD[q] * n;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      const int a = lane + 32 * c;
+      if (a < n) pk[c] = max(pk[c], __ldg(col + a));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kC; ++c) {
+    const int a = lane + 32 * c;
+    pk[c] = (a < n && a != i) ? (pk[c] << ib) | (imask - (uint32_t)a) : 0u;
+  }
+  // N + 1 rounds of "largest remaining packed word" (redux.max); equal keys come out in index-ascending order
+  uint32_t prevw = 0u;
+  bool ok = true;
+  for (int r = 0; r <= N; ++r) {
+    uint32_t loc = 0u;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) loc = max(loc, pk[c]);
+    const uint32_t w = __reduce_max_sync(SAP_FULL_MASK, loc);
+#pragma unroll
+    for (int c = 0; c < kC; ++c) pk[c] = pk[c] == w ? 0u : pk[c];
+    if (r > 0) ok = ok && pair_ok(prevw >> ib, w >> ib);
+    if (r < N && lane == 0) wN[r] = (uint16_t)(imask - (w & imask));
+    prevw = w;
+  }
+  return ok;
+}
+
 // exact float64 rival scores and selection of agent i (whole warp): every agent in exact mode, the rare uncertified
 // ones in keyed mode.  Kept out of line so that its 16 doubles per lane do not weigh on K3's register budget.
 // (Plain arguments, not the parameter struct: a struct reference would force a local-memory copy of it.)
@@ -541,6 +581,16 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   uint16_t* wN = wD + M;
   uint16_t* wO = wN + N;
   const size_t mask_off = (sizeof(uint16_t) * (size_t)kWarps * (M + N + N * H) + 15) & ~(size_t)15;
+  uint32_t* sLut = reinterpret_cast<uint32_t*>(smem_raw + mask_off + sizeof(uint32_t) * 16 * kWarps);
+  if (!done)
+    for (int pp = tid; pp < npairs; pp += kThreads) {  // obs layout (:225): own | rivals on my tasks | rivals' other tasks
+      uint32_t code;
+      if (pp < M) code = (0xffffu << 16) | pp;
+      else if (pp < M + N * M) code = (((pp - M) / M) << 16) | ((pp - M) % M);
+      else code = (((pp - M - N * M) / H) << 16) | 0x8000u | (pp - M - N * M);
+      sLut[pp] = code;
+    }
+  __syncthreads();
 
   // ------------------------------------------------------------------ my agent's observation row at slot k_new
   const int i = blockIdx.x * kWarps + warp;
@@ -565,39 +615,12 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   // rivals (:203-206): score[a] = max_q tot[a, D_i[q]], read as M coalesced [task][agent] rows
   bool need_exact = !kKeyed;
   if (kKeyed) {
-    const int ib = 32 - __clz(max(n, m));
-    const uint32_t imask = (1u << ib) - 1u;
-    uint32_t pk[16];  // packed (score key | ~agent) of agents lane, lane + 32, ...
-#pragma unroll
-    for (int c = 0; c < 16; ++c) pk[c] = 0u;
     const uint32_t* kt = s.KT + (size_t)b * m * n;
-    for (int q = 0; q < M; ++q) {
-      const uint32_t* col = kt + (size_t)wD[q] * n;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int a = lane + 32 * c;
-        if (a < n) pk[c] = max(pk[c], __ldg(col + a));
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int a = lane + 32 * c;
-      pk[c] = (a < n && a != i) ? (pk[c] << ib) | (imask - (uint32_t)a) : 0u;
-    }
-    // N + 1 rounds of "largest remaining packed word" (redux.max); equal keys come out in index-ascending order
-    uint32_t prevw = 0u;
-    bool ok = true;
-    for (int r = 0; r <= N; ++r) {
-      uint32_t loc = 0u;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) loc = max(loc, pk[c]);
-      const uint32_t w = __reduce_max_sync(SAP_FULL_MASK, loc);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) pk[c] = pk[c] == w ? 0u : pk[c];
-      if (r > 0) ok = ok && pair_ok(prevw >> ib, w >> ib);
-      if (r < N && lane == 0) wN[r] = (uint16_t)(imask - (w & imask));
-      prevw = w;
-    }
+    bool ok;
+    if (n <= 128) ok = keyed_rivals<4>(kt, wD, wN, n, m, M, N, i, lane);
+    else if (n <= 256) ok = keyed_rivals<8>(kt, wD, wN, n, m, M, N, i, lane);
+    else if (n <= 384) ok = keyed_rivals<12>(kt, wD, wN, n, m, M, N, i, lane);
+    else ok = keyed_rivals<16>(kt, wD, wN, n, m, M, N, i, lane);
     need_exact = !ok && !(p.debug_skip_redo & 1);
     __syncwarp();
   }
@@ -644,19 +667,13 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   }
   __syncwarp();
   // gather + store (:199-225)
-  auto pair_of = [&](int pp, int& a, int& j) {
+  auto pair_of = [&](int pp, int& a, int& j) {  // sLut[pp] = (rival slot or 0xffff) << 16 | other-task flag << 15 | slot
     a = i;
     j = 0;
-    if (pp < M) {
-      j = wD[pp];
-    } else if (pp < M + N * M) {
-      const int x = pp - M;
-      a = wN[x / M];
-      j = wD[x % M];
-    } else if (pp < npairs) {
-      const int x = pp - M - N * M;
-      a = wN[x / H];
-      j = wO[x];
+    if (pp < npairs) {
+      const uint32_t code = sLut[pp], ps = code >> 16, qs = code & 0x7fffu;
+      if (ps != 0xffffu) a = wN[ps];
+      j = (code & 0x8000u) ? wO[qs] : wD[qs];
     }
   };
   if (kKeyed) {  // one read per pair from the K1 image (already in the obs dtype), 4 pairs per lane in flight
@@ -744,7 +761,8 @@ int launch_mode(RealParams& p, cudaStream_t st) {
   if (wide) sap_real_large_lists<kKeyed, 8><<<g2, kThreads, 0, st>>>(p);
   else sap_real_large_lists<kKeyed, 4><<<g2, kThreads, 0, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_lists");
-  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(uint32_t) * 16 * kWarps;
+  const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(uint32_t) * 16 * kWarps +
+                      sizeof(uint32_t) * (size_t)(d.M + d.N * d.M + d.N * H);
   sap_real_large_main<kKeyed><<<g3, kThreads, smem, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_main");
   return SAP_OK;
