@@ -75,6 +75,7 @@ class _BatchedEnvBase:
         self.shared_planes = False
         self._staging = None
         self.t_host = 0  # host mirror of k (all envs step in lockstep)
+        self.launches_per_step = 1  # kernels one reset()/step() call enqueues (4 on the multi-CTA path of large shapes)
 
     # ------------------------------------------------------------------ benefits
     def load_benefits(self, sat_prox_mat):
@@ -167,6 +168,7 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
         self.scheme, self.preprocess = real_scheme(n, m, L, self.obs_size)
         need = int(self.lib.sap_real_scratch_doubles(self.dims()))
         self.scratch = th.empty(need, dtype=th.float64, device=self.device) if need > 0 else None
+        self.launches_per_step = 4 if need > 0 else 1  # prep + keys + lists + main (csrc/sap_real_large.cu)
         if sat_prox_mat is not None:
             self.load_benefits(sat_prox_mat)
 

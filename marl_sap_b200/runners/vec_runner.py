@@ -150,7 +150,7 @@ class CudaVecRunner:
         self.batch.agent_in = getattr(self, "agent_in", None)
         self.env.reset(self.batch, **reset_kwargs)
         self.batch.agent_in_t = 0
-        self.kernel_launches += 1
+        self.kernel_launches += self.env.launches_per_step
         self.t = 0
 
     def _rollout_loop(self, test_mode):
@@ -201,7 +201,7 @@ class CudaVecRunner:
         self.reset(**reset_kwargs)
         if not (getattr(self.args, "use_cuda_graph", False) and self._rollout_graph(test_mode)):
             self._rollout_loop(test_mode)
-        self.kernel_launches += 2 * self.T
+        self.kernel_launches += (1 + self.env.launches_per_step) * self.T  # selector + env kernel(s) per timestep
         self.last_episode_returns = self.env.ep_return.clone()
         self._finish_run(test_mode)
         return self.batch
