@@ -119,8 +119,10 @@ int sap_benefit_stats(const float* planes_Tnm, float* stats /*[B,T,2]*/, int32_t
  * state:  k[B] int32 in/out, prev[B,n] int32 in/out, ep_return[B] f64 accumulators.
  * top_out [B,n,M] int32 (nullable): agent i's top-M task indices of the NEW observation
  *         (shared with the filtered selector so top-M is computed once).
- * plane_stats [B or 1, T, 2] from sap_benefit_stats (nullable).
- * scratch: B*n*m doubles, required only when n*m*8 bytes do not fit shared memory. */
+ * plane_stats [B or 1, T, 2] from sap_benefit_stats (nullable).  When given it MUST bound the planes it
+ *         describes (min <= every value <= max): the kernels trust it for the key scale.
+ * scratch: sap_real_scratch_doubles(dims) doubles, 16-byte aligned; 0 (pass NULL) when an environment fits one
+ *         SM's shared memory, about 4*B*n*m otherwise (shapes like 324 x 450 run as four launches over it). */
 int sap_real_reset(const SapEnvDims* dims, const float* planes, const float* plane_stats, const float* task_prios,
                    int32_t* k, int32_t* prev, double* ep_return, const SapBatchView* view, int32_t* top_out,
                    double* scratch, void* stream);
@@ -128,7 +130,7 @@ int sap_real_step(const SapEnvDims* dims, const float* planes, const float* plan
                   const float* T_trans, double lambda_, const int64_t* actions, int32_t* k, int32_t* prev,
                   double* ep_return, int32_t* counts_out, const SapBatchView* view, int32_t* top_out, double* scratch,
                   void* stream);
-/* bytes of dynamic shared memory / scratch doubles the real-env kernels need for these dims */
+/* number of scratch doubles sap_real_reset / sap_real_step need for these dims (0: none) */
 int64_t sap_real_scratch_doubles(const SapEnvDims* dims);
 
 /* ---- MockConstellationEnv ---------------------------------------------------------------
