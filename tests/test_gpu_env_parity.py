@@ -359,6 +359,52 @@ def test_real_env_constellation_scale_matches_oracle():
     assert th.equal(batch["prev_assigns"].cpu(), _cast(want["prev_assigns"], th.int16))
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(B=2, n=37, m=53, T=4, L=4, M=10, N=12, prios=False, dtype=th.float16, gen="ref", seed=21),    # keyed, ragged tiles
+    dict(B=3, n=70, m=90, T=3, L=2, M=8, N=5, prios=True, dtype=th.float32, gen="dense", seed=22),     # keyed, priorities
+    dict(B=2, n=130, m=140, T=3, L=3, M=12, N=10, prios=False, dtype=th.float16, gen="dense", seed=23),  # M + M/2 + 1 > 16: exact mode
+    dict(B=2, n=64, m=96, T=3, L=5, M=10, N=10, prios=True, dtype=th.float32, gen="ref", seed=24),     # L > 4: exact mode
+    dict(B=2, n=200, m=200, T=3, L=3, M=10, N=10, prios=False, dtype=th.float16, gen="ties", seed=25),  # natural large path, tie-heavy
+    dict(B=1, n=511, m=511, T=2, L=2, M=10, N=15, prios=False, dtype=th.float16, gen="dense", seed=26),  # largest keyed shape
+])
+def test_real_env_multi_cta_path_matches_oracle(cfg, monkeypatch):
+    """The multi-CTA path of the large shapes (csrc/sap_real_large.cu) on ragged and extreme shapes, both of its modes."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", "2")
+    rng = np.random.default_rng(cfg["seed"])
+    B, n, m, T, L, M, N = (cfg[k] for k in ("B", "n", "m", "T", "L", "M", "N"))
+    if cfg["gen"] == "dense":
+        S = O.gen_dense(rng, B, n, m, T)
+    elif cfg["gen"] == "ties":
+        S = (np.round(O.gen_exact(rng, B, n, m, T, zero_frac=0.5) * 4) / 4).astype(np.float32)
+    else:
+        S = O.gen_ref_like(rng, B, n, m, T)
+    prios = (rng.integers(1, 4, size=m) * 0.5).astype(np.float32) if cfg["prios"] else None
+    acts = rng.integers(0, m, size=(T, B, n))
+    acts[:, :, : n // 3] = acts[:, :, :1]
+    st = O.RealState(S.astype(np.float64), L, M, N, 0.5, task_prios=prios)
+    want = O.rollout(st, lambda t, pre: acts[t], "real")
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S, task_prios=prios)
+    assert env.scratch is not None and env.launches_per_step == 4
+    batch = _batch_for(env, B, cfg["dtype"])
+    batch.agent_in = th.zeros(B, n, env.obs_size, device="cuda")
+    env.reset(batch)
+    counts = []
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+        counts.append(env.counts.cpu().numpy().copy())
+        assert th.equal(batch.agent_in, batch["obs"][:, t + 1].float())
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    assert th.equal(td["obs"], _cast(want["obs"], cfg["dtype"]))
+    assert th.equal(td["beta"], _cast(want["beta"], cfg["dtype"]))
+    assert th.equal(td["rewards"], _cast(want["rewards"], cfg["dtype"]))
+    assert th.equal(td["prev_assigns"], _cast(want["prev_assigns"], th.int16))
+    assert th.equal(td["terminated"][..., 0], th.tensor(want["terminated"]))
+    np.testing.assert_array_equal(np.stack(counts, 1), want["counts"][:, :T])
+    np.testing.assert_allclose(env.ep_return.cpu().numpy(), want["rewards"].sum((1, 2)), rtol=1e-12)
+
+
 def test_real_env_bench_batch_properties():
     """The bench configuration itself (4096 envs x 100 x 100): conflict histogram, sorted top-M, determinism."""
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
