@@ -344,6 +344,12 @@ def gpu_arm(opts, w):
     if not opts.no_cpu and world == 1:
         v, cores, sample, _ = cpu_port_throughput(w, weights, target_seconds=opts.cpu_seconds)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
+    if w["env"] != "real":
+        kernel_name = "sap_mock_kernel"
+    elif getattr(runner.env, "launches_per_step", 1) == 4:  # one env over many CTAs: the four launches of one env step
+        kernel_name = "sap_real_large_{prep,keys,lists,main} (4 launches per env step, timed together)"
+    else:
+        kernel_name = "sap_real_fast_kernel"
     line = {
         "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": opts.steps,
         "warmup": opts.warmup, "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": "weak",
@@ -357,7 +363,7 @@ def gpu_arm(opts, w):
                    "parallelism": f"envs block-partitioned, {world} rank(s), no data-path collective"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "sap_real_fast_kernel" if w["env"] == "real" else "sap_mock_kernel",
+                     "traffic": traffic, "kernel": kernel_name,
                      "algorithmic_bytes": "window read n*m*L*4 + obs write n*obs*(2 or 4) + agent-input write n*obs*4 + n*16+16 per env-step",
                      "algorithmic_bytes_per_launch": bytes_launch, "avg_launch_ms": kern_ms, "peak_source": peak_src,
                      "kernel_share_of_step": kern_ms * T / (ms / opts.steps)},

@@ -557,6 +557,14 @@ __device__ __noinline__ void exact_rivals(const float* win, const float* prios, 
   warp_select_cached(n, N, false, lane, vals, [&](int r, int a) { wN[r] = (uint16_t)a; });
 }
 
+// exact top-N (value desc, index asc) of n float64 scores staged in shared memory, one warp
+__device__ __noinline__ void exact_select_scores(const double* sScore, int n, int N, int lane, uint16_t* wN) {
+  double vals[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) vals[c] = (lane + 32 * c < n) ? sScore[lane + 32 * c] : -INFINITY;
+  warp_select_cached(n, N, false, lane, vals, [&](int r, int a) { wN[r] = (uint16_t)a; });
+}
+
 // ---------------------------------------------------------------------------------------------------- K3
 template <bool kKeyed>
 __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p) {
@@ -582,6 +590,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   uint16_t* wO = wN + N;
   const size_t mask_off = (sizeof(uint16_t) * (size_t)kWarps * (M + N + N * H) + 15) & ~(size_t)15;
   uint32_t* sLut = reinterpret_cast<uint32_t*>(smem_raw + mask_off + sizeof(uint32_t) * 16 * kWarps);
+  const size_t score_off = (mask_off + sizeof(uint32_t) * 16 * kWarps + sizeof(uint32_t) * (size_t)npairs + 15) & ~(size_t)15;
   if (!done)
     for (int pp = tid; pp < npairs; pp += kThreads) {  // obs layout (:225): own | rivals on my tasks | rivals' other tasks
       uint32_t code;
@@ -594,13 +603,13 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
 
   // ------------------------------------------------------------------ my agent's observation row at slot k_new
   const int i = blockIdx.x * kWarps + warp;
-  if (i >= n) return;
+  const bool have = i < n;  // warps without an agent stay for the CTA-wide fallback below
   const int64_t out = sap_field_off(vw.obs, b, k_new) + (int64_t)i * obs_size;
   float* arow = vw.agent_in.ptr ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride +
                                       (int64_t)i * vw.agent_in.t_stride
                                 : nullptr;
   if (done) {  // :226-228
-    for (int c = lane; c < obs_size; c += 32) {
+    for (int c = lane; have && c < obs_size; c += 32) {
       sap_store_real(vw.obs.ptr, out + c, vw.obs.dtype, 0.0);
       if (arow) arow[c] = 0.f;
     }
@@ -608,13 +617,13 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
   }
   const int Leff = min(L, T - k_new);
   const float* win = env_planes + (size_t)k_new * n * m;
-  const uint16_t* Dg = s.D + ((size_t)b * n + i) * M;
+  const uint16_t* Dg = s.D + ((size_t)b * n + (have ? i : 0)) * M;
   for (int q = lane; q < M; q += 32) wD[q] = Dg[q];
   __syncwarp();
 
   // rivals (:203-206): score[a] = max_q tot[a, D_i[q]], read as M coalesced [task][agent] rows
   bool need_exact = !kKeyed;
-  if (kKeyed) {
+  if (kKeyed && have) {
     const uint32_t* kt = s.KT + (size_t)b * m * n;
     bool ok;
     if (n <= 128) ok = keyed_rivals<4>(kt, wD, wN, n, m, M, N, i, lane);
@@ -624,8 +633,32 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p)
     need_exact = !ok && !(p.debug_skip_redo & 1);
     __syncwarp();
   }
-  if (need_exact) {
-    exact_rivals(win, p.prios, kKeyed ? nullptr : s.totT + (size_t)b * m * n, n, m, M, N, Leff, i, lane, wD, wN);
+  if (kKeyed) {
+    // Uncertified agents (rare): the WHOLE CTA computes the agent's exact float64 scores (one candidate per thread
+    // instead of sixteen per lane), then its warp runs the exact selection.  A lone warp doing all of it used to be the
+    // tail of this short kernel.
+    __shared__ int sFail[kWarps];
+    double* sScore = reinterpret_cast<double*>(smem_raw + score_off);
+    if (lane == 0) sFail[warp] = (have && need_exact) ? i : -1;
+    __syncthreads();
+    for (int w = 0; w < kWarps; ++w) {
+      const int iF = sFail[w];
+      if (iF < 0) continue;  // CTA-uniform
+      const uint16_t* fD = reinterpret_cast<const uint16_t*>(smem_raw) + (size_t)w * (M + N + N * H);
+      for (int a = tid; a < n; a += kThreads) {
+        double best = -INFINITY;
+        if (a != iF)
+          for (int q = 0; q < M; ++q) best = fmax(best, tot64(p, win, Leff, a, fD[q]));
+        sScore[a] = best;
+      }
+      __syncthreads();
+      if (warp == w) exact_select_scores(sScore, n, N, lane, wN);
+      __syncthreads();
+    }
+    if (!have) return;
+  } else {
+    if (!have) return;
+    exact_rivals(win, p.prios, s.totT + (size_t)b * m * n, n, m, M, N, Leff, i, lane, wD, wN);
     __syncwarp();
   }
   // rivals' other top tasks (:212-217): first M/2 entries of E[r] outside D[i], stored ascending
@@ -762,7 +795,7 @@ int launch_mode(RealParams& p, cudaStream_t st) {
   else sap_real_large_lists<kKeyed, 4><<<g2, kThreads, 0, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_lists");
   const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(uint32_t) * 16 * kWarps +
-                      sizeof(uint32_t) * (size_t)(d.M + d.N * d.M + d.N * H);
+                      sizeof(uint32_t) * (size_t)(d.M + d.N * d.M + d.N * H) + 16 + sizeof(double) * (size_t)d.n;
   sap_real_large_main<kKeyed><<<g3, kThreads, smem, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_main");
   return SAP_OK;
