@@ -27,6 +27,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxRowsPerCta = kThreads / 4;  // K2: 4 or 8 lanes per task list -> 64 or 32 lists per CTA
+constexpr int kTileI = 64;                    // agents per tile of the key kernel (x 32 tasks)
 constexpr int kES = 16;                       // stride of an E row (uint16 entries; K2 <= 15 in keyed mode)
 
 #define SAP_CE(a, b)            \
@@ -209,8 +210,9 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_prep(RealParams p, in
 // ---------------------------------------------------------------------------------------------------- K1
 template <bool kKeyed>
 __global__ void __launch_bounds__(kThreads) sap_real_large_keys(RealParams p) {
-  __shared__ double tile_d[kKeyed ? 1 : 32][kKeyed ? 1 : 33];
-  __shared__ uint32_t tile_k[kKeyed ? 32 : 1][kKeyed ? 33 : 1];
+  // tile = kTileI agents x 32 tasks: 8 agent rows (x L planes) in flight per thread
+  __shared__ double tile_d[kKeyed ? 1 : kTileI][kKeyed ? 1 : 33];
+  __shared__ uint32_t tile_k[kKeyed ? kTileI : 1][kKeyed ? 33 : 1];
   const SapEnvDims d = p.d;
   const int b = env_of_block(), n = d.n, m = d.m, T = d.T, L = d.L;
   if (b >= d.B) return;
@@ -228,8 +230,9 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_keys(RealParams p) {
   const uint32_t fixed_max = (1u << (31 - ib)) - 1u;
   const double k_lo = kKeyed ? s.scale[4 * b] : 0.0, k_scale = kKeyed ? s.scale[4 * b + 1] : 1.0;
   const bool k_nonneg = kKeyed ? s.scale[4 * b + 2] != 0.0 : true;
-  for (int r = ty; r < 32; r += kWarps) {
-    const int i = ti * 32 + r, j = tj * 32 + tx;
+#pragma unroll 4
+  for (int r = ty; r < kTileI; r += kWarps) {
+    const int i = ti * kTileI + r, j = tj * 32 + tx;
     if (i < n && j < m) {
       const double pr = p.prios ? (double)p.prios[j] : 1.0;
       double sum = 0.0;
@@ -275,10 +278,14 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_keys(RealParams p) {
   }
   __syncthreads();
   for (int r = ty; r < 32; r += kWarps) {
-    const int j = tj * 32 + r, i = ti * 32 + tx;
-    if (i < n && j < m) {
-      if (kKeyed) s.KT[((size_t)b * m + j) * n + i] = tile_k[tx][r];
-      else s.totT[((size_t)b * m + j) * n + i] = tile_d[tx][r];
+    const int j = tj * 32 + r;
+#pragma unroll
+    for (int h = 0; h < kTileI / 32; ++h) {
+      const int i = ti * kTileI + 32 * h + tx;
+      if (i < n && j < m) {
+        if (kKeyed) s.KT[((size_t)b * m + j) * n + i] = tile_k[32 * h + tx][r];
+        else s.totT[((size_t)b * m + j) * n + i] = tile_d[32 * h + tx][r];
+      }
     }
   }
 }
@@ -782,7 +789,7 @@ int launch_mode(RealParams& p, cudaStream_t st) {
   const SapEnvDims& d = p.d;
   const int H = d.M / 2;
   const unsigned gy = (unsigned)min(d.B, kEnvFold), gz = (unsigned)((d.B + kEnvFold - 1) / kEnvFold);
-  const dim3 g1(((d.n + 31) / 32) * ((d.m + 31) / 32), gy, gz);
+  const dim3 g1(((d.n + kTileI - 1) / kTileI) * ((d.m + 31) / 32), gy, gz);
   // 8 lanes per list when there are too few lists to fill the GPU with 4 (e.g. 64 envs x 324 agents)
   const bool wide = (int64_t)d.B * ((d.n + 63) / 64) < 8 * 148;
   const int rows_per_cta = kThreads / (wide ? 8 : 4);
