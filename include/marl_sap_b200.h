@@ -182,6 +182,12 @@ int sap_onehot(const void* actions, int32_t actions_dtype, void* onehot, int32_t
 int sap_real_beta_window(const SapEnvDims* dims, const float* planes, const float* task_prios, void* beta,
                          int32_t dtype, void* stream);
 
+/* ---- agent-input glue -----------------------------------------------------------------------
+ * sap_bias_act = the bias (+ ReLU) epilogue of one agent layer, in place: x[r, c] = act(x[r, c] + bias[c]).
+ *   The layer itself stays a torch matmul (modules/agents/rnn_agent.py:22-31: F.relu(self.fc1(inputs))); for the
+ *   first layer `mm` + this kernel is one pass cheaper than cuBLAS's beta*C epilogue and bit-identical to it. */
+int sap_bias_act(float* x, const float* bias, int64_t rows, int32_t cols, int32_t relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,38 @@ __global__ void __launch_bounds__(kThreads) sap_onehot_kernel(const void* action
   }
 }
 
+// x[r, c] = act(x[r, c] + bias[c]) in place, 128-bit accesses (cols % 4 == 0, x 16-byte aligned) or scalar
+template <bool kVec>
+__global__ void __launch_bounds__(kThreads) sap_bias_act_kernel(float* __restrict__ x, const float* __restrict__ bias,
+                                                                int64_t total, int cols, int relu) {
+  if (kVec) {
+    const int64_t total4 = total >> 2;
+    const int cols4 = cols >> 2;
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total4; e += (int64_t)gridDim.x * kThreads) {
+      const int c4 = (int)(e % cols4);
+      float4 v = reinterpret_cast<float4*>(x)[e];
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+      v.x = __fadd_rn(v.x, b.x);
+      v.y = __fadd_rn(v.y, b.y);
+      v.z = __fadd_rn(v.z, b.z);
+      v.w = __fadd_rn(v.w, b.w);
+      if (relu) {  // torch.relu: max(x, 0) with NaN propagated
+        v.x = v.x < 0.f ? 0.f : v.x;
+        v.y = v.y < 0.f ? 0.f : v.y;
+        v.z = v.z < 0.f ? 0.f : v.z;
+        v.w = v.w < 0.f ? 0.f : v.w;
+      }
+      reinterpret_cast<float4*>(x)[e] = v;
+    }
+  } else {
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+      float v = __fadd_rn(x[e], bias[e % cols]);
+      if (relu) v = v < 0.f ? 0.f : v;
+      x[e] = v;
+    }
+  }
+}
+
 // beta field [B, T+1, n, m, L] rebuilt from planes [B, T, n, m]
 __global__ void __launch_bounds__(kThreads) sap_beta_window_kernel(SapEnvDims d, const float* __restrict__ planes,
                                                                    const float* __restrict__ prios, void* beta, int dtype) {
@@ -240,6 +272,18 @@ extern "C" int sap_onehot(const void* actions, int32_t actions_dtype, void* oneh
   sap_onehot_kernel<<<grid_for(rows * m), kThreads, 0, (cudaStream_t)stream>>>(actions, actions_dtype, onehot,
                                                                               onehot_dtype, rows, m);
   SAP_CUDA_LAUNCH_CHECK("sap_onehot_kernel");
+  return SAP_OK;
+}
+
+extern "C" int sap_bias_act(float* x, const float* bias, int64_t rows, int32_t cols, int32_t relu, void* stream) {
+  SAP_REQUIRE(x && bias, SAP_E_NULL, "sap_bias_act: x/bias is null");
+  SAP_REQUIRE(rows >= 0 && cols > 0, SAP_E_DIMS, "sap_bias_act: bad dims");
+  if (rows == 0) return SAP_OK;
+  const int64_t total = rows * cols;
+  const bool vec = (cols % 4 == 0) && sap_aligned16(x) && sap_aligned16(bias);
+  if (vec) sap_bias_act_kernel<true><<<grid_for(total >> 2), kThreads, 0, (cudaStream_t)stream>>>(x, bias, total, cols, relu);
+  else sap_bias_act_kernel<false><<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(x, bias, total, cols, relu);
+  SAP_CUDA_LAUNCH_CHECK("sap_bias_act_kernel");
   return SAP_OK;
 }
 

@@ -20,13 +20,8 @@ class _FcAgent(nn.Module):
     def init_hidden(self):
         return self.fc1.weight.new(1, self.args.hidden_dim).zero_()
 
-    def _linear(self, layer, x):
-        """layer(x) as one cuBLAS sgemm with the bias as beta*C and a cached, contiguous W^T.  Same fp32 math and
-        bit-identical results as F.linear (checked in tests), but it avoids the separate bias-epilogue kernel that
-        cublasLt launches for these skinny fp32 GEMMs when W is passed as a transposed view (measured on B200:
-        0.94 ms vs 1.30 ms for the three layers at 409 600 rows)."""
-        if not (x.is_cuda and x.dim() == 2 and layer.bias is not None) or th.is_grad_enabled():
-            return layer(x)
+    def _wt(self, layer):
+        """Cached contiguous W^T of a layer (refreshed when the parameter is updated in place or moved)."""
         cache = self.__dict__.setdefault("_wt_cache", {})
         key = id(layer)
         ver = layer.weight._version
@@ -34,15 +29,41 @@ class _FcAgent(nn.Module):
         if hit is None or hit[0] != ver or hit[1].device != layer.weight.device:
             hit = (ver, layer.weight.detach().t().contiguous())
             cache[key] = hit
-        return th.addmm(layer.bias, x, hit[1])
+        return hit[1]
+
+    def _linear(self, layer, x, relu=False):
+        """``relu?(layer(x))`` for the rollout (CUDA, no grad).  Same fp32 math as ``F.relu(F.linear(x, W, b))`` - the
+        contraction is still a torch/cuBLAS sgemm, equal to F.linear up to the accumulation order cuBLAS picks per shape
+        (bit-identical at the bench shapes; tests hold it to 1e-5).  Only the way the bias / ReLU epilogue is issued
+        differs, because cuBLAS's own epilogues are slow for these skinny fp32 GEMMs (B200, 409 600 rows, three layers:
+        F.linear + F.relu 1.32 ms; addmm with a cached W^T 0.95 ms; this 0.80 ms):
+
+        * wide input (fc1, K = 490): plain ``mm`` + the in-place bias/ReLU kernel ``sap_bias_act`` (0.47 + 0.03 ms; the
+          beta*C epilogue of ``addmm`` costs 0.12 ms here);
+        * narrow input (K = hidden): ``addmm`` with the ReLU fused by ``torch._addmm_activation`` when available."""
+        if not (x.is_cuda and x.dim() == 2 and layer.bias is not None and x.dtype == th.float32) or th.is_grad_enabled():
+            y = layer(x)
+            return F.relu(y) if relu else y
+        wt = self._wt(layer)
+        if x.shape[1] >= 256 and x.is_contiguous():
+            from ... import _lib
+
+            y = th.mm(x, wt)
+            _lib.check(_lib.load().sap_bias_act(y.data_ptr(), layer.bias.data_ptr(), y.shape[0], y.shape[1], int(relu),
+                                                _lib.stream_ptr(x.device)), "sap_bias_act")
+            return y
+        if relu and hasattr(th, "_addmm_activation"):
+            return th._addmm_activation(layer.bias, x, wt)
+        y = th.addmm(layer.bias, x, wt)
+        return y.relu_() if relu else y
 
     def forward(self, inputs, hidden_state):
-        x = F.relu(self._linear(self.fc1, inputs))
+        x = self._linear(self.fc1, inputs, relu=True)
         h_in = hidden_state.reshape(-1, self.args.hidden_dim)
         if self.args.use_rnn:
             h = self.rnn(x, h_in)
         else:
-            h = F.relu(self._linear(self.rnn, x))
+            h = self._linear(self.rnn, x, relu=True)
         q = self._linear(self.fc2, h)
         return q, h
 

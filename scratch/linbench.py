@@ -30,3 +30,30 @@ t(lambda: F.linear(x,W1,b1),"fc1 F.linear only")
 t(lambda: th.mm(x,W1t),"fc1 mm only")
 t(lambda: F.linear(x,W1),"fc1 F.linear nobias")
 print("max diff", (lin()-mm_pre()).abs().max().item())
+def addmm_act():
+    h=th._addmm_activation(b1,x,W1t); h2=th._addmm_activation(b2,h,W2t); return th.addmm(b3,h2,W3t)
+t(addmm_act,"_addmm_activation (fused relu)")
+print("max diff fused", (addmm()-addmm_act()).abs().max().item())
+W3p=th.zeros(64,128,device='cuda'); W3p[:,:100]=W3t; b3p=th.zeros(128,device='cuda'); b3p[:100]=b3
+def addmm_pad():
+    h=th._addmm_activation(b1,x,W1t); h2=th._addmm_activation(b2,h,W2t); return th.addmm(b3p,h2,W3p)
+t(addmm_pad,"fused relu + out padded to 128 cols")
+t(lambda: th.addmm(b3,x[:, :64].contiguous() if False else th.relu(th.addmm(b2, th.relu(th.addmm(b1,x,W1t)), W2t)), W3t),"addmm + th.relu")
+h2_=th.relu(th.addmm(b2, th.relu(th.addmm(b1,x,W1t)), W2t))
+t(lambda: th.addmm(b3,h2_,W3t),"out layer only (64->100)")
+t(lambda: th.addmm(b3p,h2_,W3p),"out layer only padded (64->128)")
+h1_=th.relu(th.addmm(b1,x,W1t))
+t(lambda: th.addmm(b2,h1_,W2t),"fc2 only (64->64)")
+t(lambda: th.addmm(b1,x,W1t),"fc1 only (490->64)")
+print("---- per layer")
+t(lambda: th._addmm_activation(b1,x,W1t),"fc1 _addmm_activation")
+def fc1_mm_inplace():
+    h=th.mm(x,W1t); h.add_(b1); h.relu_(); return h
+t(fc1_mm_inplace,"fc1 mm + add_ + relu_")
+hbuf=th.empty(R,64,device='cuda')
+def fc1_mm_out():
+    th.mm(x,W1t,out=hbuf); hbuf.add_(b1).relu_(); return hbuf
+t(fc1_mm_out,"fc1 mm(out=) + add_ + relu_")
+t(lambda: th._addmm_activation(b2,h1_,W2t),"fc2 _addmm_activation")
+t(lambda: hbuf.add_(b1),"add_ bias only [R,64]")
+t(lambda: hbuf.relu_(),"relu_ only [R,64]")

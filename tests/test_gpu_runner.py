@@ -274,3 +274,52 @@ def test_episode_runner_matches_reference_runner_golden(name):
         assert th.equal(v.cpu(), want), f"field {k} differs from the reference runner's batch"
     assert runner.t_env == int(g["t_env_after"])
     assert logger.stats["return_mean"][-1][1] == pytest.approx(float(g["return_mean"]), rel=1e-3)  # fp16 rewards in the log sum
+
+
+@pytest.mark.parametrize("in_dim,hidden,n_out,rows", [(490, 64, 100, 4096), (301, 32, 11, 777), (40, 64, 10, 10)])
+def test_agent_rollout_forward_matches_the_reference_module_math(in_dim, hidden, n_out, rows):
+    """The rollout path of the agent (mm + sap_bias_act / fused-ReLU addmm, cached W^T) computes the reference's
+    RNNAgent.forward (modules/agents/rnn_agent.py:22-31) in fp32: equal to the F.relu(F.linear(...)) chain up to the
+    accumulation order cuBLAS picks per shape (1e-5 relative, the north star's fp32 tolerance)."""
+    import torch.nn.functional as F
+
+    from marl_sap_b200.modules.agents import RNNAgent
+
+    th.manual_seed(in_dim)
+    args = SimpleNamespace(hidden_dim=hidden, use_rnn=False, m=n_out)
+    agent = RNNAgent(in_dim, args).cuda()
+    x = th.randn(rows, in_dim, device="cuda")
+    h0 = agent.init_hidden().expand(rows, -1)
+
+    def ref():
+        h1 = F.relu(F.linear(x, agent.fc1.weight, agent.fc1.bias))
+        h2 = F.relu(F.linear(h1, agent.rnn.weight, agent.rnn.bias))
+        return F.linear(h2, agent.fc2.weight, agent.fc2.bias), h2
+
+    with th.no_grad():
+        q, h = agent(x, h0)
+        q_ref, h_ref = ref()
+    th.testing.assert_close(h, h_ref, rtol=1e-5, atol=1e-6)
+    th.testing.assert_close(q, q_ref, rtol=1e-5, atol=1e-6)
+    # an in-place parameter update must invalidate the cached transposes
+    with th.no_grad():
+        agent.fc1.weight.mul_(0.5)
+        q2, _ = agent(x, h0)
+        q2_ref, _ = ref()
+    th.testing.assert_close(q2, q2_ref, rtol=1e-5, atol=1e-6)
+    assert not th.allclose(q2, q)
+
+
+@pytest.mark.parametrize("rows,cols,relu", [(4096, 64, 1), (777, 33, 1), (5, 100, 0), (1, 4, 1)])
+def test_bias_act_kernel_is_bit_exact(rows, cols, relu):
+    """sap_bias_act (in-place x = act(x + bias)) against torch, bit for bit, vector and scalar paths."""
+    from marl_sap_b200 import _lib
+
+    g = th.Generator(device="cuda").manual_seed(rows * 131 + cols)
+    x = th.randn(rows, cols, device="cuda", generator=g)
+    b = th.randn(cols, device="cuda", generator=g)
+    want = x + b
+    if relu:
+        want = th.relu(want)
+    _lib.check(_lib.load().sap_bias_act(x.data_ptr(), b.data_ptr(), rows, cols, relu, _lib.stream_ptr()), "sap_bias_act")
+    assert th.equal(x, want)
