@@ -70,6 +70,66 @@ __device__ __forceinline__ uint32_t f32_ordered(float v) {
   return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
 }
 
+// Narrow rows (32 < A <= 16 kLPR), everything available - the rollout case: kLPR lanes per row, 32 / kLPR rows per
+// pass.  A lane reads up to four 128-bit pieces of its row and keeps its best (key, first index); log2(kLPR)
+// xor-shuffle steps reduce the row.  ~2x fewer instructions per row than two warp-wide redux per row, and several
+// rows of loads in flight.  Returns the action of row (base + lane).
+template <int kLPR>
+__device__ __forceinline__ int narrow_rows(const SelParams& p, int64_t base, int nrows, int A, float eps, float ue,
+                                           float ua, int lane) {
+  constexpr int kRPP = 32 / kLPR;  // rows per pass
+  const int g = lane / kLPR, l = lane % kLPR;
+  int my_action = 0;
+  for (int it = 0; it < kLPR; ++it) {
+    const int rr = it * kRPP + g;
+    const bool row_ok = rr < nrows;
+    const float* qr = p.q + (base + (row_ok ? rr : 0)) * A;
+    float4 v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = 4 * (l + kLPR * t);
+      v[t] = (row_ok && j < A) ? __ldg(reinterpret_cast<const float4*>(qr + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t bk = 0u;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = 4 * (l + kLPR * t);
+      if (j < A) {
+        const float x[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t key = f32_ordered(x[c]);
+          if (key > bk) {  // ascending j within the lane: strict > keeps the first index
+            bk = key;
+            bi = j + c;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 1; off < kLPR; off <<= 1) {
+      const uint32_t ok = __shfl_xor_sync(SAP_FULL_MASK, bk, off);
+      const int oi = __shfl_xor_sync(SAP_FULL_MASK, bi, off);
+      if (ok > bk || (ok == bk && oi < bi)) {
+        bk = ok;
+        bi = oi;
+      }
+    }
+    int action = bi;  // first-index argmax (classic_selectors.py:52-54)
+    const float ue_r = __shfl_sync(SAP_FULL_MASK, ue, rr & 31);
+    const float ua_r = __shfl_sync(SAP_FULL_MASK, ua, rr & 31);
+    if (ue_r < eps) {  // explore (:49-51): the floor(u * A)-th action, all of them being available
+      const int rank = (int)floorf(__fmul_rn(ua_r, (float)A));
+      action = min(rank, A - 1);
+    }
+    // row `lane` is row (lane % kRPP) of pass (lane / kRPP)
+    const int got = __shfl_sync(SAP_FULL_MASK, action, (lane % kRPP) * kLPR);
+    if (lane / kRPP == it) my_action = got;
+  }
+  return my_action;
+}
+
 __global__ void __launch_bounds__(kThreads) sap_select_classic_kernel(SelParams p, int vec4) {
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)p.B * p.n;
@@ -97,6 +157,12 @@ __global__ void __launch_bounds__(kThreads) sap_select_classic_kernel(SelParams 
   }
   int my_action = 0;
   const int nrows = (int)min((int64_t)32, rows - base);
+  if (vec4 && A <= 128 && A > 32 && !p.avail) {
+    if (A > 64) my_action = narrow_rows<8>(p, base, nrows, A, eps, ue, ua, lane);
+    else my_action = narrow_rows<4>(p, base, nrows, A, eps, ue, ua, lane);
+    if (lane < nrows) p.out[base + lane] = (int64_t)my_action;
+    return;
+  }
   for (int rr = 0; rr < nrows; ++rr) {
     const int64_t row = base + rr;
     const float* qr = p.q + row * A;

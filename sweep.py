@@ -144,7 +144,9 @@ def run_point(th, lib_mod, B, n, opts, peak):
                                                     None, out.data_ptr(), st), "select")
 
     select()
-    sel_ms = time_launches(th, select, 5)
+    for _ in range(3):
+        select()
+    sel_ms = time_launches(th, select, 20)
     sel_bytes = n * m * 4 + n * 8
     rec.update({"select_B_run": Bs, "select_kernel_ms": round(sel_ms, 5),
                 "select_hbm_gbps": Bs * sel_bytes / sel_ms / 1e6, "select_hbm_frac": Bs * sel_bytes / sel_ms / 1e6 / peak})
