@@ -182,6 +182,17 @@ int sap_onehot(const void* actions, int32_t actions_dtype, void* onehot, int32_t
 int sap_real_beta_window(const SapEnvDims* dims, const float* planes, const float* task_prios, void* beta,
                          int32_t dtype, void* stream);
 
+/* ---- assignment selectors -------------------------------------------------
+ * sap_lsa_maximize = the per-env body of SequentialAssignmentProblemSelector.select_action
+ *   (action_selectors/sap_selectors.py:77-91) and of EpsilonGreedySAPTestActionSelector's test branch (:26-33):
+ *   cols_out[b, :] = scipy.optimize.linear_sum_assignment(Q[b] + z[b] * std[b], maximize=True)[1].
+ *   z [B,n,m] standard-normal draws (nullable = no perturbation; torch's th.normal stream cannot be reproduced, so the
+ *   draws are an input), std [B] = mean|Q[b]| * eps * 2 (:84-85).  Shortest-augmenting-path solver on float64 duals
+ *   (the algorithm scipy implements): an optimal assignment, scipy's own whenever the optimum is unique.
+ *   objective_out [B] (nullable) = sum of the chosen perturbed benefits.  Requires n <= m <= 512. */
+int sap_lsa_maximize(const float* q, const float* z, const float* std_per_env, int32_t B, int32_t n, int32_t m,
+                     int64_t* cols_out, double* objective_out, void* stream);
+
 /* ---- agent-input glue -----------------------------------------------------------------------
  * sap_bias_act = the bias (+ ReLU) epilogue of one agent layer, in place: x[r, c] = act(x[r, c] + bias[c]).
  *   The layer itself stays a torch matmul (modules/agents/rnn_agent.py:22-31: F.relu(self.fc1(inputs))); for the

@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_PATH = os.path.join(PKG, "libmarl_sap_b200.so")
-SOURCES = ["sap_real.cu", "sap_real_fast.cu", "sap_real_large.cu", "sap_mock.cu", "sap_select.cu", "sap_buffer.cu"]
+SOURCES = ["sap_real.cu", "sap_real_fast.cu", "sap_real_large.cu", "sap_mock.cu", "sap_select.cu", "sap_lsa.cu", "sap_buffer.cu"]
 
 
 def nvcc_path() -> str:

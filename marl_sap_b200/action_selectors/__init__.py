@@ -1,8 +1,10 @@
 """Selector registry with the reference's ten keys (/root/reference/src/action_selectors/__init__.py:9-18).
 
-The two keys on the rollout hot path are implemented as CUDA kernels; the rest raise a clear error
-(SURVEY.md section 8f lists them as "next" rows: SAP/REDA selectors need a batched GPU assignment solver).
+The two keys on the rollout hot path and the four assignment ("SAP") selectors are
+implemented as CUDA kernels; the policy-sampling and bids-as-actions selectors raise a clear error.
 """
+from .sap_selectors import (EpsilonGreedySAPTestActionSelector, FilteredEpsGrSAPTestActionSelector,
+                            FilteredSAPActionSelector, SequentialAssignmentProblemSelector)
 from .selectors import EpsilonGreedyActionSelector, FilteredEpsilonGreedyActionSelector
 
 
@@ -21,7 +23,7 @@ REGISTRY["multinomial"] = _next_row("multinomial", "policy-sampling selector, ne
 REGISTRY["soft_policies"] = _next_row("soft_policies", "policy-sampling selector, next after the epsilon-greedy pair")
 REGISTRY["filtered_const_soft_policies"] = _next_row("filtered_const_soft_policies", "policy-sampling selector")
 REGISTRY["continuous"] = _next_row("continuous", "bids-as-actions path (scipy linear_sum_assignment in the env)")
-REGISTRY["sap"] = _next_row("sap", "needs a batched GPU linear-sum-assignment (next row 1)")
-REGISTRY["epsilon_greedy_sap_test"] = _next_row("epsilon_greedy_sap_test", "needs a batched GPU linear-sum-assignment")
-REGISTRY["filtered_const_sap"] = _next_row("filtered_const_sap", "needs a batched GPU linear-sum-assignment")
-REGISTRY["filtered_const_epsgr_sap_test"] = _next_row("filtered_const_epsgr_sap_test", "needs a batched GPU linear-sum-assignment")
+REGISTRY["sap"] = SequentialAssignmentProblemSelector
+REGISTRY["epsilon_greedy_sap_test"] = EpsilonGreedySAPTestActionSelector
+REGISTRY["filtered_const_sap"] = FilteredSAPActionSelector
+REGISTRY["filtered_const_epsgr_sap_test"] = FilteredEpsGrSAPTestActionSelector

@@ -303,6 +303,37 @@ def select_filtered_epsilon_greedy(q, top, avail, m, eps, u_tie, u_explore, u_ac
 
 
 # ------------------------------------------------------------------ episode buffer semantics
+def sap_noise_std(benefit: np.ndarray, eps: float) -> np.ndarray:
+    """stds = ones * mean|benefit[b]| * eps * 2, fp32 like torch (sap_selectors.py:84-85)."""
+    avg = np.abs(benefit.astype(np.float32)).mean(axis=(1, 2), dtype=np.float32)
+    return (avg * np.float32(eps) * np.float32(2)).astype(np.float32)
+
+
+def lsa_maximize(benefit: np.ndarray, z: np.ndarray | None = None, std: np.ndarray | None = None):
+    """Per env: scipy.optimize.linear_sum_assignment(benefit + z * std, maximize=True) (sap_selectors.py:77-91; the
+    dependency is scipy, unpinned in the reference's requirements.txt:24).  Returns (col_ind [B, n], objective [B])."""
+    from scipy.optimize import linear_sum_assignment
+
+    b32 = benefit.astype(np.float32)
+    if z is not None:
+        b32 = (b32 + (z.astype(np.float32) * std.astype(np.float32)[:, None, None]).astype(np.float32)).astype(np.float32)
+    cols, obj = [], []
+    for b in range(b32.shape[0]):
+        r, c = linear_sum_assignment(b32[b], maximize=True)
+        cols.append(c)
+        obj.append(b32[b][r, c].astype(np.float64).sum())
+    return np.stack(cols).astype(np.int64), np.asarray(obj)
+
+
+def filtered_benefit_matrix(q: np.ndarray, top: np.ndarray, m: int, u_tie: np.ndarray) -> np.ndarray:
+    """filtered_sap_selectors.py:43-57: baseline + U * 1e-8 everywhere, the top-M tasks get their own Q-values (fp32)."""
+    B, n, _ = q.shape
+    mat = (np.broadcast_to(q[:, :, -1:], (B, n, m)).astype(np.float32)
+           + (u_tie.astype(np.float32) * np.float32(1e-8)).astype(np.float32)).astype(np.float32)
+    np.put_along_axis(mat, top.astype(np.int64), q[:, :, :-1].astype(np.float32), axis=2)
+    return mat
+
+
 def one_hot(actions: np.ndarray, m: int, dtype) -> np.ndarray:
     """OneHot.transform then cast to the actions dtype (transforms.py:16-19, episode_buffer.py:123-129)."""
     out = np.zeros(actions.shape + (m,), dtype=dtype)

@@ -187,6 +187,8 @@ def ref_modules():
         "mock_env": "envs.mock_constellation_env",
         "classic_selectors": "action_selectors.classic_selectors",
         "filtered_selectors": "action_selectors.filtered_classic_selectors",
+        "sap_selectors": "action_selectors.sap_selectors",
+        "filtered_sap_selectors": "action_selectors.filtered_sap_selectors",
         "selectors": "action_selectors",
         "episode_buffer": "components.episode_buffer",
         "transforms": "components.transforms",

@@ -57,3 +57,12 @@ t(fc1_mm_out,"fc1 mm(out=) + add_ + relu_")
 t(lambda: th._addmm_activation(b2,h1_,W2t),"fc2 _addmm_activation")
 t(lambda: hbuf.add_(b1),"add_ bias only [R,64]")
 t(lambda: hbuf.relu_(),"relu_ only [R,64]")
+print("---- mm only, narrow layers")
+t(lambda: th.mm(h1_,W2t),"fc2 mm only (64->64)")
+t(lambda: th.mm(h2_,W3t),"out mm only (64->100)")
+W3t128=th.zeros(64,128,device='cuda'); W3t128[:,:100]=W3t
+t(lambda: th.mm(h2_,W3t128),"out mm only padded (64->128)")
+t(lambda: F.linear(h2_,W3,b3),"out F.linear (64->100)")
+t(lambda: th.matmul(h2_,W3t),"out matmul (64->100)")
+h2h=h2_.half(); W3h=W3t.half()
+t(lambda: th.mm(h2h,W3h),"out mm fp16 (reference only)")

@@ -207,6 +207,80 @@ def golden_selectors(R):
     np.savez_compressed(os.path.join(HERE, "selectors.npz"), **out)
 
 
+def golden_sap_selectors(R):
+    """The four assignment selectors of the reference (sap_selectors.py, filtered_sap_selectors.py) on seeded inputs.
+    th.normal / th.rand_like are replaced so that the reference consumes the recorded draws (one call per env)."""
+    import torch as th
+
+    rng = np.random.default_rng(33)
+    B, n, m, M, L = 4, 7, 11, 4, 3
+    args = SimpleNamespace(epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=1000,
+                           evaluation_epsilon=0.0, use_mps_action_selection=False, device="cpu",
+                           env_args={"M": M})
+    out = dict(sap_B=B, sap_n=n, sap_m=m, sap_M=M)
+    q = rng.standard_normal((B, n, m)).astype(np.float32)
+    z = rng.standard_normal((B, n, m)).astype(np.float32)
+    avail = np.ones((B, n, m), dtype=bool)
+    t_envs = [0, 400, 1000]
+
+    class patched:
+        def __init__(self, normals, rands):
+            self.normals, self.rands = list(normals), list(rands)
+
+        def __enter__(self):
+            self._n, self._r = th.normal, th.rand_like
+            normals, rands = self.normals, self.rands
+
+            def normal(mean=None, std=None, **k):
+                v = normals.pop(0)
+                assert tuple(v.shape) == tuple(std.shape)
+                return th.tensor(v) * std + mean
+
+            def rand_like(x, *a, **k):
+                v = rands.pop(0)
+                assert tuple(v.shape) == tuple(x.shape)
+                return th.tensor(v, dtype=x.dtype)
+
+            th.normal, th.rand_like = normal, rand_like
+            return self
+
+        def __exit__(self, *a):
+            th.normal, th.rand_like = self._n, self._r
+            return False
+
+    # "sap": Gaussian perturbation + linear_sum_assignment per env
+    sel = R.sap_selectors.SequentialAssignmentProblemSelector(args)
+    picks = []
+    for t_env in t_envs + ["test"]:
+        with patched([z[b] for b in range(B)], []):
+            a = sel.select_action(th.tensor(q), th.tensor(avail), 0 if t_env == "test" else t_env, test_mode=t_env == "test")
+        picks.append(a.numpy().astype(np.int64))
+    out.update(sap_q=q, sap_z=z, sap_t_env=np.array(t_envs), sap_actions=np.stack(picks))
+    # "epsilon_greedy_sap_test", test branch: assignment of the raw Q-values
+    sel2 = R.sap_selectors.EpsilonGreedySAPTestActionSelector(args)
+    out["egsap_test_actions"] = sel2.select_action(th.tensor(q), th.tensor(avail), 0, test_mode=True).numpy().astype(np.int64)
+    # filtered variants
+    qf = rng.standard_normal((B, n, M + 1)).astype(np.float32)
+    beta = O.gen_exact(rng, B, n, m, L)[..., :L]
+    beta = (beta + (rng.permutation(B * n * m).reshape(B, n, m, 1) + 1).astype(np.float32) * np.float32(2.0 ** -20)).astype(np.float32)
+    u_tie = rng.random((B, n, m), dtype=np.float32)
+    zf = rng.standard_normal((B, n, m)).astype(np.float32)
+    fsel = R.filtered_sap_selectors.FilteredSAPActionSelector(args)
+    fpicks = []
+    for t_env in t_envs + ["test"]:
+        with patched([zf[b] for b in range(B)], [u_tie[b] for b in range(B)]):
+            a = fsel.select_action(th.tensor(qf), th.tensor(avail), 0 if t_env == "test" else t_env,
+                                   test_mode=t_env == "test", beta=th.tensor(beta))
+        fpicks.append(a.numpy().astype(np.int64))
+    fsel2 = R.filtered_sap_selectors.FilteredEpsGrSAPTestActionSelector(args)
+    with patched([], [u_tie[b] for b in range(B)]):
+        a2 = fsel2.select_action(th.tensor(qf), th.tensor(avail), 0, test_mode=True, beta=th.tensor(beta))
+    out.update(fsap_q=qf, fsap_beta=beta, fsap_u_tie=u_tie, fsap_z=zf, fsap_actions=np.stack(fpicks),
+               fepsgr_test_actions=a2.numpy().astype(np.int64))
+    out.update(eps_start=1.0, eps_finish=0.05, eps_anneal=1000, eval_eps=0.0)
+    np.savez_compressed(os.path.join(HERE, "sap_selectors.npz"), **out)
+
+
 class _inject:
     """Feed injected uniforms to th.rand_like (in call order) and replace Categorical.sample by the
     rank-select contract of oracle.random_available_action."""
@@ -302,6 +376,7 @@ def main():
     golden_real_random(R)
     golden_mock(R)
     golden_selectors(R)
+    golden_sap_selectors(R)
     golden_buffer(R)
     golden_runner(R)
     for f in sorted(os.listdir(HERE)):

@@ -105,7 +105,8 @@ def test_registries_have_the_reference_keys():
                                    "interference_constellation_env", "dictator_env"])
     assert sorted(runners) == ["episode", "parallel"]
     with pytest.raises(NotImplementedError, match="not built yet"):
-        sel["sap"](SimpleNamespace())
+        sel["multinomial"](SimpleNamespace())
+    assert sel["sap"].__name__ == "SequentialAssignmentProblemSelector"
     with pytest.raises(NotImplementedError, match="hot path"):
         envs["dictator_env"]()
     with pytest.raises(NotImplementedError, match="sat_prox_mat"):

@@ -51,6 +51,77 @@ def test_selectors_match_reference_golden():
         np.testing.assert_array_equal(got.cpu().numpy(), want)
 
 
+def test_sap_selectors_match_reference_golden():
+    """The four assignment selectors against the picks of the unmodified reference (scipy per env), same draws."""
+    from marl_sap_b200.action_selectors import REGISTRY
+
+    g = dict(np.load(os.path.join(GOLDEN, "sap_selectors.npz")))
+    M, m = int(g["sap_M"]), int(g["sap_m"])
+    args = _args(env_args={"M": M, "m": m})
+    t_envs = list(g["sap_t_env"]) + ["test"]
+    avail = th.ones(g["sap_q"].shape, dtype=th.bool, device="cuda")
+    sel = REGISTRY["sap"](args)
+    for t_env, want in zip(t_envs, g["sap_actions"]):
+        sel.inject_draws(z=_cu(g["sap_z"]))
+        got = sel.select_action(_cu(g["sap_q"]), avail, 0 if t_env == "test" else int(t_env), test_mode=t_env == "test")
+        assert got.dtype == th.int64 and got.is_cuda
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+    got = REGISTRY["epsilon_greedy_sap_test"](args).select_action(_cu(g["sap_q"]), avail, 0, test_mode=True)
+    np.testing.assert_array_equal(got.cpu().numpy(), g["egsap_test_actions"])
+    fsel = REGISTRY["filtered_const_sap"](args)
+    for t_env, want in zip(t_envs, g["fsap_actions"]):
+        fsel.inject_draws(z=_cu(g["fsap_z"]), u_tie=_cu(g["fsap_u_tie"]))
+        got = fsel.select_action(_cu(g["fsap_q"]), avail, 0 if t_env == "test" else int(t_env), test_mode=t_env == "test",
+                                 beta=_cu(g["fsap_beta"]))
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+    fsel2 = REGISTRY["filtered_const_epsgr_sap_test"](args)
+    fsel2.inject_draws(u_tie=_cu(g["fsap_u_tie"]))
+    got = fsel2.select_action(_cu(g["fsap_q"]), avail, 0, test_mode=True, beta=_cu(g["fsap_beta"]))
+    np.testing.assert_array_equal(got.cpu().numpy(), g["fepsgr_test_actions"])
+    # training branches delegate to the epsilon-greedy kernels: actions stay in range, epsilon follows the schedule
+    a = fsel2.select_action(_cu(g["fsap_q"]), avail, 500, test_mode=False, beta=_cu(g["fsap_beta"]))
+    assert a.shape == (g["fsap_q"].shape[0], g["fsap_q"].shape[1]) and int(a.min()) >= 0 and int(a.max()) < m
+
+
+@pytest.mark.parametrize("B,n,m,noise", [(8, 4, 4, False), (33, 10, 10, True), (16, 50, 50, True), (64, 100, 100, True),
+                                         (5, 37, 53, True), (3, 324, 450, True), (2, 200, 512, False), (4, 1, 7, True)])
+def test_lsa_kernel_matches_scipy(B, n, m, noise):
+    """sap_lsa_maximize against scipy.optimize.linear_sum_assignment (through the oracle): feasible, same optimal
+    objective to 1e-9 relative, and - the optimum being unique for continuous inputs - the same assignment."""
+    from marl_sap_b200.action_selectors.sap_selectors import lsa_maximize
+
+    rng = np.random.default_rng(B * 1000 + m)
+    q = rng.standard_normal((B, n, m)).astype(np.float32)
+    z = rng.standard_normal((B, n, m)).astype(np.float32) if noise else None
+    std = O.sap_noise_std(q, 0.3) if noise else None
+    want, want_obj = O.lsa_maximize(q, z, std)
+    got, obj = lsa_maximize(_cu(q), None if z is None else _cu(z), None if std is None else _cu(std), want_objective=True)
+    got, obj = got.cpu().numpy(), obj.cpu().numpy()
+    for b in range(B):
+        assert len(set(got[b].tolist())) == n and got[b].min() >= 0 and got[b].max() < m
+    np.testing.assert_allclose(obj, want_obj, rtol=1e-9, atol=1e-9)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_lsa_kernel_ties_and_errors():
+    """Exact ties (constant and integer matrices): any optimal assignment is accepted, the objective must be optimal."""
+    from marl_sap_b200 import _lib
+    from marl_sap_b200.action_selectors.sap_selectors import lsa_maximize
+
+    rng = np.random.default_rng(5)
+    q = np.stack([np.zeros((6, 9), np.float32), np.ones((6, 9), np.float32),
+                  rng.integers(0, 3, size=(6, 9)).astype(np.float32), rng.integers(-2, 2, size=(6, 9)).astype(np.float32)])
+    want, want_obj = O.lsa_maximize(q)
+    got, obj = lsa_maximize(_cu(q), want_objective=True)
+    got = got.cpu().numpy()
+    for b in range(q.shape[0]):
+        assert len(set(got[b].tolist())) == 6
+    np.testing.assert_allclose(obj.cpu().numpy(), want_obj, rtol=0, atol=1e-12)
+    with pytest.raises(RuntimeError, match="n <= m"):
+        lsa_maximize(_cu(np.zeros((1, 5, 3), np.float32)))
+    assert _lib.load().sap_lsa_maximize(None, None, None, 1, 1, 1, None, None, None) != 0
+
+
 @pytest.mark.parametrize("B,n,A", [(4, 10, 10), (3, 50, 50), (2, 100, 100), (2, 7, 450), (1, 3, 33)])
 def test_epsilon_greedy_matches_oracle(B, n, A):
     from marl_sap_b200.action_selectors import REGISTRY

@@ -103,3 +103,23 @@ def test_rollout_timeline_real():
     assert out["terminated"][:, :3].sum() == 0 and out["terminated"][:, 3].all() and not out["terminated"][:, 4].any()
     assert not out["obs"][:, 4].any() and not out["beta"][:, 4].any()
     np.testing.assert_array_equal(out["prev_assigns"][:, 4], acts[3])
+
+
+def test_sap_selectors_oracle_matches_reference():
+    """The assignment selectors (sap_selectors.py, filtered_sap_selectors.py): the oracle's scipy restatement, fed the
+    recorded Gaussian / tie draws, reproduces the reference's picks on every fixture."""
+    g = _load("sap_selectors.npz")
+    eps_list = [O.epsilon_linear(1.0, 0.05, 1000, int(t)) for t in g["sap_t_env"]] + [float(g["eval_eps"])]
+    for eps, want in zip(eps_list, g["sap_actions"]):
+        got, _ = O.lsa_maximize(g["sap_q"], g["sap_z"], O.sap_noise_std(g["sap_q"], eps))
+        np.testing.assert_array_equal(got, want)
+    got, _ = O.lsa_maximize(g["sap_q"])
+    np.testing.assert_array_equal(got, g["egsap_test_actions"])
+    M, m = int(g["sap_M"]), int(g["sap_m"])
+    top = O.top_m_tasks(g["fsap_beta"], M)
+    mat = O.filtered_benefit_matrix(g["fsap_q"], top, m, g["fsap_u_tie"])
+    for eps, want in zip(eps_list, g["fsap_actions"]):
+        got, _ = O.lsa_maximize(mat, g["fsap_z"], O.sap_noise_std(mat, eps))
+        np.testing.assert_array_equal(got, want)
+    got, _ = O.lsa_maximize(mat)
+    np.testing.assert_array_equal(got, g["fepsgr_test_actions"])
