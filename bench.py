@@ -190,7 +190,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def build_runner(w, rank_seed, planes, use_graph=False):
+def build_runner(w, rank_seed, planes, use_graph=False, selector="epsilon_greedy"):
     import torch as th
 
     from marl_sap_b200.components.episode_buffer import ReplayBuffer
@@ -209,7 +209,7 @@ def build_runner(w, rank_seed, planes, use_graph=False):
         env_args = dict(n=w["n"], m=w["m"], T=w["T"], L=w["L"], lambda_=0.5, sat_prox_mat=placeholder)
         env_name = "mock_constellation_env"
     args = SimpleNamespace(env=env_name, env_args=env_args, batch_size_run=w["B"], device="cuda", runner="parallel",
-                           mac="basic_mac", action_selector="epsilon_greedy", epsilon_start=0.5, epsilon_finish=0.5,
+                           mac="basic_mac", action_selector=selector, epsilon_start=0.5, epsilon_finish=0.5,
                            epsilon_anneal_time=1, evaluation_epsilon=0.0, agent="rnn", hidden_dim=64, use_rnn=False,
                            obs_agent_id=False, obs_last_action=False, agent_output_type="q", test_nepisode=w["B"],
                            runner_log_interval=10 ** 12, seed=rank_seed, use_mps_action_selection=True,
@@ -249,7 +249,7 @@ def gpu_arm(opts, w):
     # synthetic benefits, U(0,1), distinct per env and per rank, generated straight in the device layout
     g = th.Generator(device=dev).manual_seed(1234 + rank)
     planes = th.rand(B, T, n, m, device=dev, generator=g)
-    runner, buffer, weights = build_runner(w, 1 + rank, planes, opts.graph)
+    runner, buffer, weights = build_runner(w, 1 + rank, planes, opts.graph, opts.selector)
     n_fields = len(buffer.data.transition_data)
 
     # per-launch event pairs around the fused env kernel
@@ -341,7 +341,7 @@ def gpu_arm(opts, w):
     except Exception:
         pass
     cpu = None
-    if not opts.no_cpu and world == 1:
+    if not opts.no_cpu and world == 1 and opts.selector == "epsilon_greedy":
         v, cores, sample, _ = cpu_port_throughput(w, weights, target_seconds=opts.cpu_seconds)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample}
     if w["env"] != "real":
@@ -355,7 +355,7 @@ def gpu_arm(opts, w):
         "warmup": opts.warmup, "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{opts.workload}: {w['desc']}, T={T}, L={w['L']}, M={w['M']}, N={w['N']}, {w['env']} env, "
-                               "epsilon_greedy + fc agent(hidden 64)",
+                               f"{opts.selector} + fc agent(hidden 64)",
                    "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch", "cuda_graph": bool(opts.graph),
                    "inputs": f"benefit planes {planes.numel() * 4 / 2 ** 30:.1f} GiB per GPU (> 126 MB L2), distinct per env",
                    "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
@@ -495,6 +495,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--selector", default="epsilon_greedy", choices=["epsilon_greedy", "sap"],
+                    help="action selector of the rollout (sap = noise-perturbed optimal assignment per env; no CPU leg)")
     ap.add_argument("--graph", action="store_true", help="replay the T-step loop of every episode as one CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

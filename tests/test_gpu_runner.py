@@ -323,3 +323,42 @@ def test_bias_act_kernel_is_bit_exact(rows, cols, relu):
         want = th.relu(want)
     _lib.check(_lib.load().sap_bias_act(x.data_ptr(), b.data_ptr(), rows, cols, relu, _lib.stream_ptr()), "sap_bias_act")
     assert th.equal(x, want)
+
+
+@pytest.mark.parametrize("selector,agent", [("sap", "rnn"), ("filtered_const_sap", "flat_const_agent")])
+def test_runner_with_assignment_selectors_matches_oracle(selector, agent):
+    """iql_sap.yaml / filtered_reda.yaml style rollouts: the runner with the assignment selectors against the oracle
+    rollout (scipy per env) fed the same Gaussian / tie draws; every env's joint action is conflict-free."""
+    rng = np.random.default_rng(41)
+    B, n, m, T, L, M, N = 3, 10, 20, 5, 3, 4, 3
+    S = O.gen_dense(rng, B, n, m, T)
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=0.5, sat_prox_mat=S, graphs=1)
+    args = make_args("real_constellation_env", env_args, B, selector=selector, agent=agent, epsilon_start=0.3,
+                     epsilon_finish=0.3, epsilon_anneal_time=1)
+    runner, mac, buffer, logger = build(args)
+    draws = {"z": rng.standard_normal((T, B, n, m)).astype(np.float32), "u_tie": rng.random((T, B, n, m), dtype=np.float32)}
+    if selector == "sap":
+        del draws["u_tie"]
+    DrawInjector(mac.action_selector, draws)
+    state = O.RealState(S.astype(np.float64), L, M, N, 0.5)
+
+    def policy(t, pre):
+        x = th.tensor(pre["obs"], dtype=th.float16).float().reshape(B * n, -1).cuda()
+        with th.no_grad():
+            q, _ = mac.agent(x, mac.agent.init_hidden().expand(B * n, -1))
+        q = q.view(B, n, -1).cpu().numpy()
+        if selector == "sap":
+            mat = q
+        else:
+            mat = O.filtered_benefit_matrix(q, O.top_m_tasks(pre["beta"], M), m, draws["u_tie"][t])
+        return O.lsa_maximize(mat, draws["z"][t], O.sap_noise_std(mat, 0.3))[0]
+
+    want = O.rollout(state, policy, "real")
+    with th.no_grad():
+        batch = runner.run(test_mode=False)
+    acts = batch["actions"][..., 0].cpu()
+    assert th.equal(acts, th.tensor(want["actions"]).to(th.int16))
+    assert th.equal(batch["rewards"].cpu(), th.tensor(want["rewards"], dtype=th.float16))
+    for t in range(T):
+        for b in range(B):
+            assert len(set(acts[b, t].tolist())) == n  # an assignment: no two agents on one task
