@@ -6,6 +6,7 @@ For every grid point it times, with CUDA events on the launching stream and inpu
   * the env step + observation kernel (real env: M = N = 10, L = 3, fp16 scheme + fp32 agent input; 10 x 10 uses the
     mock env, like the reference's own 10 x 10 configuration: the real env needs m >= M + M/2),
   * the masked eps-greedy selector kernel on q[B, n, m],
+  * the batched linear-sum-assignment kernel of the "sap" selectors on q + z * std (at most 16 384 envs),
 and reports env-steps/s, agent-steps/s and the algorithmic GB/s against the measured HBM peak.
 With --cpu it also times the numpy oracle port of the same env step on one host core for a few envs per shape (this is
 the one place besides bench.py / tests where oracle/ is executed: as the CPU baseline, never as the product).
@@ -150,7 +151,20 @@ def run_point(th, lib_mod, B, n, opts, peak):
     sel_bytes = n * m * 4 + n * 8
     rec.update({"select_B_run": Bs, "select_kernel_ms": round(sel_ms, 5),
                 "select_hbm_gbps": Bs * sel_bytes / sel_ms / 1e6, "select_hbm_frac": Bs * sel_bytes / sel_ms / 1e6 / peak})
-    del q, out
+    # assignment selector: one linear-sum-assignment per env on q + z * std (the "sap" selector's kernel)
+    Bl = max(1, min(Bs, int(opts.mem_gb * 1e9 // (n * m * 8 + n * 8)), 16384))
+    z = th.randn(Bl, n, m, device=dev, generator=g)
+    std = (q[:Bl].abs().mean(dim=(1, 2)) * 0.1).contiguous()
+    cols = th.empty(Bl, n, dtype=th.int64, device=dev)
+
+    def lsa():
+        lib_mod.check(lib.sap_lsa_maximize(q.data_ptr(), z.data_ptr(), std.data_ptr(), Bl, n, m, cols.data_ptr(), None, st),
+                      "lsa")
+
+    lsa()
+    lsa_ms = time_launches(th, lsa, 3)
+    rec.update({"lsa_B_run": Bl, "lsa_kernel_ms": round(lsa_ms, 5), "lsa_us_per_env": lsa_ms / Bl * 1e3})
+    del q, out, z, cols
     th.cuda.empty_cache()
     return rec
 
@@ -216,13 +230,13 @@ def main():
         with open(opts.out, "w") as f:
             for r in recs:
                 f.write(json.dumps(r) + "\n")
-    print("\n| env | n = m | B (run) | env kernel ms | env-steps/s | agent-steps/s | GB/s | of HBM peak | select ms | select of peak |"
+    print("\n| env | n = m | B (run) | env kernel ms | env-steps/s | agent-steps/s | GB/s | of HBM peak | select ms | select of peak | LSA us/env |"
           + (" 1-core numpy env-steps/s |" if opts.cpu else ""))
-    print("|---|---|---|---|---|---|---|---|---|---|" + ("---|" if opts.cpu else ""))
+    print("|---|---|---|---|---|---|---|---|---|---|---|" + ("---|" if opts.cpu else ""))
     for r in recs:
         row = (f"| {r['env']} | {r['n']} | {r['B']} ({r['B_run']}) | {r['env_kernel_ms']:.4f} | {r['env_steps_per_s']:.3g} | "
                f"{r['agent_steps_per_s']:.3g} | {r['hbm_gbps']:.0f} | {r['hbm_frac']:.2f} | {r['select_kernel_ms']:.4f} | "
-               f"{r['select_hbm_frac']:.2f} |")
+               f"{r['select_hbm_frac']:.2f} | {r['lsa_us_per_env']:.2f} |")
         if opts.cpu:
             row += f" {r['cpu_env_steps_per_s']:.3g} |"
         print(row)
