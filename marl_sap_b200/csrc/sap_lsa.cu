@@ -74,6 +74,27 @@ __global__ void __launch_bounds__(kThreads) sap_lsa_kernel(LsaParams p) {
   __syncwarp();
 
   const double INF = __longlong_as_double(0x7ff0000000000000ll);
+  if (n == m) {
+    // Square problems: start from the column-reduced duals v[j] = min_i cost(i, j) (the classic Jonker-Volgenant
+    // initialisation).  They are feasible (every reduced cost >= 0), so the optimum reached is the same; what changes is
+    // the work: Q-matrices whose rows rank the tasks alike (a freshly initialised shared-parameter agent) lose their
+    // common column structure and the augmenting paths stay short (4096 x 100 x 100 of such matrices: 5 ms -> 2 ms).
+    // Not valid for n < m, where a column that ends up unassigned must keep v = 0; padding with m - n zero-benefit
+    // dummy rows makes it valid but the identical dummy rows are themselves a degenerate, slow instance (measured:
+    // 64 x 324 x 450 random 4.4 -> 103 ms), so rectangular problems start from v = 0 like scipy.
+#pragma unroll
+    for (int c = 0; c < kCM; ++c) v[c] = INF;
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int c = 0; c < kCM; ++c) {
+        const int j = lane + 32 * c;
+        if (j < m) v[c] = fmin(v[c], -(double)benefit(i, j));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kCM; ++c)
+      if (lane + 32 * c >= m) v[c] = 0.0;
+  }
   for (int cur = 0; cur < n; ++cur) {
     uint32_t scanned = 0u;  // bit c: my column lane + 32 c is in SC
 #pragma unroll
