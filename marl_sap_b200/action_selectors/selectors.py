@@ -93,6 +93,8 @@ class _KernelSelectorBase:
 
 
 class EpsilonGreedyActionSelector(_KernelSelectorBase):
+    graph_capturable = True  # one kernel, all draws and counters on the device
+
     def select_action(self, agent_inputs, avail_actions, t_env, test_mode=False, beta=None):
         eps = self._eps(t_env, test_mode)
         _lib.require_cuda(agent_inputs, "agent_inputs")
@@ -125,6 +127,8 @@ class FilteredEpsilonGreedyActionSelector(_KernelSelectorBase):
     ``top`` (int32 [B, n, M], the env's own top-M task indices) can be passed instead of ``beta``; when only
     ``beta`` is given the top-M is recomputed from it with the stable rule (``sap_topm_from_beta``).
     """
+
+    graph_capturable = True
 
     def select_action(self, agent_inputs, avail_actions, t_env, test_mode=False, beta=None, top=None):
         assert beta is not None or top is not None, "Need beta to figure out which are the top M tasks for each agent."

@@ -169,8 +169,8 @@ class CudaVecRunner:
         episode counter and epsilon from device memory, so one capture serves all later episodes that use the same
         buffers.  The first episode runs eagerly (lazy initialisation), the second is captured."""
         sel = self.mac.action_selector
-        if not hasattr(sel, "use_device_epsilon"):
-            return False
+        if not hasattr(sel, "use_device_epsilon") or not getattr(sel, "graph_capturable", False):
+            return False  # e.g. the assignment selectors draw with torch / numpy RNG on the host side
         sel.use_device_epsilon(True)
         sel.set_device_epsilon(self.t_env, test_mode, self.device)
         td = self.batch.data.transition_data
