@@ -103,6 +103,11 @@ class CudaVecRunner:
         self.mac.action_selector.envs = [self.get_env()]
         if hasattr(self.mac.action_selector, "bind_counters"):
             self.mac.action_selector.bind_counters(self.episode_ctr, self.env.k)
+        js = getattr(self.mac, "jumpstart_action_selector", None)
+        if js is not None:  # JumpstartMAC: the non-learning policy reads the env state directly
+            js.envs = [self.get_env()]
+            if hasattr(js, "bind_env"):
+                js.bind_env(self.env)
         # fp32 staging of the agent network's input: the env kernel writes float(obs) of the new slot into it, so
         # the per-step `batch["obs"][:, t].float()` conversion of basic_controller.py:82 disappears
         self.agent_in = None

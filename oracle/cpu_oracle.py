@@ -325,6 +325,17 @@ def lsa_maximize(benefit: np.ndarray, z: np.ndarray | None = None, std: np.ndarr
     return np.stack(cols).astype(np.int64), np.asarray(obj)
 
 
+def haa_actions(beta: np.ndarray, prev: np.ndarray, lambda_: float, T_trans=None, buffer_dtype=np.float16) -> np.ndarray:
+    """HAASelector.select_action (non_rl_selectors.py:18-50) on real-env state: beta is read back from the episode
+    batch, i.e. rounded to the scheme dtype (fp16, real_constellation_env.py:96), then
+    linear_sum_assignment(beta_hat(beta, prev)[..., 0], maximize=True) per env."""
+    from scipy.optimize import linear_sum_assignment
+
+    b = np.asarray(beta).astype(buffer_dtype).astype(np.float64)
+    bh = real_beta_hat_full(b, np.asarray(prev, dtype=np.int64), lambda_, T_trans)[..., 0]
+    return np.stack([linear_sum_assignment(bh[e], maximize=True)[1] for e in range(bh.shape[0])]).astype(np.int64)
+
+
 def filtered_benefit_matrix(q: np.ndarray, top: np.ndarray, m: int, u_tie: np.ndarray) -> np.ndarray:
     """filtered_sap_selectors.py:43-57: baseline + U * 1e-8 everywhere, the top-M tasks get their own Q-values (fp32)."""
     B, n, _ = q.shape

@@ -281,6 +281,35 @@ def golden_sap_selectors(R):
     np.savez_compressed(os.path.join(HERE, "sap_selectors.npz"), **out)
 
 
+def golden_haa(R):
+    """HAASelector (non_rl_selectors.py:10-50) of the unmodified reference on real-env states: at every step of a short
+    episode, the reference's pick from the state fields (beta, prev_assigns) of its own EpisodeBatch."""
+    import importlib
+
+    import torch as th
+
+    non_rl = importlib.import_module("action_selectors.non_rl_selectors")
+    rng = np.random.default_rng(77)
+    n, m, T, L, M, N, lam = 6, 9, 5, 3, 4, 3, 0.5
+    S = O.gen_dense(rng, 1, n, m, T)[0]
+    env = R.real_env.RealConstellationEnv(1, n, m=m, T=T, N=N, M=M, L=L, lambda_=lam,
+                                          sat_prox_mat=S.astype(np.float64), graphs=1)
+    args = SimpleNamespace(use_mps_action_selection=False, device="cpu", runner="episode")
+    sel = non_rl.HAASelector(args)
+    sel.envs = [env]
+    batch = R.episode_buffer.EpisodeBatch(env.scheme, {"agents": n}, 1, T + 1, preprocess=env.preprocess, device="cpu")
+    env.reset()
+    picks, follow = [], rng.integers(0, m, size=(T, n))
+    for t in range(T):
+        batch.update(env.get_pretransition_data(), ts=t)
+        a = sel.select_action(batch[:, t]).numpy().astype(np.int64)[0]
+        picks.append(a)
+        # alternate between following HAA and a random joint action so that prev_assigns varies
+        env.step(a if t % 2 == 0 else follow[t])
+    np.savez_compressed(os.path.join(HERE, "haa.npz"), S=S, L=L, M=M, N=N, lambda_=lam, haa_actions=np.stack(picks),
+                        follow=follow)
+
+
 class _inject:
     """Feed injected uniforms to th.rand_like (in call order) and replace Categorical.sample by the
     rank-select contract of oracle.random_available_action."""
@@ -377,6 +406,7 @@ def main():
     golden_mock(R)
     golden_selectors(R)
     golden_sap_selectors(R)
+    golden_haa(R)
     golden_buffer(R)
     golden_runner(R)
     for f in sorted(os.listdir(HERE)):

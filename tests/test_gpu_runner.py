@@ -362,3 +362,50 @@ def test_runner_with_assignment_selectors_matches_oracle(selector, agent):
     for t in range(T):
         for b in range(B):
             assert len(set(acts[b, t].tolist())) == n  # an assignment: no two agents on one task
+
+
+def test_haa_selector_and_jumpstart_mac():
+    """haa_selector + jumpstart_mac (filtered_reda.yaml): HAA picks equal the reference's on its golden episode, through
+    the env-bound path and through the batch's own state fields; a jump-started rollout matches the oracle."""
+    import os
+
+    from marl_sap_b200.action_selectors.non_rl_selectors import REGISTRY as non_rl
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "haa.npz")))
+    S = g["S"].astype(np.float32)
+    n, m, T = S.shape
+    L, M, N, lam = int(g["L"]), int(g["M"]), int(g["N"]), float(g["lambda_"])
+    B = 3
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=lam, sat_prox_mat=S, graphs=1)
+    args = make_args("real_constellation_env", env_args, B, selector="filtered_const_sap", agent="flat_const_agent",
+                     mac="jumpstart_mac", jumpstart_action_selector="haa_selector", jumpstart_epsilon_start=1.0,
+                     jumpstart_epsilon_finish=1.0, jumpstart_epsilon_anneal_time=1, jumpstart_evaluation_epsilon=1.0)
+    runner, mac, buffer, logger = build(args)
+    assert type(mac).__name__ == "JumpstartMAC"
+    # 1. pure HAA rollout (jumpstart epsilon = 1): every step the optimal assignment of beta_hat
+    st = O.RealState(np.broadcast_to(S, (B, n, m, T)).astype(np.float64), L, M, N, lam)
+    want = O.rollout(st, lambda t, pre: O.haa_actions(pre["beta"], pre["prev_assigns"], lam), "real")
+    with th.no_grad():
+        batch = runner.run(test_mode=False)
+    assert th.equal(batch["actions"][..., 0].cpu(), th.tensor(want["actions"]).to(th.int16))
+    assert th.equal(batch["rewards"].cpu(), th.tensor(want["rewards"], dtype=th.float16))
+    np.testing.assert_array_equal(want["actions"][0, 0], g["haa_actions"][0])  # the reference's own first pick
+    # 2. the reference's golden episode step by step, once via the bound env and once via the batch fields
+    for bound in (True, False):
+        runner.reset()
+        sel = non_rl["haa_selector"](args)
+        if bound:
+            sel.bind_env(runner.env)
+        else:
+            sel._env = None
+            sel.args.env_args = env_args
+        for t, want_a in enumerate(g["haa_actions"]):
+            if bound:
+                got = sel.select_action(runner.batch, t)
+            else:  # generic path needs prev_assigns / beta in the batch (beta is materialised lazily)
+                got = sel.select_action(runner.batch, t)
+            np.testing.assert_array_equal(got[0].cpu().numpy(), want_a)
+            a = want_a if t % 2 == 0 else g["follow"][t]
+            runner.env.step(th.tensor(np.broadcast_to(a, (B, n)).copy(), device="cuda"), runner.batch)
+    with pytest.raises(NotImplementedError, match="haal_selector"):
+        non_rl["haal_selector"](args)

@@ -123,3 +123,15 @@ def test_sap_selectors_oracle_matches_reference():
         np.testing.assert_array_equal(got, want)
     got, _ = O.lsa_maximize(mat)
     np.testing.assert_array_equal(got, g["fepsgr_test_actions"])
+
+
+def test_haa_oracle_matches_reference():
+    """HAASelector of the reference (non_rl_selectors.py:10-50) along a short real-env episode."""
+    g = _load("haa.npz")
+    S = g["S"][None].astype(np.float64)
+    st = O.RealState(S, int(g["L"]), int(g["M"]), int(g["N"]), float(g["lambda_"]))
+    st.reset()
+    for t, want in enumerate(g["haa_actions"]):
+        got = O.haa_actions(st.beta, st.prev, float(g["lambda_"]))[0]
+        np.testing.assert_array_equal(got, want)
+        st.step((want if t % 2 == 0 else g["follow"][t])[None])
