@@ -165,6 +165,14 @@ int sap_select_filtered_epsilon_greedy(const float* q, const int32_t* top, const
 int sap_topm_from_beta(const void* beta, int32_t dtype, int32_t B, int32_t n, int32_t m, int32_t L, int32_t M,
                        int32_t* top_out, void* stream);
 
+/* sap_sample_categorical = `Categorical(probs).sample()` of the policy-sampling selectors
+ *   (action_selectors/classic_selectors.py:15-27 MultinomialActionSelector, :56-64 SoftPoliciesSelector,
+ *   filtered_classic_selectors.py:65-102): rows of `A` unnormalised probabilities (masked by `avail` when given).
+ *   torch.multinomial's stream cannot be reproduced, so the draw is an input: out[r] = first k with
+ *   cdf[k] > u[r] * cdf[A-1], cdf accumulated in float64.  u [rows] fp32 in [0, 1). */
+int sap_sample_categorical(const float* probs, const uint8_t* avail, int64_t rows, int32_t A, const float* u, int64_t* out,
+                           void* stream);
+
 /* ---- episode buffer -------------------------------------------------------------------------
  * sap_buffer_insert  = ReplayBuffer.insert_episode_batch (components/episode_buffer.py:244-259):
  *   copies `count` episode rows of `row_bytes` each from src (starting at src_row0) into the ring

@@ -68,6 +68,7 @@ SIGNATURES = {
     "sap_real_beta_window": (C.c_int, [_DIMS, _P, _P, _P, _I32, _P]),
     "sap_bias_act": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
     "sap_lsa_maximize": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "sap_sample_categorical": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
 }
 
 _lib = None

@@ -1,8 +1,9 @@
 """Selector registry with the reference's ten keys (/root/reference/src/action_selectors/__init__.py:9-18).
 
-The two keys on the rollout hot path and the four assignment ("SAP") selectors are
-implemented as CUDA kernels; the policy-sampling and bids-as-actions selectors raise a clear error.
+The two keys on the rollout hot path, the four assignment ("SAP") selectors and the
+three policy-sampling selectors are backed by CUDA kernels; only the bids-as-actions selector raises a clear error.
 """
+from .policy_selectors import FilteredSoftPoliciesSelector, MultinomialActionSelector, SoftPoliciesSelector
 from .sap_selectors import (EpsilonGreedySAPTestActionSelector, FilteredEpsGrSAPTestActionSelector,
                             FilteredSAPActionSelector, SequentialAssignmentProblemSelector)
 from .selectors import EpsilonGreedyActionSelector, FilteredEpsilonGreedyActionSelector
@@ -19,9 +20,9 @@ def _next_row(name, why):
 REGISTRY = {}
 REGISTRY["epsilon_greedy"] = EpsilonGreedyActionSelector
 REGISTRY["filtered_const_epsilon_greedy"] = FilteredEpsilonGreedyActionSelector
-REGISTRY["multinomial"] = _next_row("multinomial", "policy-sampling selector, next after the epsilon-greedy pair")
-REGISTRY["soft_policies"] = _next_row("soft_policies", "policy-sampling selector, next after the epsilon-greedy pair")
-REGISTRY["filtered_const_soft_policies"] = _next_row("filtered_const_soft_policies", "policy-sampling selector")
+REGISTRY["multinomial"] = MultinomialActionSelector
+REGISTRY["soft_policies"] = SoftPoliciesSelector
+REGISTRY["filtered_const_soft_policies"] = FilteredSoftPoliciesSelector
 REGISTRY["continuous"] = _next_row("continuous", "bids-as-actions path (scipy linear_sum_assignment in the env)")
 REGISTRY["sap"] = SequentialAssignmentProblemSelector
 REGISTRY["epsilon_greedy_sap_test"] = EpsilonGreedySAPTestActionSelector

@@ -361,6 +361,58 @@ extern "C" int sap_select_filtered_epsilon_greedy(const float* q, const int32_t*
   return SAP_OK;
 }
 
+// Categorical sampling by inverse CDF, one warp per row: out = first k with cdf[k] > u * cdf[A-1], cdf accumulated in
+// float64 over probs * avail.  Lane l owns the contiguous chunk [l * per, (l + 1) * per).
+__global__ void __launch_bounds__(kThreads) sap_sample_categorical_kernel(const float* __restrict__ probs,
+                                                                          const uint8_t* __restrict__ avail, int64_t rows,
+                                                                          int A, const float* __restrict__ u,
+                                                                          int64_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* pr = probs + row * A;
+  const uint8_t* av = avail ? avail + row * A : nullptr;
+  const int per = (A + 31) / 32, j0 = lane * per, j1 = min(A, j0 + per);
+  double part = 0.0;
+  for (int j = j0; j < j1; ++j) part += (av && !av[j]) ? 0.0 : (double)pr[j];
+  double incl = part;  // inclusive scan of the lane sums
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double o = __shfl_up_sync(SAP_FULL_MASK, incl, off);
+    if (lane >= off) incl += o;
+  }
+  const double total = __shfl_sync(SAP_FULL_MASK, incl, 31);
+  const double target = (double)u[row] * total;
+  const unsigned hit = __ballot_sync(SAP_FULL_MASK, incl > target);  // lanes whose chunk end passes the target
+  int pick = A - 1;
+  if (hit) {
+    const int owner = __ffs(hit) - 1;
+    if (lane == owner) {
+      double c = incl - part;
+      for (int j = j0; j < j1; ++j) {
+        c += (av && !av[j]) ? 0.0 : (double)pr[j];
+        if (c > target) {
+          pick = j;
+          break;
+        }
+      }
+    }
+    pick = __shfl_sync(SAP_FULL_MASK, pick, owner);
+  }
+  if (lane == 0) out[row] = (int64_t)pick;
+}
+
+extern "C" int sap_sample_categorical(const float* probs, const uint8_t* avail, int64_t rows, int32_t A, const float* u,
+                                      int64_t* out, void* stream) {
+  SAP_REQUIRE(probs && u && out, SAP_E_NULL, "sap_sample_categorical: probs/u/out is null");
+  SAP_REQUIRE(rows >= 0 && A > 0, SAP_E_DIMS, "sap_sample_categorical: bad dims rows=%lld A=%d", (long long)rows, A);
+  if (rows == 0) return SAP_OK;
+  sap_sample_categorical_kernel<<<(unsigned)((rows + kWarps - 1) / kWarps), kThreads, 0, (cudaStream_t)stream>>>(
+      probs, avail, rows, A, u, out);
+  SAP_CUDA_LAUNCH_CHECK("sap_sample_categorical_kernel");
+  return SAP_OK;
+}
+
 extern "C" int sap_topm_from_beta(const void* beta, int32_t dtype, int32_t B, int32_t n, int32_t m, int32_t L, int32_t M,
                                   int32_t* top_out, void* stream) {
   SAP_REQUIRE(beta && top_out, SAP_E_NULL, "sap_topm_from_beta: beta/top_out is null");

@@ -303,6 +303,18 @@ def select_filtered_epsilon_greedy(q, top, avail, m, eps, u_tie, u_explore, u_ac
 
 
 # ------------------------------------------------------------------ episode buffer semantics
+def sample_categorical(probs: np.ndarray, u: np.ndarray, avail: np.ndarray | None = None) -> np.ndarray:
+    """Contract of the policy-sampling selectors' Categorical(p).sample() (classic_selectors.py:25-26, :61-63) with an
+    injected uniform per row: the first k with cdf[k] > u * cdf[-1], cdf in float64 (zero-probability actions are never
+    drawn, like torch.multinomial)."""
+    p = probs.astype(np.float64)
+    if avail is not None:
+        p = p * (np.asarray(avail) != 0)
+    cdf = np.cumsum(p, axis=-1)
+    target = u.astype(np.float64)[..., None] * cdf[..., -1:]
+    return np.minimum((cdf <= target).sum(-1), p.shape[-1] - 1).astype(np.int64)
+
+
 def sap_noise_std(benefit: np.ndarray, eps: float) -> np.ndarray:
     """stds = ones * mean|benefit[b]| * eps * 2, fp32 like torch (sap_selectors.py:84-85)."""
     avg = np.abs(benefit.astype(np.float32)).mean(axis=(1, 2), dtype=np.float32)

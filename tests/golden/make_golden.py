@@ -281,6 +281,55 @@ def golden_sap_selectors(R):
     np.savez_compressed(os.path.join(HERE, "sap_selectors.npz"), **out)
 
 
+def golden_policy_selectors(R):
+    """Multinomial / SoftPolicies / FilteredSoftPolicies selectors of the reference.  Categorical.sample is replaced by
+    the injected-uniform contract of oracle.sample_categorical and th.rand by recorded draws, so the fixture pins the
+    masking, the greedy test branch and the filtered index mapping of the reference code."""
+    import torch as th
+    from torch.distributions import Categorical
+
+    rng = np.random.default_rng(55)
+    B, n, m, M, L = 3, 6, 10, 4, 3
+    args = SimpleNamespace(epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=1000, evaluation_epsilon=0.0,
+                           use_mps_action_selection=True, device="cpu", env_args={"M": M}, test_greedy=True)
+    p = rng.random((B, n, m)).astype(np.float32)
+    p[0, 0, :3] = 0.0
+    p /= p.sum(-1, keepdims=True)
+    avail = rng.random((B, n, m)) > 0.3
+    avail[..., 0] |= ~avail.any(-1)
+    u = rng.random((B, n), dtype=np.float32)
+    u[0, 0], u[0, 1] = 0.0, np.float32(1.0 - 2.0 ** -24)
+    orig_sample, orig_rand = Categorical.sample, th.rand
+    state = {}
+
+    def sample(dist, sample_shape=th.Size()):
+        return th.tensor(O.sample_categorical(dist.probs.numpy(), state["u"]))
+
+    Categorical.sample = sample
+    try:
+        state["u"] = u
+        msel = R.classic_selectors.MultinomialActionSelector(args)
+        a_train = msel.select_action(th.tensor(p), th.tensor(avail), 0, test_mode=False).numpy()
+        a_test = msel.select_action(th.tensor(p), th.tensor(avail), 0, test_mode=True).numpy()
+        ssel = R.classic_selectors.SoftPoliciesSelector(args)
+        a_soft = ssel.select_action(th.tensor(p), th.tensor(avail), 0).numpy()
+        pf = rng.random((B, n, M + 1)).astype(np.float32)
+        pf /= pf.sum(-1, keepdims=True)
+        beta = O.gen_exact(rng, B, n, m, L)[..., :L]
+        beta = (beta + (rng.permutation(B * n * m).reshape(B, n, m, 1) + 1).astype(np.float32) * np.float32(2.0 ** -20)).astype(np.float32)
+        u_rand = rng.random((B, n, m), dtype=np.float32)
+        th.rand = lambda *a, **k: th.tensor(u_rand)
+        fsel = R.filtered_selectors.FilteredSoftPoliciesSelector(args)
+        uf = rng.random((B, n), dtype=np.float32)
+        uf[0, :3] = np.float32(0.999)  # force the "anything else" slot
+        state["u"] = uf
+        a_filt = fsel.select_action(th.tensor(pf), th.tensor(avail), 0, beta=th.tensor(beta)).numpy()
+    finally:
+        Categorical.sample, th.rand = orig_sample, orig_rand
+    np.savez_compressed(os.path.join(HERE, "policy_selectors.npz"), p=p, avail=avail, u=u, multinomial_train=a_train,
+                        multinomial_test=a_test, soft=a_soft, pf=pf, beta=beta, u_rand=u_rand, uf=uf, filtered=a_filt, M=M)
+
+
 def golden_haa(R):
     """HAASelector (non_rl_selectors.py:10-50) of the unmodified reference on real-env states: at every step of a short
     episode, the reference's pick from the state fields (beta, prev_assigns) of its own EpisodeBatch."""
@@ -407,6 +456,7 @@ def main():
     golden_selectors(R)
     golden_sap_selectors(R)
     golden_haa(R)
+    golden_policy_selectors(R)
     golden_buffer(R)
     golden_runner(R)
     for f in sorted(os.listdir(HERE)):

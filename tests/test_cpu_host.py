@@ -105,7 +105,7 @@ def test_registries_have_the_reference_keys():
                                    "interference_constellation_env", "dictator_env"])
     assert sorted(runners) == ["episode", "parallel"]
     with pytest.raises(NotImplementedError, match="not built yet"):
-        sel["multinomial"](SimpleNamespace())
+        sel["continuous"](SimpleNamespace())
     assert sel["sap"].__name__ == "SequentialAssignmentProblemSelector"
     with pytest.raises(NotImplementedError, match="hot path"):
         envs["dictator_env"]()

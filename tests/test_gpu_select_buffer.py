@@ -83,6 +83,50 @@ def test_sap_selectors_match_reference_golden():
     assert a.shape == (g["fsap_q"].shape[0], g["fsap_q"].shape[1]) and int(a.min()) >= 0 and int(a.max()) < m
 
 
+def test_policy_selectors_match_reference_golden():
+    """multinomial / soft_policies / filtered_const_soft_policies against the reference's picks (same uniforms)."""
+    from marl_sap_b200.action_selectors import REGISTRY
+
+    g = dict(np.load(os.path.join(GOLDEN, "policy_selectors.npz")))
+    M, m = int(g["M"]), g["p"].shape[2]
+    args = _args(env_args={"M": M, "m": m}, test_greedy=True)
+    msel = REGISTRY["multinomial"](args)
+    msel.inject_draws(u_sample=_cu(g["u"]))
+    np.testing.assert_array_equal(msel.select_action(_cu(g["p"]), _cu(g["avail"]), 0).cpu().numpy(), g["multinomial_train"])
+    np.testing.assert_array_equal(msel.select_action(_cu(g["p"]), _cu(g["avail"]), 0, test_mode=True).cpu().numpy(),
+                                  g["multinomial_test"])
+    ssel = REGISTRY["soft_policies"](args)
+    ssel.inject_draws(u_sample=_cu(g["u"]))
+    np.testing.assert_array_equal(ssel.select_action(_cu(g["p"]), _cu(g["avail"]), 0).cpu().numpy(), g["soft"])
+    fsel = REGISTRY["filtered_const_soft_policies"](args)
+    fsel.inject_draws(u_sample=_cu(g["uf"]), u_rand=_cu(g["u_rand"]))
+    got = fsel.select_action(_cu(g["pf"]), _cu(g["avail"]), 0, beta=_cu(g["beta"]))
+    np.testing.assert_array_equal(got.cpu().numpy(), g["filtered"])
+
+
+@pytest.mark.parametrize("rows,A,masked", [(1000, 100, True), (77, 450, False), (33, 5, True), (4, 1, False)])
+def test_sample_categorical_matches_oracle(rows, A, masked):
+    """sap_sample_categorical vs the float64 inverse-CDF contract; the empirical distribution follows the probabilities."""
+    from marl_sap_b200.action_selectors.policy_selectors import sample_categorical
+
+    rng = np.random.default_rng(rows + A)
+    p = rng.random((rows, A)).astype(np.float32)
+    p[:, ::3] = 0.0 if A > 3 else p[:, ::3]
+    avail = (rng.random((rows, A)) > 0.3) if masked else None
+    if masked:
+        avail[:, -1] = True
+    u = rng.random(rows, dtype=np.float32)
+    u[:2] = [0.0, np.float32(1.0 - 2.0 ** -24)][: min(2, rows)]
+    got = sample_categorical(_cu(p), None if avail is None else _cu(avail), _cu(u)).cpu().numpy()
+    np.testing.assert_array_equal(got, O.sample_categorical(p, u, avail))
+    eff = p if avail is None else p * avail
+    assert (eff[np.arange(rows), got] > 0).all()  # a zero-probability action is never drawn
+    if rows >= 1000:  # the kernel's own uniforms: frequencies of one fixed distribution
+        q = np.tile(np.array([0.5, 0.0, 0.3, 0.2], np.float32), (20000, 1))
+        freq = np.bincount(sample_categorical(_cu(q)).cpu().numpy(), minlength=4) / 20000
+        np.testing.assert_allclose(freq, [0.5, 0.0, 0.3, 0.2], atol=0.02)
+
+
 @pytest.mark.parametrize("B,n,m,noise", [(8, 4, 4, False), (33, 10, 10, True), (16, 50, 50, True), (64, 100, 100, True),
                                          (5, 37, 53, True), (3, 324, 450, True), (2, 200, 512, False), (4, 1, 7, True)])
 def test_lsa_kernel_matches_scipy(B, n, m, noise):

@@ -135,3 +135,19 @@ def test_haa_oracle_matches_reference():
         got = O.haa_actions(st.beta, st.prev, float(g["lambda_"]))[0]
         np.testing.assert_array_equal(got, want)
         st.step((want if t % 2 == 0 else g["follow"][t])[None])
+
+
+def test_policy_selectors_oracle_matches_reference():
+    """Multinomial / SoftPolicies / FilteredSoftPolicies (classic_selectors.py:5-27, 56-64, filtered_classic_selectors.py:
+    65-102) with the injected-uniform sampling contract."""
+    g = _load("policy_selectors.npz")
+    np.testing.assert_array_equal(O.sample_categorical(g["p"], g["u"], g["avail"]), g["multinomial_train"])
+    np.testing.assert_array_equal((g["p"] * g["avail"]).argmax(-1), g["multinomial_test"])
+    np.testing.assert_array_equal(O.sample_categorical(g["p"], g["u"]), g["soft"])
+    M = int(g["M"])
+    top = O.top_m_tasks(g["beta"], M)
+    picked = O.sample_categorical(g["pf"], g["uf"])
+    masked = g["u_rand"].copy()
+    np.put_along_axis(masked, top, -1.0, axis=2)
+    choices = np.concatenate([top, masked.argmax(-1)[..., None]], axis=2)
+    np.testing.assert_array_equal(np.take_along_axis(choices, picked[..., None], axis=2)[..., 0], g["filtered"])
