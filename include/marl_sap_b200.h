@@ -102,6 +102,15 @@ int sap_benefit_ingest(const float* src_nmT, float* dst_Tnm, int32_t B, int32_t 
 int sap_benefit_upload_host(const float* src_nmT_host, float* staging_dev, float* dst_Tnm, int32_t B, int32_t n,
                             int32_t m, int32_t T, void* stream);
 
+/* sap_benefit_generate = generate_benefits_over_time (envs/mock_constellation_env.py:276-299), the synthetic
+ * "constellation-like" benefits MockConstellationEnv draws in its constructor (:34, widths 5..8) and at every reset
+ * (:99-100, widths 3..6) when no sat_prox_mat is given, for B envs at once and straight into the planes layout.
+ * numpy's stream cannot be reproduced: same law (scale in {1,1,1,10} per task, P(active) = 1/4, centre U(0,T),
+ * width U(width_min, width_max), value scale * exp(-(t - centre)^2 / sigma_2 / 2)), Philox draws keyed by
+ * (seed; element, episode). */
+int sap_benefit_generate(float* planes_Tnm, int32_t B, int32_t n, int32_t m, int32_t T, float width_min, float width_max,
+                         uint64_t seed, uint64_t episode, void* stream);
+
 /* Per-plane range metadata, computed once per episode when the benefits are installed:
  * stats[b, t] = {min, max} over planes[b, t, :, :].  The real-env kernels use it to scale window sums into
  * 32-bit selection keys without an extra pass over the window (nullable there: bounds are then derived

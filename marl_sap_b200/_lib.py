@@ -53,6 +53,7 @@ SIGNATURES = {
     "sap_benefit_ingest": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
     "sap_benefit_upload_host": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "sap_benefit_stats": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P]),
+    "sap_benefit_generate": (C.c_int, [_P, _I32, _I32, _I32, _I32, _F32, _F32, _U64, _U64, _P]),
     "sap_real_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_step": (C.c_int, [_DIMS, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_scratch_doubles": (C.c_int64, [_DIMS]),

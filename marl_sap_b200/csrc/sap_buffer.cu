@@ -98,6 +98,36 @@ __global__ void __launch_bounds__(kThreads) sap_onehot_kernel(const void* action
   }
 }
 
+// "Constellation-like" synthetic benefits, the law of generate_benefits_over_time (mock_constellation_env.py:276-299),
+// written straight into the planes layout [B, T, n, m]: per (env, task) a scale drawn from {1, 1, 1, 10}; per
+// (env, agent, task) active with probability 1/4, then a Gaussian bump in time with centre U(0, T) and width
+// U(width_min, width_max).  Draws: Philox4x32-10 keyed by (seed; element, episode).
+__global__ void __launch_bounds__(kThreads) sap_benefit_generate_kernel(float* __restrict__ planes, int B, int n, int m, int T,
+                                                                        float wmin, float wmax, uint64_t seed,
+                                                                        uint64_t episode) {
+  const int64_t total = (int64_t)B * n * m;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t ep_lo = (uint32_t)episode, ep_hi = (uint32_t)(episode >> 32);
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+    const int j = (int)(e % m);
+    const int64_t bi = e / m;
+    const int i = (int)(bi % n), b = (int)(bi / n);
+    const SapPhilox4 rs = sap_philox4x32_10((uint32_t)(b * m + j), ep_lo, ep_hi, 0x5CA1Eu, k0, k1);   // :281
+    const float scale = (rs.x >> 30) == 3u ? 10.f : 1.f;
+    const SapPhilox4 r = sap_philox4x32_10((uint32_t)e, (uint32_t)(e >> 32) ^ ep_lo, ep_hi, 0xBEEFu, k0, k1);
+    const bool active = sap_u01(r.x) > 0.75f;                                                          // :284
+    const float center = sap_u01(r.y) * (float)T;                                                      // :288
+    const float spread = wmin + sap_u01(r.z) * (wmax - wmin);                                          // :291
+    const float sigma_2 = sqrtf(spread * spread / (-8.f * logf(0.05f)));                               // :292
+    const float inv = 1.f / (2.f * sigma_2);
+    float* dst = planes + (((int64_t)b * T) * n + i) * m + j;
+    for (int t = 0; t < T; ++t) {
+      const float d = (float)t - center;
+      dst[(int64_t)t * n * m] = active ? scale * expf(-d * d * inv) : 0.f;                             // :297
+    }
+  }
+}
+
 // x[r, c] = act(x[r, c] + bias[c]) in place, 128-bit accesses (cols % 4 == 0, x 16-byte aligned) or scalar
 template <bool kVec>
 __global__ void __launch_bounds__(kThreads) sap_bias_act_kernel(float* __restrict__ x, const float* __restrict__ bias,
@@ -272,6 +302,18 @@ extern "C" int sap_onehot(const void* actions, int32_t actions_dtype, void* oneh
   sap_onehot_kernel<<<grid_for(rows * m), kThreads, 0, (cudaStream_t)stream>>>(actions, actions_dtype, onehot,
                                                                               onehot_dtype, rows, m);
   SAP_CUDA_LAUNCH_CHECK("sap_onehot_kernel");
+  return SAP_OK;
+}
+
+extern "C" int sap_benefit_generate(float* planes_Tnm, int32_t B, int32_t n, int32_t m, int32_t T, float width_min,
+                                    float width_max, uint64_t seed, uint64_t episode, void* stream) {
+  SAP_REQUIRE(planes_Tnm, SAP_E_NULL, "sap_benefit_generate: planes is null");
+  SAP_REQUIRE(B > 0 && n > 0 && m > 0 && T > 0, SAP_E_DIMS, "sap_benefit_generate: bad dims B=%d n=%d m=%d T=%d", B, n, m, T);
+  SAP_REQUIRE(width_min > 0.f && width_max >= width_min, SAP_E_CONSTRAINT, "sap_benefit_generate: bad widths");
+  sap_benefit_generate_kernel<<<grid_for((int64_t)B * n * m), kThreads, 0, (cudaStream_t)stream>>>(planes_Tnm, B, n, m, T,
+                                                                                                width_min, width_max, seed,
+                                                                                                episode);
+  SAP_CUDA_LAUNCH_CHECK("sap_benefit_generate_kernel");
   return SAP_OK;
 }
 

@@ -205,12 +205,28 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
 class BatchedMockConstellationEnv(_BatchedEnvBase):
     kind = "mock"
 
-    def __init__(self, B, n, m, T, L, lambda_, sat_prox_mat=None, T_trans=None, device=None):
+    def __init__(self, B, n, m, T, L, lambda_, sat_prox_mat=None, T_trans=None, device=None, generate_seed=None):
         super().__init__(B, n, m, T, L, 0, 0, lambda_, T_trans, device)
         self.obs_size = (L + 1) * m
         self.scheme, self.preprocess = mock_scheme(n, m, L)
+        # constant_benefits = False in the reference (no sat_prox_mat given, mock_constellation_env.py:32-37): benefits are
+        # drawn in the constructor (widths 5..8) and redrawn at every reset (widths 3..6, :99-100) - here on the device
+        self.constant_benefits = generate_seed is None
+        self._gen_seed, self._gen_episode = generate_seed, 0
         if sat_prox_mat is not None:
             self.load_benefits(sat_prox_mat)
+        elif generate_seed is not None:
+            self.generate_benefits(5.0, 8.0)
+
+    def generate_benefits(self, width_min, width_max):
+        """``generate_benefits_over_time`` for all B envs at once, straight into the planes (``sap_benefit_generate``)."""
+        if self.planes is None or self.planes.shape[0] != self.B:
+            self.planes = th.empty(self.B, self.T, self.n, self.m, dtype=th.float32, device=self.device)
+            self.shared_planes = False
+        _lib.check(self.lib.sap_benefit_generate(self.planes.data_ptr(), self.B, self.n, self.m, self.T, float(width_min),
+                                                 float(width_max), int(self._gen_seed or 0) & 0xFFFFFFFFFFFFFFFF,
+                                                 self._gen_episode, _lib.stream_ptr(self.device)), "sap_benefit_generate")
+        self._gen_episode += 1
 
     def draw_prev_assigns(self):
         """mock_constellation_env.py:105: np.random.choice(m, n, replace=False) per env, host RNG like the reference."""
@@ -220,6 +236,8 @@ class BatchedMockConstellationEnv(_BatchedEnvBase):
 
     def reset(self, batch, prev0=None):
         self._check_batch(batch)
+        if not self.constant_benefits:
+            self.generate_benefits(3.0, 6.0)  # :99-100
         if prev0 is None:
             prev0 = self.draw_prev_assigns()
         prev0 = th.as_tensor(np.asarray(prev0) if not isinstance(prev0, th.Tensor) else prev0, dtype=th.int64)

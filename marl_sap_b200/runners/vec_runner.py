@@ -37,9 +37,13 @@ def build_batched_env(env_name, env_args, B, device):
         env_REGISTRY[env_name]()  # raises the explanatory NotImplementedError for off-path envs
     ea = dict(env_args)
     S = ea.get("sat_prox_mat", None)
+    if S is None and env_name == "mock_constellation_env" and not ea.get("bids_as_actions"):
+        # the reference's MockConstellationEnv draws its own benefits (ctor and every reset): generated on the device
+        return batched_REGISTRY[env_name](B, ea["n"], ea["m"], ea["T"], ea["L"], ea["lambda_"], T_trans=ea.get("T_trans"),
+                                          device=device, generate_seed=int(ea.get("seed", 0) or 0) + 1)
     if S is None:
-        raise NotImplementedError("batched runners need env_args['sat_prox_mat'] ([n,m,T] shared or [B,n,m,T]); "
-                                  "on-device benefit generation is a 'next' row (SURVEY.md 8f-4)")
+        raise NotImplementedError("batched real-env runners need env_args['sat_prox_mat'] ([n,m,T] shared or [B,n,m,T]): "
+                                  "the orbit simulator that would produce it is out of scope (DESIGN.md)")
     shape = tuple(S.shape)
     n, m, T = shape[-3:]
     if ea.get("bids_as_actions"):

@@ -431,3 +431,52 @@ def test_real_env_bench_batch_properties():
         sums.append((batch["obs"].float().sum(dtype=th.float64).item(), batch["rewards"].float().sum(dtype=th.float64).item(),
                      batch["obs"].clone()))
     assert sums[0][0] == sums[1][0] and sums[0][1] == sums[1][1] and th.equal(sums[0][2], sums[1][2])
+
+
+def test_benefit_generation_follows_the_reference_law():
+    """sap_benefit_generate vs the law of generate_benefits_over_time (mock_constellation_env.py:276-299): per-task scale in
+    {1, 10} (P = 3/4, 1/4), P(active) = 1/4, Gaussian bumps whose width lies in the requested range, reproducible per
+    (seed, episode), and the same mean benefit as the oracle's numpy sampler of that law."""
+    from marl_sap_b200.envs.batched import BatchedMockConstellationEnv
+
+    B, n, m, T, L = 48, 20, 30, 60, 3
+    env = BatchedMockConstellationEnv(B, n, m, T, L, 0.5, generate_seed=5)
+    assert not env.constant_benefits
+    ctor = env.planes.clone()           # widths 5..8 (:34)
+    env.generate_benefits(3.0, 6.0)     # what reset() draws (:99-100)
+    P = env.planes.double().cpu().numpy()  # [B, T, n, m]
+    assert not np.array_equal(P, ctor.double().cpu().numpy())
+    peak = P.max(1)                                     # [B, n, m]
+    active = peak > 0
+    assert abs(active.mean() - 0.25) < 0.02
+    tmax = P.argmax(1)
+    interior = active & (tmax > 8) & (tmax < T - 9)     # bumps whose centre is well inside the horizon
+    logp = np.log(np.where(P > 0, P, 1.0))
+    idx = np.argwhere(interior)
+    b, i, j = idx[:, 0], idx[:, 1], idx[:, 2]
+    t0 = tmax[b, i, j]
+    # log of a Gaussian bump is a parabola: its second difference is -1 / sigma_2, and the centre gives the scale back
+    d2 = logp[b, t0 + 1, i, j] - 2 * logp[b, t0, i, j] + logp[b, t0 - 1, i, j]
+    sigma_2 = -1.0 / d2
+    spread = np.sqrt(sigma_2 ** 2 * (-8 * np.log(0.05)))
+    assert spread.min() > 3.0 - 1e-3 and spread.max() < 6.0 + 1e-3
+    d1 = (logp[b, t0 + 1, i, j] - logp[b, t0 - 1, i, j]) / 2
+    center = t0 + d1 * sigma_2
+    scale = np.exp(logp[b, t0, i, j] + (t0 - center) ** 2 / sigma_2 / 2)
+    assert np.all((np.abs(scale - 1) < 1e-3) | (np.abs(scale - 10) < 1e-2))
+    per_task = np.round(scale).astype(int)
+    for bb in range(4):  # one scale per (env, task), shared by all agents
+        for jj in range(m):
+            vals = per_task[(b == bb) & (j == jj)]
+            assert len(set(vals.tolist())) <= 1
+    assert abs((per_task == 10).mean() - 0.25) < 0.08
+    # same law as the numpy sampler of the oracle
+    ref = O.gen_ref_like(np.random.default_rng(0), B, n, m, T)  # [B, n, m, T]
+    assert abs(P.mean() / ref.mean() - 1) < 0.15
+    # reproducible: same (seed, episode) -> same planes; the episode counter advances at every reset
+    env2 = BatchedMockConstellationEnv(B, n, m, T, L, 0.5, generate_seed=5)
+    assert th.equal(env2.planes, ctor)
+    batch = _batch_for(env2, B)
+    env2.reset(batch)
+    assert th.equal(env2.planes, env.planes)
+    assert th.equal(batch["obs"][:, 0, :, m:2 * m].cpu(), env2.planes[:, 0].cpu())  # obs = [onehot | S[:, :, k] | ...]

@@ -409,3 +409,19 @@ def test_haa_selector_and_jumpstart_mac():
             runner.env.step(th.tensor(np.broadcast_to(a, (B, n)).copy(), device="cuda"), runner.batch)
     with pytest.raises(NotImplementedError, match="haal_selector"):
         non_rl["haal_selector"](args)
+
+
+def test_runner_mock_env_draws_its_own_benefits_on_the_device():
+    """MockConstellationEnv without sat_prox_mat (the reference redraws its benefits at every reset,
+    mock_constellation_env.py:99-100): the batched runner generates them on the device, new ones every episode."""
+    args = make_args("mock_constellation_env", dict(n=6, m=8, T=12, L=3, lambda_=0.5), 5)
+    runner, mac, buffer, logger = build(args)
+    assert not runner.env.constant_benefits
+    with th.no_grad():
+        b1 = runner.run(test_mode=False)
+        p1 = runner.env.planes.clone()
+        o1 = b1["obs"].clone()
+        b2 = runner.run(test_mode=False)
+    assert not th.equal(p1, runner.env.planes) and not th.equal(o1, b2["obs"])
+    assert th.equal(o1[:, 0, :, 8:16].cpu(), p1[:, 0].cpu())  # first obs slice = benefits at k = 0
+    assert bool(th.isfinite(b2["rewards"].float()).all()) and int(b2["filled"].sum()) == 5 * 13
