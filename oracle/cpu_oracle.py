@@ -303,6 +303,30 @@ def select_filtered_epsilon_greedy(q, top, avail, m, eps, u_tie, u_explore, u_ac
 
 
 # ------------------------------------------------------------------ episode buffer semantics
+def calc_conflicting_actions(actions: np.ndarray, m: int) -> float:
+    """learners/q_learner.py:157-170, loop for loop."""
+    B, T, n = actions.shape[:3]
+    dup = 0
+    for b in range(B):
+        for k in range(T):
+            cnt = np.zeros(m)
+            for i in range(n):
+                cnt[int(actions[b, k, i])] += 1
+            dup += np.where(cnt > 0, cnt - 1, 0).sum()
+    return dup / B / T
+
+
+def calc_raw_benefits(beta: np.ndarray, actions: np.ndarray) -> float:
+    """learners/q_learner.py:172-191 (4-D beta), loop for loop."""
+    B, T, n = actions.shape[:3]
+    tot = 0.0
+    for b in range(B):
+        for k in range(T):
+            for i in range(n):
+                tot += beta[b, k, i, int(actions[b, k, i])]
+    return tot / B / T / n
+
+
 def sample_categorical(probs: np.ndarray, u: np.ndarray, avail: np.ndarray | None = None) -> np.ndarray:
     """Contract of the policy-sampling selectors' Categorical(p).sample() (classic_selectors.py:25-26, :61-63) with an
     injected uniform per row: the first k with cdf[k] > u * cdf[-1], cdf in float64 (zero-probability actions are never

@@ -425,3 +425,20 @@ def test_runner_mock_env_draws_its_own_benefits_on_the_device():
     assert not th.equal(p1, runner.env.planes) and not th.equal(o1, b2["obs"])
     assert th.equal(o1[:, 0, :, 8:16].cpu(), p1[:, 0].cpu())  # first obs slice = benefits at k = 0
     assert bool(th.isfinite(b2["rewards"].float()).all()) and int(b2["filled"].sum()) == 5 * 13
+
+
+def test_rollout_diagnostics_match_the_learner_loops():
+    """Device versions of q_learner.py:157-191 (conflicts per joint action, mean chosen benefit) vs the loops."""
+    from marl_sap_b200.utils.rollout_stats import (calc_conflicting_actions, calc_raw_benefits,
+                                                   calc_raw_benefits_from_planes)
+
+    rng = np.random.default_rng(3)
+    B, T, n, m = 4, 7, 9, 6
+    acts = rng.integers(0, m, size=(B, T, n))
+    beta = rng.random((B, T, n, m)).astype(np.float32)
+    a = th.tensor(acts).cuda().unsqueeze(-1).to(th.int16)
+    assert calc_conflicting_actions(a, m) == pytest.approx(O.calc_conflicting_actions(acts, m), rel=1e-12)
+    want = O.calc_raw_benefits(beta.astype(np.float64), acts)
+    assert calc_raw_benefits(th.tensor(beta).cuda(), a) == pytest.approx(want, rel=1e-9)
+    assert calc_raw_benefits(th.tensor(beta).cuda().unsqueeze(-1).expand(-1, -1, -1, -1, 3), a) == pytest.approx(want, rel=1e-9)
+    assert calc_raw_benefits_from_planes(th.tensor(beta).cuda(), a) == pytest.approx(want, rel=1e-9)
