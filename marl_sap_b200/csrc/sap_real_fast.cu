@@ -719,18 +719,35 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
         if (l < Leff) va[l] = ldg_hint4(win + (size_t)l * nm + (size_t)e4 * 4, pol_drop);
         if (l < Leff && has_b) vb[l] = ldg_hint4(win + (size_t)l * nm + (size_t)e4b * 4, pol_drop);
       }
+      if (C::kCommon) {
+        // L = 3, fp16: planes 0 and 1 interleaved as half2 per (agent, task), plane 2 behind them: the gather reads
+        // a pair's three benefits with two loads (one 32-bit, one 16-bit) instead of three
+        auto put_pair = [&](int e4, const float4 (&v)[4]) {
+          __half2 h[4] = {__floats2half2_rn(v[0].x, v[1].x), __floats2half2_rn(v[0].y, v[1].y),
+                          __floats2half2_rn(v[0].z, v[1].z), __floats2half2_rn(v[0].w, v[1].w)};
+          *reinterpret_cast<uint4*>(reinterpret_cast<__half2*>(tile) + (size_t)e4 * 4) = *reinterpret_cast<const uint4*>(h);
+          __half2 g2[2] = {__floats2half2_rn(v[2].x, v[2].y), __floats2half2_rn(v[2].z, v[2].w)};
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(tile) + 2 * (size_t)nm + (size_t)e4 * 4) =
+              *reinterpret_cast<const uint2*>(g2);
+        };
+        put_pair(e4, va);
+        if (has_b) put_pair(e4b, vb);
+      } else {
 #pragma unroll
-      for (int l = 0; l < 4; ++l)
-        if (l < L) {
-          put4(l, e4, va[l]);
-          if (has_b) put4(l, e4b, vb[l]);
-        }
+        for (int l = 0; l < 4; ++l)
+          if (l < L) {
+            put4(l, e4, va[l]);
+            if (has_b) put4(l, e4b, vb[l]);
+          }
+      }
     }
   } else {
     for (int e = tid; e < L * nm; e += kThreads) {
       const int l = e / nm, x = e - l * nm;
       const double pr = kPrios ? sPrio[x % m] : 1.0;
-      tile[e] = to_out<OutT>(l < Leff ? (double)win[e] * pr : 0.0);
+      const OutT o = to_out<OutT>(l < Leff ? (double)win[e] * pr : 0.0);
+      if (C::kCommon) tile[l < 2 ? 2 * x + l : 2 * nm + x] = o;  // same paired layout as the vector path
+      else tile[e] = o;
     }
   }
   __syncthreads();
@@ -773,10 +790,19 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
           const uint32_t ps = code[g] >> 8, qs = code[g] & 0xffu;
           const int a = ps == 0xffu ? i : a_r[g];
           const int j = (qs & 0x80u) ? j_o[g] : j_d[g];
-          const OutT* src = tile + a * m + j;
+          if (C::kCommon) {
+            const int x = a * m + j;
+            const uint32_t p01 = reinterpret_cast<const uint32_t*>(tile)[x];
+            const __half2 h01 = *reinterpret_cast<const __half2*>(&p01);
+            val[g][0] = *reinterpret_cast<const OutT*>(&h01.x);
+            val[g][1] = *reinterpret_cast<const OutT*>(&h01.y);
+            val[g][2] = tile[2 * nm + x];
+          } else {
+            const OutT* src = tile + a * m + j;
 #pragma unroll
-          for (int l = 0; l < 4; ++l)
-            if (l < L) val[g][l] = src[(size_t)l * nm];
+            for (int l = 0; l < 4; ++l)
+              if (l < L) val[g][l] = src[(size_t)l * nm];
+          }
         }
 #pragma unroll
         for (int g = 0; g < kGB; ++g) {
