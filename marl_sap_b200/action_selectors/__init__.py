@@ -1,8 +1,10 @@
 """Selector registry with the reference's ten keys (/root/reference/src/action_selectors/__init__.py:9-18).
 
 The two keys on the rollout hot path, the four assignment ("SAP") selectors and the
-three policy-sampling selectors are backed by CUDA kernels; only the bids-as-actions selector raises a clear error.
+three policy-sampling selectors are backed by CUDA kernels; the bids-as-actions selector adds its noise with torch and
+the env turns the bids into assignments with the batched assignment kernel.  All ten keys of the reference resolve.
 """
+from .bet_selectors import ContinuousActionSelector
 from .policy_selectors import FilteredSoftPoliciesSelector, MultinomialActionSelector, SoftPoliciesSelector
 from .sap_selectors import (EpsilonGreedySAPTestActionSelector, FilteredEpsGrSAPTestActionSelector,
                             FilteredSAPActionSelector, SequentialAssignmentProblemSelector)
@@ -23,7 +25,7 @@ REGISTRY["filtered_const_epsilon_greedy"] = FilteredEpsilonGreedyActionSelector
 REGISTRY["multinomial"] = MultinomialActionSelector
 REGISTRY["soft_policies"] = SoftPoliciesSelector
 REGISTRY["filtered_const_soft_policies"] = FilteredSoftPoliciesSelector
-REGISTRY["continuous"] = _next_row("continuous", "bids-as-actions path (scipy linear_sum_assignment in the env)")
+REGISTRY["continuous"] = ContinuousActionSelector
 REGISTRY["sap"] = SequentialAssignmentProblemSelector
 REGISTRY["epsilon_greedy_sap_test"] = EpsilonGreedySAPTestActionSelector
 REGISTRY["filtered_const_sap"] = FilteredSAPActionSelector

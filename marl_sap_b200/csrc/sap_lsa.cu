@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) sap_lsa_kernel(LsaParams p) {
     for (int c = 0; c < kCM; ++c) spc[c] = INF;
     int nSR = 0, sink = -1, i = cur;
     double minVal = 0.0;
-    while (true) {
+    while (nSR < n) {  // every step scans a new row
       if (lane == 0) {
         srl[nSR] = (int16_t)i;
         entry[nSR] = minVal;
@@ -171,13 +171,14 @@ __global__ void __launch_bounds__(kThreads) sap_lsa_kernel(LsaParams p) {
     __syncwarp();
     // augment along the predecessor chain
     int j = sink;
-    while (true) {
+    for (int guard = 0; guard <= n; ++guard) {  // a path visits every row at most once (bound: NaN input cannot hang it)
       const int owner = j & 31, slot = j >> 5;
       int pi = -1;
 #pragma unroll
       for (int c = 0; c < kCM; ++c)
         if (c == slot) pi = pth[c];
       pi = __shfl_sync(SAP_FULL_MASK, pi, owner);
+      if (pi < 0) break;  // unreachable with finite input
       if (lane == owner) {
 #pragma unroll
         for (int c = 0; c < kCM; ++c)
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) sap_lsa_kernel(LsaParams p) {
       if (lane == 0) col4row[pi] = (int16_t)j;
       __syncwarp();
       j = prev;
-      if (pi == cur) break;
+      if (pi == cur || j < 0) break;
     }
   }
   __syncwarp();

@@ -148,6 +148,26 @@ class _BatchedEnvBase:
         actions = actions.reshape(self.B, self.n).contiguous()
         return actions
 
+    def enable_bids_as_actions(self):
+        """``bids_as_actions`` of the reference envs (real_constellation_env.py:75-80, 110-112, 140-141;
+        mock_constellation_env.py:53-56, 88-90, 121-122): an action is a bid per task, the buffer's ``actions`` field holds
+        the bids (fp32 [m]), and ``step`` turns every env's bid matrix into an assignment with one batched
+        linear-sum-assignment before the usual step."""
+        self.bids_as_actions = True
+        self.scheme["actions"] = {"vshape": (self.m,), "group": "agents", "dtype": th.float32}
+        self.preprocess = {}
+
+    def _actions_for_step(self, actions, view, batch):
+        if not getattr(self, "bids_as_actions", False):
+            return self._check_actions(actions)
+        from ..action_selectors.sap_selectors import lsa_maximize
+
+        _lib.require_cuda(actions, "actions")
+        bids = actions.detach().float().reshape(self.B, self.n, self.m).contiguous()
+        batch.data.transition_data["actions"][:, self.t_host] = bids   # the kernel must not write its int actions there
+        view.actions = _lib.SapField()
+        return lsa_maximize(bids)
+
     def episode_returns(self):
         return self.ep_return
 
@@ -182,8 +202,8 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
         self.t_host = 0
 
     def step(self, actions, batch):
-        actions = self._check_actions(actions)
         view = batch.kernel_view()
+        actions = self._actions_for_step(actions, view, batch)
         _lib.check(self.lib.sap_real_step(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
                                           _lib.ptr(self.task_prios),
                                           _lib.ptr(self.T_trans), self.lambda_, actions.data_ptr(), _lib.ptr(self.k),
@@ -249,8 +269,8 @@ class BatchedMockConstellationEnv(_BatchedEnvBase):
         self.t_host = 0
 
     def step(self, actions, batch):
-        actions = self._check_actions(actions)
         view = batch.kernel_view()
+        actions = self._actions_for_step(actions, view, batch)
         _lib.check(self.lib.sap_mock_step(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.T_trans), self.lambda_,
                                           actions.data_ptr(), _lib.ptr(self.k), _lib.ptr(self.prev),
                                           _lib.ptr(self.ep_return), _lib.ptr(self.counts), view,

@@ -45,6 +45,8 @@ class _SingleEnvBase:
     def _device_state(self):
         if self._impl is None:
             self._impl = self._make_impl()
+            if self.bids_as_actions:
+                self._impl.enable_bids_as_actions()
             scheme = copy.deepcopy(self.scheme)
             for key in ("obs", "rewards", "beta"):  # read back at fp32, returned to the caller as float64
                 scheme[key]["dtype"] = th.float32
@@ -75,12 +77,15 @@ class _SingleEnvBase:
     def step(self, actions):
         impl, batch = self._device_state()
         t = self.k
-        a = th.as_tensor(np.asarray(actions, dtype=np.int64), device=impl.device).reshape(1, self.n)
+        if self.bids_as_actions:  # a bid per task and agent; the assignment is solved on the device (:140-141)
+            a = th.as_tensor(np.asarray(actions, dtype=np.float32), device=impl.device).reshape(1, self.n, self.m)
+        else:
+            a = th.as_tensor(np.asarray(actions, dtype=np.int64), device=impl.device).reshape(1, self.n)
         done = impl.step(a, batch)
         self.k += 1
         self.done = bool(done)
         rewards = batch["rewards"][0, t].double().cpu().numpy()
-        self.prev_assigns = np.asarray(actions, dtype=int)
+        self.prev_assigns = impl.prev[0].cpu().numpy().astype(int) if self.bids_as_actions else np.asarray(actions, dtype=int)
         self._refresh(batch)
         return [r for r in rewards], self.done, {}
 
@@ -129,9 +134,6 @@ class RealConstellationEnv(_SingleEnvBase):
     def __init__(self, num_planes, num_sats_per_plane, m, T, N, M, L, lambda_, sat_prox_mat=None, graphs=None,
                  bids_as_actions=False, seed=None, T_trans=None, task_prios=None, device=None):
         self.seed(seed)
-        if bids_as_actions:
-            raise NotImplementedError("bids_as_actions (continuous bids + linear_sum_assignment) is outside the "
-                                      "B200 hot path; see DESIGN.md 'out of scope'")
         if sat_prox_mat is None or graphs is None:
             raise NotImplementedError("orbit-propagated benefits (HighPerformanceConstellationSim, poliastro) are out of "
                                       "scope: pass sat_prox_mat=[n,m,T] and graphs (real_constellation_env.py:47-60)")
@@ -144,10 +146,13 @@ class RealConstellationEnv(_SingleEnvBase):
         self.lambda_ = lambda_
         self.T_trans = T_trans
         self.task_prios_arg = task_prios
-        self.bids_as_actions = False
+        self.bids_as_actions = bool(bids_as_actions)
         self.k, self.done, self.beta, self.prev_assigns, self._obs = 0, False, None, None, None
         self.obs_space_size = real_obs_size(self.M, self.N, self.L)
         self.scheme, self.preprocess = real_scheme(self.n, self.m, self.L, self.obs_space_size)
+        if self.bids_as_actions:  # :110-112
+            self.scheme["actions"] = {"vshape": (self.m,), "group": "agents", "dtype": th.float32}
+            self.preprocess = {}
         self._device = device
         self._impl = self._batch = None
 
@@ -192,8 +197,6 @@ class MockConstellationEnv(_SingleEnvBase):
     def __init__(self, n, m, T, L, lambda_, bids_as_actions=False, seed=None, sat_prox_mat=None, T_trans=None,
                  device=None):
         self.seed(seed)
-        if bids_as_actions:
-            raise NotImplementedError("bids_as_actions is outside the B200 hot path; see DESIGN.md 'out of scope'")
         self.n, self.m, self.T, self.L, self.lambda_ = n, m, T, L, lambda_
         if sat_prox_mat is None:
             self.constant_benefits = False
@@ -203,10 +206,13 @@ class MockConstellationEnv(_SingleEnvBase):
             self.sat_prox_mat = np.asarray(sat_prox_mat)
         self.T_trans = T_trans
         self.graphs = None
-        self.bids_as_actions = False
+        self.bids_as_actions = bool(bids_as_actions)
         self.k, self.beta, self.prev_assigns, self._obs = 0, None, None, None
         self.obs_space_size = self.L * self.m + self.m
         self.scheme, self.preprocess = mock_scheme(n, m, L)
+        if self.bids_as_actions:  # :88-90
+            self.scheme["actions"] = {"vshape": (self.m,), "group": "agents", "dtype": th.float32}
+            self.preprocess = {}
         self._device = device
         self._impl = self._batch = None
 

@@ -37,23 +37,28 @@ def build_batched_env(env_name, env_args, B, device):
         env_REGISTRY[env_name]()  # raises the explanatory NotImplementedError for off-path envs
     ea = dict(env_args)
     S = ea.get("sat_prox_mat", None)
-    if S is None and env_name == "mock_constellation_env" and not ea.get("bids_as_actions"):
+    if S is None and env_name == "mock_constellation_env":
         # the reference's MockConstellationEnv draws its own benefits (ctor and every reset): generated on the device
-        return batched_REGISTRY[env_name](B, ea["n"], ea["m"], ea["T"], ea["L"], ea["lambda_"], T_trans=ea.get("T_trans"),
-                                          device=device, generate_seed=int(ea.get("seed", 0) or 0) + 1)
+        env = batched_REGISTRY[env_name](B, ea["n"], ea["m"], ea["T"], ea["L"], ea["lambda_"], T_trans=ea.get("T_trans"),
+                                         device=device, generate_seed=int(ea.get("seed", 0) or 0) + 1)
+        if ea.get("bids_as_actions"):
+            env.enable_bids_as_actions()
+        return env
     if S is None:
         raise NotImplementedError("batched real-env runners need env_args['sat_prox_mat'] ([n,m,T] shared or [B,n,m,T]): "
                                   "the orbit simulator that would produce it is out of scope (DESIGN.md)")
     shape = tuple(S.shape)
     n, m, T = shape[-3:]
-    if ea.get("bids_as_actions"):
-        raise NotImplementedError("bids_as_actions is outside the B200 hot path")
     if env_name == "real_constellation_env":
-        return batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["M"], ea["N"], ea["lambda_"], sat_prox_mat=S,
-                                          task_prios=ea.get("task_prios"), T_trans=ea.get("T_trans"), device=device,
-                                          T_ctor=ea.get("T", T))
-    return batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["lambda_"], sat_prox_mat=S, T_trans=ea.get("T_trans"),
-                                      device=device)
+        env = batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["M"], ea["N"], ea["lambda_"], sat_prox_mat=S,
+                                         task_prios=ea.get("task_prios"), T_trans=ea.get("T_trans"), device=device,
+                                         T_ctor=ea.get("T", T))
+    else:
+        env = batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["lambda_"], sat_prox_mat=S, T_trans=ea.get("T_trans"),
+                                         device=device)
+    if ea.get("bids_as_actions"):
+        env.enable_bids_as_actions()
+    return env
 
 
 class _EnvInfo:

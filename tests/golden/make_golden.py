@@ -330,6 +330,36 @@ def golden_policy_selectors(R):
                         multinomial_test=a_test, soft=a_soft, pf=pf, beta=beta, u_rand=u_rand, uf=uf, filtered=a_filt, M=M)
 
 
+def golden_bids(R):
+    """bids_as_actions (real_constellation_env.py:140-141, mock_constellation_env.py:121-122): the reference envs stepped
+    with a bid matrix per step (scipy turns it into the assignment)."""
+    rng = np.random.default_rng(91)
+    n, m, T, L, M, N, lam = 6, 9, 4, 3, 4, 3, 0.5
+    S = O.gen_dense(rng, 1, n, m, T)[0]
+    bids = rng.random((T, n, m)).astype(np.float32)
+    out = dict(S=S, bids=bids, L=L, M=M, N=N, lambda_=lam)
+    env = R.real_env.RealConstellationEnv(1, n, m=m, T=T, N=N, M=M, L=L, lambda_=lam, sat_prox_mat=S.astype(np.float64),
+                                          graphs=1, bids_as_actions=True)
+    assert env.scheme["actions"]["vshape"] == (m,)
+    env.reset()
+    rew, obs = [], [np.array(env.get_obs())]
+    for t in range(T):
+        r, d, _ = env.step(bids[t].astype(np.float64))
+        rew.append(r)
+        obs.append(np.array(env.get_obs()))
+    out.update(real_rewards=np.array(rew), real_obs=np.stack(obs), real_prev=np.array(env.prev_assigns))
+    menv = R.mock_env.MockConstellationEnv(n, m, T, L, lam, bids_as_actions=True, sat_prox_mat=S.astype(np.float64))
+    np.random.seed(4)
+    menv.reset()
+    out["mock_prev0"] = np.array(menv.prev_assigns)
+    mrew = []
+    for t in range(T):
+        r, d, _ = menv.step(bids[t].astype(np.float64))
+        mrew.append(r)
+    out.update(mock_rewards=np.array(mrew))
+    np.savez_compressed(os.path.join(HERE, "bids.npz"), **out)
+
+
 def golden_haa(R):
     """HAASelector (non_rl_selectors.py:10-50) of the unmodified reference on real-env states: at every step of a short
     episode, the reference's pick from the state fields (beta, prev_assigns) of its own EpisodeBatch."""
@@ -456,6 +486,7 @@ def main():
     golden_selectors(R)
     golden_sap_selectors(R)
     golden_haa(R)
+    golden_bids(R)
     golden_policy_selectors(R)
     golden_buffer(R)
     golden_runner(R)

@@ -480,3 +480,43 @@ def test_benefit_generation_follows_the_reference_law():
     env2.reset(batch)
     assert th.equal(env2.planes, env.planes)
     assert th.equal(batch["obs"][:, 0, :, m:2 * m].cpu(), env2.planes[:, 0].cpu())  # obs = [onehot | S[:, :, k] | ...]
+
+
+def test_bids_as_actions_matches_reference_golden():
+    """bids_as_actions through the single-env facades (reference API) and the batched envs: the bid matrix of every env
+    becomes an assignment on the device, the buffer keeps the bids."""
+    from marl_sap_b200.envs import REGISTRY
+    from marl_sap_b200.envs.batched import BatchedMockConstellationEnv, BatchedRealConstellationEnv
+
+    g = _load("bids.npz")
+    S = g["S"].astype(np.float32)
+    n, m, T = S.shape
+    L, M, N, lam = int(g["L"]), int(g["M"]), int(g["N"]), float(g["lambda_"])
+    env = REGISTRY["real_constellation_env"](num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=lam,
+                                             sat_prox_mat=S, graphs=1, bids_as_actions=True)
+    assert env.scheme["actions"]["vshape"] == (m,) and env.preprocess == {}
+    env.reset()
+    np.testing.assert_allclose(np.array(env.get_obs()), g["real_obs"][0], rtol=0, atol=0)
+    for t, bids in enumerate(g["bids"]):
+        r, d, _ = env.step(bids)
+        np.testing.assert_allclose(r, g["real_rewards"][t], rtol=1e-6, atol=1e-7)  # facade reads rewards back at fp32
+        np.testing.assert_allclose(np.array(env.get_obs()), g["real_obs"][t + 1], rtol=0, atol=0)
+    np.testing.assert_array_equal(env.prev_assigns, g["real_prev"])
+    # batched: B copies, bids stored in the batch
+    B = 3
+    benv = BatchedRealConstellationEnv(B, n, m, T, L, M, N, lam, sat_prox_mat=S)
+    benv.enable_bids_as_actions()
+    batch = _batch_for(benv, B, th.float32)
+    assert batch["actions"].shape == (B, T + 1, n, m) and batch["actions"].dtype == th.float32
+    benv.reset(batch)
+    for t, bids in enumerate(g["bids"]):
+        benv.step(th.tensor(np.broadcast_to(bids, (B, n, m)).copy(), device="cuda"), batch)
+    assert th.equal(batch["rewards"][0, :T].cpu(), _cast(g["real_rewards"], th.float32))
+    assert th.equal(batch["actions"][1, :T].cpu(), th.tensor(g["bids"]))
+    menv = BatchedMockConstellationEnv(B, n, m, T, L, lam, sat_prox_mat=S)
+    menv.enable_bids_as_actions()
+    mb = _batch_for(menv, B)
+    menv.reset(mb, prev0=np.broadcast_to(g["mock_prev0"], (B, n)).copy())
+    for t, bids in enumerate(g["bids"]):
+        menv.step(th.tensor(np.broadcast_to(bids, (B, n, m)).copy(), device="cuda"), mb)
+    assert th.equal(mb["rewards"][2, :T].cpu(), _cast(g["mock_rewards"], th.float32))

@@ -356,3 +356,19 @@ def test_onehot_kernel_dtypes():
         oh = OneHot(11).transform(a.to(dt))
         assert oh.dtype == th.float32
         assert th.equal(oh, th.nn.functional.one_hot(a[..., 0], 11).float())
+
+
+def test_lsa_kernel_terminates_on_nan_and_inf_input():
+    """Non-finite Q-values must not hang the assignment kernel (every loop is bounded); finite envs are unaffected."""
+    from marl_sap_b200.action_selectors.sap_selectors import lsa_maximize
+
+    rng = np.random.default_rng(2)
+    q = rng.standard_normal((6, 12, 12)).astype(np.float32)
+    q[1, 3, :] = np.nan
+    q[2] = np.nan
+    q[3, :, 5] = -np.inf
+    q[4, 0, 0] = np.inf
+    got = lsa_maximize(_cu(q)).cpu().numpy()
+    want, _ = O.lsa_maximize(q[[0, 5]])
+    np.testing.assert_array_equal(got[[0, 5]], want)
+    assert got.shape == (6, 12)

@@ -151,3 +151,23 @@ def test_policy_selectors_oracle_matches_reference():
     np.put_along_axis(masked, top, -1.0, axis=2)
     choices = np.concatenate([top, masked.argmax(-1)[..., None]], axis=2)
     np.testing.assert_array_equal(np.take_along_axis(choices, picked[..., None], axis=2)[..., 0], g["filtered"])
+
+
+def test_bids_as_actions_oracle_matches_reference():
+    """bids_as_actions: scipy assignment of the bid matrix, then the ordinary step (real and mock env)."""
+    g = _load("bids.npz")
+    S = g["S"][None].astype(np.float64)
+    lam = float(g["lambda_"])
+    st = O.RealState(S, int(g["L"]), int(g["M"]), int(g["N"]), lam)
+    st.reset()
+    np.testing.assert_array_equal(st.obs[0], g["real_obs"][0])
+    for t, bids in enumerate(g["bids"]):
+        a, _ = O.lsa_maximize(bids[None])
+        r, _ = st.step(a)
+        np.testing.assert_array_equal(r[0], g["real_rewards"][t])
+        np.testing.assert_array_equal(st.obs[0], g["real_obs"][t + 1])
+    ms = O.MockState(S, int(g["L"]), lam)
+    ms.reset(g["mock_prev0"][None])
+    for t, bids in enumerate(g["bids"]):
+        r, _ = ms.step(O.lsa_maximize(bids[None])[0])
+        np.testing.assert_array_equal(r[0], g["mock_rewards"][t])
