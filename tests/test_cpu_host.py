@@ -191,3 +191,21 @@ def test_cpu_oracle_port_throughput_helper_runs():
     dt, steps = bench._cpu_worker((w, 2, 3, 0, weights))
     assert steps == 2 * w["n"] * 3 and dt > 0
     assert bench.algorithmic_bytes_per_env_step(bench.WORKLOADS["c3"], 2) == 100 * 100 * 3 * 4 + 100 * 490 * 6 + 1616
+
+
+def test_rollout_diagnostics_on_cpu_tensors():
+    """utils/rollout_stats (device array ops replacing q_learner.py:157-191's loops) vs the loops, on CPU tensors."""
+    import torch as th
+
+    from marl_sap_b200.utils.rollout_stats import calc_conflicting_actions, calc_raw_benefits
+    from oracle import cpu_oracle as O
+
+    rng = np.random.default_rng(8)
+    B, T, n, m = 3, 5, 7, 4
+    acts = rng.integers(0, m, size=(B, T, n))
+    beta = rng.random((B, T, n, m))
+    a = th.tensor(acts).unsqueeze(-1)
+    assert calc_conflicting_actions(a, m) == pytest.approx(O.calc_conflicting_actions(acts, m), rel=1e-12)
+    assert calc_raw_benefits(th.tensor(beta), a) == pytest.approx(O.calc_raw_benefits(beta, acts), rel=1e-12)
+    with pytest.raises(ValueError, match="unexpected shape"):
+        calc_raw_benefits(th.tensor(beta[0]), a)
