@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int TPL = 2;  // threads cooperating on one list
+// threads cooperating on one list: 2, or 4 when there are too few lists to occupy the CTA with 2 (n <= 64)
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr size_t kMaxSmem = 227 * 1024 - 1024;
@@ -80,7 +80,7 @@ __host__ __device__ inline FastLayout fast_layout(const SapEnvDims& d, int out_e
 // ---------------------------------------------------------------------------------------------------------
 // top-16 of a list under the packed order, TPL adjacent lanes per list.  key(e) returns the packed word of
 // element e (0 = padding).  On return every lane of the group holds the same descending top[16].
-template <typename KeyFn>
+template <int TPL, typename KeyFn>
 __device__ __forceinline__ void group_top16(int len, int s, KeyFn key, uint32_t (&top)[16]) {
   const int per = (len + TPL - 1) / TPL;  // elements per thread
 #pragma unroll
@@ -173,8 +173,9 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   return r;
 }
 
-template <typename OutT_, typename IdxT_, bool kPrios_, bool kCommon_>
+template <typename OutT_, typename IdxT_, bool kPrios_, bool kCommon_, int kTPL_ = 2>
 struct Cfg {
+  static constexpr int kTPL = kTPL_;
   using OutT = OutT_;
   using IdxT = IdxT_;
   static constexpr bool kPrios = kPrios_;
@@ -186,6 +187,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   using OutT = typename C::OutT;
   using IdxT = typename C::IdxT;
   constexpr bool kPrios = C::kPrios;
+  constexpr int TPL = C::kTPL;
   const SapEnvDims d = p.d;
   const int n = d.n, m = d.m, T = d.T;
   const int L = C::kCommon ? 3 : d.L, M = C::kCommon ? 10 : d.M, N = C::kCommon ? 10 : d.N;
@@ -545,7 +547,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     if (!__any_sync(SAP_FULL_MASK, live)) continue;  // whole warp beyond the last list
     const uint32_t* row = K32 + (live ? i : 0) * ms;
     uint32_t top[16];
-    group_top16(live ? m : 0, s, [&](int e) { return (row[e] << ib) | (imask - (uint32_t)e); }, top);
+    group_top16<TPL>(live ? m : 0, s, [&](int e) { return (row[e] << ib) | (imask - (uint32_t)e); }, top);
     if (live && s == 0) {
       if (!certified(top, K2, ib) && !p.debug_skip_redo) {
         qRows[atomicAdd(&sQ[0], 1)] = i;
@@ -629,7 +631,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
 #pragma unroll
     for (int q = 0; q < 16; ++q) dcol[q] = (live && q < M) ? (int)sD[i * M + q] : 0;
     uint32_t top[16];
-    group_top16(live ? n : 0, s,
+    group_top16<TPL>(live ? n : 0, s,
                 [&](int a) {
                   const uint32_t* row = K32 + a * ms;
                   uint32_t best = 0u;
@@ -925,6 +927,7 @@ int sap_real_fast_try(RealParams& p, void* stream, int* handled) {
   }
   *handled = 1;
   if (common) {
+    if (idx8 && d.n <= 64) return launch_fast<Cfg<__half, uint8_t, false, true, 4>>(p, stream, f.total);
     if (idx8) return launch_fast<Cfg<__half, uint8_t, false, true>>(p, stream, f.total);
     return launch_fast<Cfg<__half, uint16_t, false, true>>(p, stream, f.total);
   }

@@ -520,3 +520,32 @@ def test_bids_as_actions_matches_reference_golden():
     for t, bids in enumerate(g["bids"]):
         menv.step(th.tensor(np.broadcast_to(bids, (B, n, m)).copy(), device="cuda"), mb)
     assert th.equal(mb["rewards"][2, :T].cpu(), _cast(g["mock_rewards"], th.float32))
+
+
+@pytest.mark.parametrize("n,m,gen", [(50, 50, "dense"), (64, 100, "ties"), (33, 47, "ref")])
+def test_real_env_small_common_config_matches_oracle(n, m, gen):
+    """The bench's C2 shape family (n <= 64, fp16 scheme, M = N = 10, L = 3): the fast kernel's 4-lanes-per-list variant."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    rng = np.random.default_rng(n * 7 + m)
+    B, T, L, M, N = 4, 5, 3, 10, 10
+    if gen == "dense":
+        S = O.gen_dense(rng, B, n, m, T)
+    elif gen == "ties":
+        S = (np.round(O.gen_exact(rng, B, n, m, T, zero_frac=0.5) * 4) / 4).astype(np.float32)
+    else:
+        S = O.gen_ref_like(rng, B, n, m, T)
+    acts = rng.integers(0, m, size=(T, B, n))
+    st = O.RealState(S.astype(np.float64), L, M, N, 0.5)
+    want = O.rollout(st, lambda t, pre: acts[t], "real")
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S)
+    assert env.scratch is None
+    batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
+    batch.agent_in = th.zeros(B, n, env.obs_size, device="cuda")
+    env.reset(batch)
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+        assert th.equal(batch.agent_in, batch["obs"][:, t + 1].float())
+    assert th.equal(batch["obs"].cpu(), _cast(want["obs"], th.float16))
+    assert th.equal(batch["rewards"].cpu(), _cast(want["rewards"], th.float16))
+    assert th.equal(batch["prev_assigns"].cpu(), _cast(want["prev_assigns"], th.int16))
