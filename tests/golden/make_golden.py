@@ -495,8 +495,6 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
-if __name__ == "__main__" and "--runner-only" not in sys.argv:
-    main()
 
 
 def golden_runner(R):
@@ -571,5 +569,8 @@ def golden_runner(R):
                             t_env_after=runner.t_env, return_mean=log.stats["return_mean"][-1][1], **extra_out, **out)
 
 
-if __name__ == "__main__" and "--runner-only" in sys.argv:
-    golden_runner(ref_import.ref_modules())
+if __name__ == "__main__":
+    if "--runner-only" in sys.argv:
+        golden_runner(ref_import.ref_modules())
+    else:
+        main()
