@@ -280,7 +280,8 @@ def gpu_arm(opts, w):
 
     for _ in range(opts.warmup):
         step()
-    launches0 = runner.kernel_launches + buffer.kernel_launches
+    agent_launches = lambda: getattr(runner.mac.agent, "kernel_launches", 0)  # noqa: E731  (sap_bias_act epilogues)
+    launches0 = runner.kernel_launches + buffer.kernel_launches + agent_launches()
     sampler = ClockSampler(local_rank)
     barrier()
     th.cuda.synchronize()
@@ -309,7 +310,8 @@ def gpu_arm(opts, w):
         runner.args.use_cuda_graph = True
     ms = e0.elapsed_time(e1)
     kern_ms = sum(a.elapsed_time(b) for a, b in ev_pairs) / max(len(ev_pairs), 1)
-    launches = runner.kernel_launches + buffer.kernel_launches - launches0  # selector + env kernels (+ replay copies, if any)
+    # selector + env kernels + the agent's bias/ReLU epilogue (+ replay copies, if any)
+    launches = runner.kernel_launches + buffer.kernel_launches + agent_launches() - launches0
     t = th.tensor([ms, kern_ms], dtype=th.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

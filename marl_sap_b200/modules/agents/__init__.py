@@ -49,6 +49,7 @@ class _FcAgent(nn.Module):
             from ... import _lib
 
             y = th.mm(x, wt)
+            self.__dict__["kernel_launches"] = self.__dict__.get("kernel_launches", 0) + 1  # sap_bias_act launches so far
             _lib.check(_lib.load().sap_bias_act(y.data_ptr(), layer.bias.data_ptr(), y.shape[0], y.shape[1], int(relu),
                                                 _lib.stream_ptr(x.device)), "sap_bias_act")
             return y
