@@ -42,14 +42,27 @@ __device__ __forceinline__ void stg_stream4(float4* p, const float4& v) {
                : "memory");
 }
 
+// kEnvWarps warps per environment: 8 (one CTA per env) or, for tiny envs such as the reference's own 10 x 10
+// configuration, 1 (eight envs per CTA, warp-level synchronisation only): at 65 536 envs of 10 x 10 the launch is
+// otherwise bound by the rate at which CTAs can be issued, not by memory.
+template <int kEnvWarps>
 __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* cnt = reinterpret_cast<int32_t*>(smem_raw);          // [m]
-  int32_t* act = cnt + p.d.m;                                   // [n] clamped actions (or -1 on reset)
-  __shared__ double red[kWarps];
+  constexpr int kT = kEnvWarps * 32;         // threads per env
+  constexpr int kEnvsPerCta = kThreads / kT;
+  const int sub = threadIdx.x / kT;          // which env of this CTA
   const SapEnvDims d = p.d;
-  const int b = blockIdx.x, n = d.n, m = d.m, T = d.T, L = d.L;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x * kEnvsPerCta + sub, n = d.n, m = d.m, T = d.T, L = d.L;
+  if (b >= d.B) return;  // whole warps only (kT is a multiple of 32)
+  int32_t* cnt = reinterpret_cast<int32_t*>(smem_raw) + (size_t)sub * (m + n);  // [m]
+  int32_t* act = cnt + m;                                                       // [n] clamped actions (or -1 on reset)
+  __shared__ double red_all[kWarps];
+  double* red = red_all + sub * kEnvWarps;
+  const int tid = threadIdx.x % kT, lane = tid & 31, warp = tid >> 5;
+  auto env_sync = [&]() {
+    if (kEnvWarps == 1) __syncwarp();
+    else __syncthreads();
+  };
   const float* env_planes = p.planes + (d.shared_planes ? (size_t)0 : (size_t)b * T * n * m);
   const SapBatchView& vw = p.view;
   const int obs_size = (L + 1) * m;
@@ -58,18 +71,18 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
   if (!p.is_reset) {
     const int k_old = p.k[b];
     if (k_old >= T) return;
-    for (int j = tid; j < m; j += kThreads) cnt[j] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += kThreads) {
+    for (int j = tid; j < m; j += kT) cnt[j] = 0;
+    env_sync();
+    for (int i = tid; i < n; i += kT) {
       int a = (int)p.actions[(size_t)b * n + i];
       a = min(max(a, 0), m - 1);
       act[i] = a;
       atomicAdd(&cnt[a], 1);  // :128-130
     }
-    __syncthreads();
+    env_sync();
     double local_ret = 0.0;
     const float* cur = env_planes + (size_t)k_old * n * m;  // beta = S[:,:,k]  (:104,:157)
-    for (int i = tid; i < n; i += kThreads) {
+    for (int i = tid; i < n; i += kT) {
       const int a = act[i];
       const int pv = p.prev[(size_t)b * n + i];
       const double bv = (double)cur[(size_t)i * m + a];
@@ -87,25 +100,25 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
     if (lane == 0) red[warp] = local_ret;
     if (vw.actions_onehot.ptr) {
       const int64_t base = sap_field_off(vw.actions_onehot, b, k_old);
-      for (int e = tid; e < n * m; e += kThreads) {
+      for (int e = tid; e < n * m; e += kT) {
         const int i = e / m, j = e - i * m;
         sap_store_int(vw.actions_onehot.ptr, base + e, vw.actions_onehot.dtype, act[i] == j ? 1 : 0);
       }
     }
     if (p.counts_out)
-      for (int j = tid; j < m; j += kThreads) p.counts_out[(size_t)b * m + j] = cnt[j];
-    __syncthreads();
+      for (int j = tid; j < m; j += kT) p.counts_out[(size_t)b * m + j] = cnt[j];
+    env_sync();
     k_new = k_old + 1;
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < kWarps; ++w) t += red[w];
+      for (int w = 0; w < kEnvWarps; ++w) t += red[w];
       p.ep_return[b] += t;
       p.k[b] = k_new;  // :145
       if (vw.terminated.ptr)
         sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, k_new >= T);  // :154
     }
   } else {
-    for (int i = tid; i < n; i += kThreads) {
+    for (int i = tid; i < n; i += kT) {
       act[i] = -1;  // curr_assignment = 0 (:96)
       int pv = (int)p.prev0[(size_t)b * n + i];
       p.prev[(size_t)b * n + i] = min(max(pv, 0), m - 1);  // :105 (injected draw)
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
       p.k[b] = 0;
       p.ep_return[b] = 0.0;
     }
-    __syncthreads();
+    env_sync();
   }
 
   // ------------------------------------------------------------------ slot t = k_new
@@ -122,12 +135,12 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
   if (tid == 0 && vw.filled.ptr) sap_store_int(vw.filled.ptr, sap_field_off(vw.filled, b, t_slot), vw.filled.dtype, 1);
   if (vw.avail_actions.ptr) {
     const int64_t base = sap_field_off(vw.avail_actions, b, t_slot);
-    for (int e = tid; e < n * m; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
+    for (int e = tid; e < n * m; e += kT) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
   }
   if (vw.beta.ptr) {  // beta = S[:,:,k] or zeros when done (:156-159)
     const int64_t bb = sap_field_off(vw.beta, b, t_slot);
     const float* cur = env_planes + (size_t)k_new * n * m;
-    for (int e = tid; e < n * m; e += kThreads)
+    for (int e = tid; e < n * m; e += kT)
       sap_store_real(vw.beta.ptr, bb + e, vw.beta.dtype, k_new < T ? (double)cur[e] : 0.0);
   }
   const int64_t obs_base = sap_field_off(vw.obs, b, t_slot);
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
     // Warp per agent row, lane per 4 tasks: no index arithmetic beyond adds, up to 4 independent 128-bit loads in
     // flight per lane, every segment of a row leaves as one contiguous run.
     const int m4 = m >> 2, row4 = (L + 1) * m4;
-    for (int i = warp; i < n; i += kWarps) {
+    for (int i = warp; i < n; i += kEnvWarps) {
       float4* orow = reinterpret_cast<float4*>(out) + (size_t)i * row4;
       float* arow = ain ? ain + i * ain_row : nullptr;
       const int ai = act[i];
@@ -178,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) sap_mock_kernel(MockParams p) {
     }
   } else {
     const int total = n * obs_size;
-    for (int e = tid; e < total; e += kThreads) {
+    for (int e = tid; e < total; e += kT) {
       const int i = e / obs_size, r = e - i * obs_size;
       const int seg = r / m, j = r - seg * m;
       double v;
@@ -208,15 +221,18 @@ int launch(MockParams& p, void* stream) {
   const SapField& ai = p.view.agent_in;
   p.ain_vec4 = ai.ptr && sap_aligned16(ai.ptr) && (ai.env_stride % 4 == 0) && (ai.t_stride % 4 == 0);
   SAP_REQUIRE(!ai.ptr || ai.dtype == SAP_F32, SAP_E_DTYPE, "sap_mock: agent_in must be f32");
-  size_t bytes = sizeof(int32_t) * (size_t)(d.m + d.n);
+  // tiny envs: one warp per env, eight envs per CTA
+  const bool tiny = (int64_t)d.n * (d.L + 1) * d.m <= 2048 && d.B >= 64;
+  size_t bytes = sizeof(int32_t) * (size_t)(d.m + d.n) * (tiny ? kWarps : 1);
   if (bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(sap_mock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(sap_mock_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
       sap_set_error("sap_mock: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
   }
-  sap_mock_kernel<<<d.B, kThreads, bytes, (cudaStream_t)stream>>>(p);
+  if (tiny) sap_mock_kernel<1><<<(d.B + kWarps - 1) / kWarps, kThreads, bytes, (cudaStream_t)stream>>>(p);
+  else sap_mock_kernel<8><<<d.B, kThreads, bytes, (cudaStream_t)stream>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_mock_kernel");
   return SAP_OK;
 }

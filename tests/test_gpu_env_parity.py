@@ -166,7 +166,10 @@ def test_mock_env_matches_reference_golden(name):
 
 
 @pytest.mark.parametrize("cfg", [dict(B=4, n=10, m=10, T=7, L=3), dict(B=3, n=100, m=100, T=5, L=3),
-                                 dict(B=2, n=17, m=23, T=4, L=2), dict(B=2, n=50, m=52, T=3, L=5)])
+                                 dict(B=2, n=17, m=23, T=4, L=2), dict(B=2, n=50, m=52, T=3, L=5),
+                                 # tiny envs, many of them: the one-warp-per-env variant (8 envs per CTA)
+                                 dict(B=70, n=10, m=10, T=7, L=3), dict(B=67, n=17, m=23, T=4, L=2),
+                                 dict(B=130, n=10, m=12, T=5, L=3), dict(B=64, n=3, m=40, T=3, L=4)])
 def test_mock_env_matches_oracle(cfg):
     from marl_sap_b200.envs.batched import BatchedMockConstellationEnv
 
