@@ -383,7 +383,7 @@ __device__ __forceinline__ void reward_phase(const RealParams& p, int b, int k_o
 
 // ---------------------------------------------------------------------------------------------------- K2
 template <bool kKeyed, int kTPL>
-__global__ void __launch_bounds__(kThreads) sap_real_large_lists(RealParams p) {
+__global__ void __launch_bounds__(kThreads, 4) sap_real_large_lists(RealParams p) {
   constexpr int kRowsPerCta = kThreads / kTPL;
   __shared__ int32_t q_cnt;
   __shared__ int32_t q_rows[kMaxRowsPerCta];
@@ -574,7 +574,7 @@ __device__ __noinline__ void exact_select_scores(const double* sScore, int n, in
 
 // ---------------------------------------------------------------------------------------------------- K3
 template <bool kKeyed>
-__global__ void __launch_bounds__(kThreads, 3) sap_real_large_main(RealParams p) {
+__global__ void __launch_bounds__(kThreads, 5) sap_real_large_main(RealParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SapEnvDims d = p.d;
   const int b = env_of_block();
