@@ -176,6 +176,7 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
 template <typename OutT_, typename IdxT_, bool kPrios_, bool kCommon_, int kTPL_ = 2>
 struct Cfg {
   static constexpr int kTPL = kTPL_;
+  static constexpr int kMinBlocks = kTPL_ == 4 ? 5 : 3;  // small shapes need little shared memory: more CTAs per SM
   using OutT = OutT_;
   using IdxT = IdxT_;
   static constexpr bool kPrios = kPrios_;
@@ -884,7 +885,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
 // One CTA per environment; the hardware block scheduler balances the (slightly uneven) per-env durations better
 // than a static persistent partition did (measured: 0.95 ms vs 1.18 ms at 4096 x 100 x 100).
 template <typename C>
-__global__ void __launch_bounds__(kThreads, 3) sap_real_fast_kernel(RealParams p) {
+__global__ void __launch_bounds__(kThreads, C::kMinBlocks) sap_real_fast_kernel(RealParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   process_env<C>(p, blockIdx.x, smem);
 }
