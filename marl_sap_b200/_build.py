@@ -1,6 +1,14 @@
-"""Build the CUDA shared library in-tree with nvcc for sm_100a (no torch headers, plain C ABI)."""
+"""Build the CUDA shared library in-tree with nvcc for sm_100a (no torch headers, plain C ABI).
+
+Every .cu is compiled to its own object (in parallel) and the objects are linked into
+`marl_sap_b200/libmarl_sap_b200.so`.  An object is reused only when the SHA-256 of its source, of every header under
+`csrc/` and `include/`, and of the compiler flags matches the stamp written next to it, so a stale library can not
+survive a source change (mtimes are not trusted: a fresh checkout gives every file the same one).
+"""
 from __future__ import annotations
 
+import concurrent.futures as cf
+import hashlib
 import os
 import subprocess
 import sys
@@ -8,8 +16,12 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "build")
 LIB_PATH = os.path.join(PKG, "libmarl_sap_b200.so")
-SOURCES = ["sap_real.cu", "sap_real_fast.cu", "sap_real_large.cu", "sap_mock.cu", "sap_select.cu", "sap_lsa.cu", "sap_buffer.cu"]
+STAMP = os.path.join(OBJ, "libmarl_sap_b200.stamp")
+SOURCES = ["sap_real.cu", "sap_real_fast.cu", "sap_real_fast2.cu", "sap_real_large.cu", "sap_mock.cu", "sap_select.cu",
+           "sap_lsa.cu", "sap_buffer.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def nvcc_path() -> str:
@@ -19,27 +31,77 @@ def nvcc_path() -> str:
     return "nvcc"
 
 
+def _extra_flags() -> list[str]:
+    # SAP_ABLATE=1 compiles the timing-ablation / forced-path hooks into the kernels (profiling builds only)
+    return ["-DSAP_ABLATE=1"] if os.environ.get("SAP_ABLATE") == "1" else []
+
+
+def _headers() -> list[str]:
+    hs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    inc = os.path.join(ROOT, "include")
+    return hs + [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
+
+
+def _digest(paths: list[str], extra: str = "") -> str:
+    h = hashlib.sha256(extra.encode())
+    for p in paths:
+        with open(p, "rb") as fh:
+            h.update(p.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def _read(path: str) -> str:
+    try:
+        with open(path) as fh:
+            return fh.read().strip()
+    except OSError:
+        return ""
+
+
+def source_digest() -> str:
+    """Digest of everything the library is built from."""
+    return _digest([os.path.join(CSRC, s) for s in SOURCES] + _headers(), " ".join(FLAGS + _extra_flags()))
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "marl_sap_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB_PATH) or _read(STAMP) != source_digest()
+
+
+def _compile_one(src: str, verbose: bool) -> tuple[str, str]:
+    path = os.path.join(CSRC, src)
+    obj = os.path.join(OBJ, src[:-3] + ".o")
+    want = _digest([path] + _headers(), " ".join(FLAGS + _extra_flags()))
+    if os.path.exists(obj) and _read(obj + ".stamp") == want:
+        return obj, ""
+    cmd = [nvcc_path(), *FLAGS, *_extra_flags(), "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", path, "-o", obj]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    with open(obj + ".stamp", "w") as fh:
+        fh.write(want)
+    return obj, proc.stdout + proc.stderr
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "--shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
+    os.makedirs(OBJ, exist_ok=True)
+    if force:
+        for f in os.listdir(OBJ):
+            if f.endswith(".stamp"):
+                os.remove(os.path.join(OBJ, f))
+    with cf.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda s: _compile_one(s, verbose), SOURCES))
+    cmd = [nvcc_path(), "--shared", "-o", LIB_PATH] + [o for o, _ in results]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(source_digest())
     if verbose:
-        print(proc.stdout + proc.stderr)
+        print("".join(log for _, log in results))
     return LIB_PATH
 
 

@@ -22,13 +22,28 @@ class _KernelSelectorBase:
         self.schedule = DecayThenFlatSchedule(args.epsilon_start, args.epsilon_finish, args.epsilon_anneal_time,
                                               decay="linear")
         self.epsilon = self.schedule.eval(0)
-        self.seed = int(getattr(args, "seed", 0) or 0) & 0xFFFFFFFFFFFFFFFF
+        self.seed = self._base_seed = int(getattr(args, "seed", 0) or 0) & 0xFFFFFFFFFFFFFFFF
+        self.env_offset = 0
         self.envs = None            # assigned by the runners (reference: episode_runner.py:39)
         self.episode_ctr = None     # device uint64 scalar (as int64 tensor), set by the runner
         self.step_k = None          # device int32 [B] step counters of the batched env
         self._injected = None
         self._calls = 0
         self._local_ctr = None
+
+    def set_env_offset(self, env_offset):
+        """Global index of this process's first env (multi-GPU runs: rank r owns envs [offset, offset + B)).  The kernels
+        key Philox by (seed; local row, episode, step); folding the offset into the seed keeps the streams of different
+        ranks apart (identical seeds on every rank would make all ranks explore identically).  Offset 0 leaves the seed
+        as given."""
+        self.env_offset = int(env_offset)
+        if self.env_offset:
+            z = (self._base_seed + 0x9E3779B97F4A7C15 * (self.env_offset + 1)) & 0xFFFFFFFFFFFFFFFF  # splitmix64 finaliser
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+            self.seed = z ^ (z >> 31)
+        else:
+            self.seed = self._base_seed
 
     def bind_counters(self, episode_ctr, step_k):
         """Give the kernel device-side (episode, step) counters so each (env, agent, t) draw is unique and the

@@ -23,6 +23,10 @@ def _obs_width(scheme):
 
 
 class BasicMAC:
+    # select_actions is torch modules + device-side kernels only (no host decision per step): the runner may capture
+    # its T-step loop in a CUDA graph.  Subclasses that decide on the host (JumpstartMAC) set this to False.
+    graph_capturable = True
+
     def __init__(self, scheme, groups, args):
         self.args = args
         self.n = args.n

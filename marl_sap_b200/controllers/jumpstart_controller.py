@@ -10,6 +10,8 @@ from .basic_controller import BasicMAC
 
 
 class JumpstartMAC(BasicMAC):
+    graph_capturable = False  # the HAA-vs-network decision is a host draw per step: a captured graph would freeze it
+
     def __init__(self, scheme, groups, args):
         super().__init__(scheme, groups, args)
         self.jumpstart_action_selector = non_rl_action_REGISTRY[args.jumpstart_action_selector](args)

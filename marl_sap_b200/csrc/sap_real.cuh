@@ -96,6 +96,8 @@ __device__ __forceinline__ void warp_select_cached(int len, int count, bool idx_
 // Launches the shared-memory-resident fast kernel when the problem fits it.
 // Returns SAP_OK / error like every entry point; *handled = 0 means "not eligible, use the generic kernel".
 int sap_real_fast_try(RealParams& p, void* stream, int* handled);
+// Second-generation kernel for the shipped configuration (M = N = 10, L = 3, fp16) at 64 < n <= 128 (sap_real_fast2.cu).
+int sap_real_fast2_try(RealParams& p, void* stream, int* handled);
 
 // One environment spread over many CTAs, for shapes whose window sums do not fit shared memory (sap_real_large.cu).
 int sap_real_large_launch(RealParams& p, void* stream);

@@ -20,6 +20,7 @@
 //      the fp32 copy the agent network reads (agent_in).
 #include "sap_real.cuh"
 #include "sap_sortnet.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -912,6 +913,13 @@ int launch_fast(RealParams& p, void* stream, size_t bytes) {
 
 int sap_real_fast_try(RealParams& p, void* stream, int* handled) {
   *handled = 0;
+  {
+    const char* v1 = getenv("SAP_REAL_FAST_V1");  // A/B switch while the second-generation kernel is being measured
+    if (!(v1 && v1[0] == '1')) {
+      const int rc = sap_real_fast2_try(p, stream, handled);
+      if (rc != SAP_OK || *handled) return rc;
+    }
+  }
   const SapEnvDims& d = p.d;
   const int H = d.M / 2;
   const bool half_out = p.view.obs.dtype == SAP_F16;

@@ -2,8 +2,9 @@
 
 Replaces /root/reference/src/runners/parallel_runner.py:12-299 (ParallelRunner + env_worker processes +
 pickle over Pipes) and runners/episode_runner.py:8-137 (EpisodeRunner) for the SAP envs: all
-``batch_size_run`` environments live in one device-resident batched env and advance in lockstep, one fused
-kernel launch per timestep (select -> step -> obs(t+1) -> buffer writes).
+``batch_size_run`` environments live in one device-resident batched env and advance in lockstep: per timestep the
+torch agent forward, one selection kernel and one env kernel (step -> obs(t+1) -> buffer writes; four launches on the
+multi-CTA path of the large shapes).
 
 Same surface as the reference runners: ``Runner(args, logger)``, ``setup(scheme, groups, preprocess, mac)``,
 ``get_env()``, ``run(test_mode) -> EpisodeBatch``, ``close_env()``, ``save_replay()``, attributes
@@ -15,8 +16,16 @@ at t = T-1), no extra selection at t = T, independent per-(env, agent, step) ran
 ParallelRunner's bugs (terminated list-truthiness, extra select, shared numpy RNG) are NOT
 reproduced.
 
-Multi-GPU: one process per GPU, each rank owns ``batch_size_run`` envs (block partition); the only collective
+Multi-GPU: one process per GPU.  By default every rank owns ``batch_size_run`` envs (weak scaling); with
+``args.batch_size_run_is_global = True`` the ``batch_size_run`` envs are block-partitioned over the ranks
+(``utils.dist.env_partition``; strong scaling, the north star's "4096 envs sharded across 2/4/8 GPUs") and a
+``sat_prox_mat`` of shape [batch_size_run, n, m, T] is sliced to the rank's block.  Either way a rank's random streams
+are keyed by the GLOBAL index of its first env, so no two ranks draw the same exploration noise.  The only collective
 is one all-reduce of [sum return, sum return^2, n_episodes, sum ep_length] per ``run()``.
+
+``compat_parallel_runner_quirks = True`` reproduces what the reference ParallelRunner writes into ``terminated``
+(parallel_runner.py:181-187: the flag is assigned from the truthiness of the per-agent reward LIST, not from the env's
+done flag, so every stored ``terminated`` is True) - off by default, EpisodeRunner semantics otherwise.
 """
 from __future__ import annotations
 
@@ -29,6 +38,7 @@ import torch as th
 from ..components.episode_buffer import EpisodeBatch
 from ..envs import BATCHED as batched_REGISTRY
 from ..envs import REGISTRY as env_REGISTRY
+from ..utils.dist import env_partition
 
 
 def build_batched_env(env_name, env_args, B, device):
@@ -86,10 +96,29 @@ class CudaVecRunner:
     def __init__(self, args, logger):
         self.args = args
         self.logger = logger
-        self.batch_size = self.args.batch_size_run
         dev = getattr(args, "device", "cuda")
         self.device = th.device(dev if str(dev).startswith("cuda") else "cuda")
-        self.env = build_batched_env(self.args.env, self.args.env_args, self.batch_size, self.device)
+        rank, world = 0, 1
+        if th.distributed.is_available() and th.distributed.is_initialized():
+            rank, world = th.distributed.get_rank(), th.distributed.get_world_size()
+        self.rank, self.world = rank, world
+        self.global_batch = bool(getattr(args, "batch_size_run_is_global", False)) and world > 1
+        if self.global_batch:  # strong scaling: this rank's block of the batch_size_run envs
+            self.env_offset, self.batch_size = env_partition(self.args.batch_size_run, rank, world)
+            if self.batch_size == 0:
+                raise ValueError(f"batch_size_run={self.args.batch_size_run} leaves rank {rank} of {world} without an env")
+        else:
+            self.env_offset, self.batch_size = rank * self.args.batch_size_run, self.args.batch_size_run
+        env_args = dict(self.args.env_args)
+        S = env_args.get("sat_prox_mat", None)
+        if self.global_batch and S is not None and len(S.shape) == 4:
+            if S.shape[0] != self.args.batch_size_run:
+                raise ValueError(f"sat_prox_mat has {S.shape[0]} envs, batch_size_run is {self.args.batch_size_run}")
+            env_args["sat_prox_mat"] = S[self.env_offset:self.env_offset + self.batch_size]
+        if env_args.get("sat_prox_mat", None) is None and "seed" in env_args:
+            env_args["seed"] = int(env_args["seed"] or 0) + 7919 * self.env_offset  # device-generated benefits differ per rank
+        self.env = build_batched_env(self.args.env, env_args, self.batch_size, self.device)
+        self.compat_quirks = bool(getattr(args, "compat_parallel_runner_quirks", False))
         self.T = self.env.T
         self.t = 0
         self.t_env = 0
@@ -102,6 +131,7 @@ class CudaVecRunner:
         self.last_episode_returns = None
         self._batch = None
         self.kernel_launches = 0
+        self.max_graphs = int(getattr(args, "max_cuda_graphs", 16))
 
     # ------------------------------------------------------------------ reference runner API
     def setup(self, scheme, groups, preprocess, mac):
@@ -112,6 +142,8 @@ class CudaVecRunner:
         self.mac.action_selector.envs = [self.get_env()]
         if hasattr(self.mac.action_selector, "bind_counters"):
             self.mac.action_selector.bind_counters(self.episode_ctr, self.env.k)
+        if hasattr(self.mac.action_selector, "set_env_offset"):
+            self.mac.action_selector.set_env_offset(self.env_offset)
         js = getattr(self.mac, "jumpstart_action_selector", None)
         if js is not None:  # JumpstartMAC: the non-learning policy reads the env state directly
             js.envs = [self.get_env()]
@@ -127,7 +159,27 @@ class CudaVecRunner:
             self.agent_in = th.zeros(self.batch_size, self.env.n, row, dtype=th.float32, device=self.device)
 
     def get_env(self):
-        return _EnvInfo(self.env)
+        """The reference returns worker 0's env, pickled through the Pipe (parallel_runner.py:246-247, 281-282): a COPY
+        with the full env API (``beta_hat``, ``step``, ... - HAAL deep-copies and steps it).  Here: a single-env facade
+        built from the same ``env_args``; when they cannot build one (planes adopted with ``set_planes``) the shape /
+        scheme record that ``run.py`` reads (run.py:113-131)."""
+        if getattr(self, "_env_facade", None) is None:
+            self._env_facade = _EnvInfo(self.env)
+            ea = dict(self.args.env_args)
+            S = ea.get("sat_prox_mat", None)
+            try:
+                if S is not None and len(S.shape) == 4:
+                    S0 = S[self.env_offset if self.global_batch else 0]
+                    ea["sat_prox_mat"] = S0.cpu().numpy() if isinstance(S0, th.Tensor) else np.asarray(S0)
+                elif isinstance(S, th.Tensor):
+                    ea["sat_prox_mat"] = S.cpu().numpy()
+                if S is not None and tuple(ea["sat_prox_mat"].shape) == (self.env.n, self.env.m, self.env.T):
+                    facade = env_REGISTRY[self.args.env](**ea)
+                    facade.obs_size = self.env.obs_size
+                    self._env_facade = facade
+            except (NotImplementedError, TypeError, KeyError):
+                pass
+        return self._env_facade
 
     def get_env_info(self):
         return self.get_env().get_env_info()
@@ -144,12 +196,14 @@ class CudaVecRunner:
         the rows would wrap."""
         self._replay = buffer
 
-    def reset(self, **reset_kwargs):
+    def reset(self, test_mode=False, **reset_kwargs):
         ring = getattr(self, "_replay", None)
-        view = ring.view_next(self.batch_size) if ring is not None else None
+        # test episodes are never inserted: they must not be rolled out over sampleable rows of the ring
+        view = ring.view_next(self.batch_size) if ring is not None and not test_mode else None
         if view is not None:
             self.batch = view
-        elif self.reuse_batch and self._batch is not None:
+        elif (self.reuse_batch or getattr(self.args, "use_cuda_graph", False)) and self._batch is not None:
+            # (CUDA graphs bake buffer addresses in: a graph runner always rolls out into the same private batch)
             self.batch = self._batch
             for v in self.batch.data.transition_data.values():
                 v.zero_()
@@ -185,16 +239,31 @@ class CudaVecRunner:
         sel = self.mac.action_selector
         if not hasattr(sel, "use_device_epsilon") or not getattr(sel, "graph_capturable", False):
             return False  # e.g. the assignment selectors draw with torch / numpy RNG on the host side
+        if not getattr(self.mac, "graph_capturable", False) or getattr(self.mac, "jumpstart_action_selector", None) is not None:
+            # JumpstartMAC decides HAA-vs-network per step with host RNG against a host epsilon schedule: a capture
+            # would freeze that pattern.  Only MACs that declare themselves capturable (BasicMAC) are replayed.
+            return False
         sel.use_device_epsilon(True)
         sel.set_device_epsilon(self.t_env, test_mode, self.device)
-        td = self.batch.data.transition_data
-        key = (td["obs"].data_ptr(), td["filled"].data_ptr(), self.env.planes.data_ptr(),
-               0 if self.env.plane_stats is None else self.env.plane_stats.data_ptr(), bool(test_mode))
+        # the captured launches bake in the address of EVERY buffer they touch: all of them go into the key, and the
+        # cache entry keeps the tensors alive so that a later allocation can not reuse an address under a stale graph
+        view_ptrs = tuple(v.data_ptr() for _, v in sorted(self.batch.data.transition_data.items()))
+        extras = (self.env.planes, self.env.plane_stats, self.batch.agent_in, getattr(self.env, "top", None),
+                  getattr(self.env, "scratch", None))
+        key = view_ptrs + tuple(0 if x is None else x.data_ptr() for x in extras) + (bool(test_mode),)
         graphs = self.__dict__.setdefault("_graphs", {})
-        g = graphs.get(key)
-        if g is None:
-            if not self.__dict__.get("_graph_warm", False) or len(graphs) >= 8:
-                self._graph_warm = True
+        entry = graphs.get(key)
+        if entry is None:
+            if not self.__dict__.get("_graph_warm", False):
+                self._graph_warm = True   # first episode runs eagerly (lazy initialisation inside torch / cuBLAS)
+                return False
+            if len(graphs) >= self.max_graphs:
+                if not self.__dict__.get("_graph_full_warned", False):
+                    self._graph_full_warned = True
+                    self.logger.console_logger.warning(
+                        "CudaVecRunner: %d CUDA graphs cached and the rollout buffers changed again; running eagerly. "
+                        "Keep the buffers stable (reuse_episode_batch / attach_replay with batch_size_run dividing the "
+                        "ring) or raise runner.max_graphs.", len(graphs))
                 return False
             g = th.cuda.CUDAGraph()
             th.cuda.synchronize(self.device)
@@ -203,7 +272,9 @@ class CudaVecRunner:
                 self._rollout_loop(test_mode)
             self.env.t_host = t_host  # capture only recorded the launches
             self.t = 0
-            graphs[key] = g
+            entry = (g, self.batch, extras)
+            graphs[key] = entry
+        g = entry[0]
         g.replay()
         self.env.t_host += self.T
         self.t = self.T
@@ -212,9 +283,12 @@ class CudaVecRunner:
 
     @th.no_grad()
     def run(self, test_mode=False, **reset_kwargs):
-        self.reset(**reset_kwargs)
+        self.reset(test_mode=test_mode, **reset_kwargs)
         if not (getattr(self.args, "use_cuda_graph", False) and self._rollout_graph(test_mode)):
             self._rollout_loop(test_mode)
+        if self.compat_quirks and "terminated" in self.batch.data.transition_data:
+            # parallel_runner.py:181-187: `terminated` <- truthiness of the non-empty reward list of every env
+            self.batch.data.transition_data["terminated"][:, :self.T] = True
         self.kernel_launches += (1 + self.env.launches_per_step) * self.T  # selector + env kernel(s) per timestep
         self.last_episode_returns = self.env.ep_return.clone()
         self._finish_run(test_mode)

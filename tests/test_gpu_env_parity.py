@@ -552,3 +552,68 @@ def test_real_env_small_common_config_matches_oracle(n, m, gen):
     assert th.equal(batch["obs"].cpu(), _cast(want["obs"], th.float16))
     assert th.equal(batch["rewards"].cpu(), _cast(want["rewards"], th.float16))
     assert th.equal(batch["prev_assigns"].cpu(), _cast(want["prev_assigns"], th.int16))
+
+
+def _gen_benefits(gen, rng, B, n, m, T):
+    if gen == "dense":
+        return O.gen_dense(rng, B, n, m, T)
+    if gen == "ties":
+        return (np.round(O.gen_exact(rng, B, n, m, T, zero_frac=0.5) * 4) / 4).astype(np.float32)
+    if gen == "dup":      # duplicates above the minimum + near-ties one ulp apart: exercises the exact redo path
+        S = (np.round(O.gen_dense(rng, B, n, m, T) * 16) / 16 + 1).astype(np.float32)
+        S[:, ::3] = np.nextafter(S[:, ::3], np.float32(4))
+        return S
+    if gen == "neg":      # negative benefits: every key is inexact, every list goes through the exact selection
+        return (O.gen_ref_like(rng, B, n, m, T) - np.float32(0.25) * (rng.random((B, n, m, T)) < 0.1)).astype(np.float32)
+    if gen == "const":    # every window sum identical
+        return np.full((B, n, m, T), 0.5, dtype=np.float32)
+    return O.gen_ref_like(rng, B, n, m, T)
+
+
+@pytest.mark.parametrize("n,m,gen,opts", [
+    (100, 100, "dense", ""), (100, 100, "ties", ""), (100, 100, "ref", "eager"), (100, 100, "dup", ""),
+    (100, 100, "neg", ""), (100, 100, "const", ""), (68, 72, "dense", "noain"), (128, 128, "ties", ""),
+    (96, 128, "ref", "ttrans"), (72, 100, "dup", "shared"), (124, 128, "dense", "eager"),
+])
+def test_real_env_fast2_matches_oracle(n, m, gen, opts):
+    """The bench shape family (64 < n <= 128, fp16 scheme, M = N = 10, L = 3): the second-generation one-CTA-per-env
+    kernel (csrc/sap_real_fast2.cu: transposed key tile, slot gather) against the oracle, including tie-heavy,
+    near-tie, negative and constant benefits, eager beta / avail / onehot fields, a custom T_trans and shared planes."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    rng = np.random.default_rng(n * 13 + m + len(gen))
+    B, T, L, M, N = 3, 5, 3, 10, 10
+    shared = opts == "shared"
+    S = _gen_benefits(gen, rng, 1 if shared else B, n, m, T)
+    Tt = rng.integers(0, 2, size=(m, m)).astype(np.float64) if opts == "ttrans" else None
+    acts = rng.integers(0, m, size=(T, B, n))
+    acts[:, :, : n // 3] = acts[:, :, :1]
+    S_or = np.broadcast_to(S, (B, n, m, T)) if shared else S
+    st = O.RealState(S_or.astype(np.float64), L, M, N, 0.5, T_trans=Tt)
+    want = O.rollout(st, lambda t, pre: acts[t], "real")
+    env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S[0] if shared else S, T_trans=Tt)
+    assert env.scratch is None
+    batch = _batch_for(env, B, lazy=() if opts == "eager" else ("beta", "avail_actions", "actions_onehot"))
+    if opts != "noain":
+        batch.agent_in = th.zeros(B, n, env.obs_size, device="cuda")
+    env.reset(batch)
+    tops, counts = [env.top.cpu().numpy().copy()], []
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+        tops.append(env.top.cpu().numpy().copy())
+        counts.append(env.counts.cpu().numpy().copy())
+        if opts != "noain":
+            assert th.equal(batch.agent_in, batch["obs"][:, t + 1].float())
+    assert th.equal(batch["obs"].cpu(), _cast(want["obs"], th.float16))
+    assert th.equal(batch["rewards"].cpu(), _cast(want["rewards"], th.float16))
+    assert th.equal(batch["prev_assigns"].cpu(), _cast(want["prev_assigns"], th.int16))
+    assert th.equal(batch["terminated"][..., 0].cpu(), th.tensor(want["terminated"]))
+    assert th.equal(batch["filled"][..., 0].cpu(), th.tensor(want["filled"]))
+    np.testing.assert_array_equal(np.stack(counts, 1), want["counts"][:, :T])
+    for t in range(T):
+        np.testing.assert_array_equal(tops[t], O.top_m_tasks(want["beta"][:, t], M))
+    np.testing.assert_allclose(env.ep_return.cpu().numpy(), want["rewards"].sum((1, 2)), rtol=1e-12)
+    if opts == "eager":
+        assert th.equal(batch["beta"].cpu(), _cast(want["beta"], th.float16))
+        assert bool(batch["avail_actions"].all())
+        assert th.equal(batch["actions_onehot"][:, :T].cpu(), _cast(O.one_hot(np.moveaxis(acts, 0, 1), m, np.int16), th.int16))
