@@ -296,8 +296,12 @@ constexpr size_t kMaxSmem = 227 * 1024;
 int launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
   const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: "1" generic kernel, "2" / "3" multi-CTA large path (keyed / exact)
+#ifdef SAP_ABLATE
   const char* skip = getenv("SAP_DEBUG_SKIP_REDO");
-  p.debug_skip_redo = skip ? atoi(skip) : 0;  // bit 0: accept uncertified lists; other bits: timing ablations
+  p.debug_skip_redo = skip ? atoi(skip) : 0;  // timing ablations (profiling builds only: -DSAP_ABLATE)
+#else
+  p.debug_skip_redo = 0;
+#endif
   if (force && (force[0] == '2' || force[0] == '3')) return sap_real_large_launch(p, stream);
   if (!(force && force[0] == '1')) {
     int handled = 0;

@@ -21,6 +21,7 @@ struct RealParams {
   int debug_skip_redo;  // timing experiments only (SAP_DEBUG_SKIP_REDO=1): accept uncertified lists
   int tot_in_smem;
   int ms;  // row stride of tot (odd -> conflict-free column walks)
+  int lookahead;  // sap_real_fast2: blocks of L2 look-ahead for the benefit window (0 = off)
 };
 
 

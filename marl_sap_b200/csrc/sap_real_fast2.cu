@@ -21,6 +21,7 @@
 // key resolution.
 #include "sap_real.cuh"
 #include "sap_sortnet.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 namespace {
@@ -35,6 +36,13 @@ constexpr int kKP = 128;                        // key tile pitch in words
 constexpr int kRows = kWarps;                   // observation rows staged per pass
 constexpr size_t kMaxSmem = 227 * 1024 - 1024;
 
+#ifdef SAP_ABLATE
+#define SAP_STOP_AFTER(k)                      \
+  if (p.debug_skip_redo == (k)) return;  // timing ablation: the kernel ends after phase k (profiling builds only)
+#else
+#define SAP_STOP_AFTER(k)
+#endif
+
 #define SAP_CE(a, b)            \
   {                             \
     uint32_t hi__ = max(a, b);  \
@@ -44,7 +52,7 @@ constexpr size_t kMaxSmem = 227 * 1024 - 1024;
 
 struct F2Layout {
   uint32_t D, nbr, other;                    // live through the whole kernel
-  uint32_t KT, E, dmask, cnt, red, queue;    // overlay 1: list building
+  uint32_t KT, E, dmask, cnt, red, queue, stage1;  // overlay 1: list building
   uint32_t t01, t2, stage;                   // overlay 2: gather
   uint32_t total;
   int p01, p2;                               // pitches of the two tile planes (words / halves)
@@ -61,12 +69,14 @@ __host__ __device__ inline F2Layout f2_layout(int n, int m) {
   const uint32_t base = (off + 127u) & ~127u;
   off = base;
   f.KT = off;    off += 4u * ((m + 7) & ~7) * kKP;  // rows m .. 8 ceil(m / 8) hold zero keys (list padding)
-  f.E = off;     off += 16u * n;
-  f.dmask = off; off += 16u * n;
   f.cnt = off;   off = up16(off + 4u * m);
   f.red = off;   off += 8u * 80;
   f.queue = off; off = up16(off + 4u * (2 * n + 4));
-  const uint32_t end1 = off;
+  f.stage1 = off;                                    // key pass only: per-warp staging tiles, dead before E is written
+  f.E = off;     off += 16u * n;
+  f.dmask = off; off += 16u * n;
+  const uint32_t end1s = f.stage1 + (uint32_t)kWarps * 16u * m;
+  const uint32_t end1 = off > end1s ? off : end1s;
   f.p01 = m;
   f.p2 = m;
   off = base;
@@ -161,6 +171,14 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
 #pragma unroll
   for (int l = 0; l < kL; ++l)
     if (l < Leff) pst[l] = __ldg(reinterpret_cast<const float2*>(p.plane_stats) + (env_plane0 + k_new + l));
+  // L2 look-ahead: the CTA that will run `lookahead` blocks after this one reads the same window of its own env (all
+  // envs of a batch step in lockstep; a wrong guess only wastes the prefetch).  By then the window sits in L2, so the
+  // key pass of that CTA pays L2 latency instead of DRAM latency.
+  if (tid == 0 && p.lookahead > 0 && !d.shared_planes && b + p.lookahead < d.B && Leff > 0) {
+    const float* nxt = p.planes + ((size_t)(b + p.lookahead) * T + k_new) * nm;
+    for (int l = 0; l < Leff; ++l)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxt + (size_t)l * nm), "r"((uint32_t)(nm * 4)) : "memory");
+  }
 
   if (tid == 0) {
     sQ[0] = 0;
@@ -252,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     return;
   }
 
+  SAP_STOP_AFTER(1)
   // ------------------------------------------------------------------ 3. key scale from the per-plane {min, max}
   double k_lo, k_scale;
   bool k_nonneg;
@@ -304,85 +323,86 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   auto key_at = [&](int a, int j) -> uint32_t { return KT[j * kKP + ((((a >> 2) ^ (j & 3)) << 2) | (a & 3))]; };
 
   // ------------------------------------------------------------------ 4. key pass: window -> KT
-  // item = (agent group I of 4, task group j4 of 4); 4 lanes per item, lane `sub` loads agent 4I + sub, tasks
-  // 4 j4 .. 4 j4 + 3 (a warp reads 128 contiguous bytes of 4 agent rows per plane); the 4 x 4 block of keys is
-  // transposed across the 4 lanes, so lane `sub` ends up with task 4 j4 + sub, agents 4I .. 4I + 3: one 128-bit store.
+  // A warp takes a group of 4 consecutive agents (4 I .. 4 I + 3): their rows are ONE contiguous 4 m float run per
+  // plane, read with fully coalesced 128-bit loads, all 3 x 4 loads of a lane in flight at once (the pass is bound
+  // by how many bytes an SM keeps in flight, not by arithmetic: row-wise 128-byte pieces of 4 separate rows were
+  // 0.045 ms slower at 4096 x 100 x 100).  The keys go through a per-warp staging tile [4][m] so that they can be
+  // re-read per TASK (4 agents of one task = one 128-bit store into the transposed tile).
   {
-    const int m4 = m >> 2, n4 = n >> 2, items = n4 * m4, m8 = (m + 7) & ~7;
+    const int m4 = m >> 2, n4 = n >> 2, m8 = (m + 7) & ~7;
     // zero keys for the agents n .. 127 of every task and for the padding tasks m .. m8 - 1: the lists below read them
     // as (key 0 | ~index) words, which rank behind every real entry, so no list needs a bounds test
-    for (int row = warp; row < m8; row += kWarps)
-      for (int g = (row < m ? n4 : 0) + lane; g < kKP / 4; g += 32)
+    for (int row = tid >> 3; row < m8; row += kThreads / 8) {
+      const int g0 = row < m ? n4 : 0;
+      for (int g = g0 + (tid & 7); g < kKP / 4; g += 8)
         *reinterpret_cast<uint4*>(KT + row * kKP + ((g ^ (row & 3)) << 2)) = make_uint4(0u, 0u, 0u, 0u);
-    const uint32_t inv_m4 = (uint32_t)((0x100000000ull + (uint32_t)m4 - 1u) / (uint32_t)m4);  // item / m4 = umulhi(item, inv)
-    const int sub = lane & 3, q8 = lane >> 2;
-    const bool hi = (sub & 2) != 0, lo = (sub & 1) != 0;
-    const float* wsub = win + sub * m;
-    auto transpose_store = [&](bool valid, int I, int j4, const uint32_t (&kk)[4]) {
-      const uint32_t s0 = hi ? kk[0] : kk[2], s1 = hi ? kk[1] : kk[3];
-      const uint32_t r0 = __shfl_xor_sync(SAP_FULL_MASK, s0, 2), r1 = __shfl_xor_sync(SAP_FULL_MASK, s1, 2);
-      const uint32_t x0 = hi ? r0 : kk[0], x1 = hi ? r1 : kk[1], x2 = hi ? kk[2] : r0, x3 = hi ? kk[3] : r1;
-      const uint32_t y0 = lo ? x0 : x1, y1 = lo ? x2 : x3;
-      const uint32_t u0 = __shfl_xor_sync(SAP_FULL_MASK, y0, 1), u1 = __shfl_xor_sync(SAP_FULL_MASK, y1, 1);
-      uint4 o;
-      o.x = lo ? u0 : x0;
-      o.y = lo ? x1 : u0;
-      o.z = lo ? u1 : x2;
-      o.w = lo ? x3 : u1;
-      if (valid) *reinterpret_cast<uint4*>(KT + (4 * j4 + sub) * kKP + ((I ^ sub) << 2)) = o;
-    };
-    auto run = [&](auto tag) {
-      constexpr bool kFast = decltype(tag)::value;  // full window of non-negative benefits: no predicates in the loop
-      auto loads = [&](bool valid, int item, int& I, int& j4, float4 (&v)[kL]) {
-        I = (int)__umulhi((uint32_t)item, inv_m4);
-        j4 = item - I * m4;
-        const float* src = wsub + (4 * I) * m + 4 * j4;
+    }
+    uint32_t* Sw = reinterpret_cast<uint32_t*>(smem + f.stage1) + warp * 4 * m;  // this warp's staging tile
+    const uint32_t inv_m4 = (uint32_t)((0x100000000ull + (uint32_t)m4 - 1u) / (uint32_t)m4);  // x / m4 = umulhi(x, inv)
+    // one unit = agents 4 I .. 4 I + 3, task groups [ja, ja + len)
+    auto unit = [&](auto tag, int I, int ja, int len, bool whole_rows) {
+      constexpr bool kFast = decltype(tag)::value;  // full window of non-negative benefits: no predicates on the loads
+      const int cnt4 = 4 * len;                    // float4 positions of the unit
+      float4 v[4][kL];
+      int so[4];                                   // staging offset (words) of position t, -1 = none
 #pragma unroll
-        for (int l = 0; l < kL; ++l) {
-          if (kFast) {
-            v[l] = ldg_hint4(src + l * nm, pol_keep);
-          } else {
-            v[l] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid && l < Leff) v[l] = ldg_hint4(src + l * nm, pol_keep);
+      for (int t = 0; t < 4; ++t) {
+        const int fpos = lane + 32 * t;
+        so[t] = -1;
+        if (fpos < cnt4) {  // divergent only at the tail of a unit
+          const int r = whole_rows ? (int)__umulhi((uint32_t)fpos, inv_m4) : fpos / len;
+          const int j4 = ja + fpos - r * len;
+          so[t] = r * m + 4 * j4;
+          const float* src = win + (4 * I + r) * m + 4 * j4;
+#pragma unroll
+          for (int l = 0; l < kL; ++l) {
+            if (kFast) {
+              v[t][l] = ldg_hint4(src + l * nm, pol_keep);
+            } else {
+              v[t][l] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (l < Leff) v[t][l] = ldg_hint4(src + l * nm, pol_keep);
+            }
           }
         }
-      };
-      auto keys = [&](const float4 (&v)[kL], uint32_t (&kk)[4]) {
-        double tot[4] = {(double)v[0].x, (double)v[0].y, (double)v[0].z, (double)v[0].w};  // 0.0 + x == x
+      }
 #pragma unroll
-        for (int l = 1; l < kL; ++l) {
-          tot[0] += (double)v[l].x;
-          tot[1] += (double)v[l].y;
-          tot[2] += (double)v[l].z;
-          tot[3] += (double)v[l].w;
-        }
+      for (int t = 0; t < 4; ++t) {
+        if (so[t] >= 0) {
+          double tot[4] = {(double)v[t][0].x, (double)v[t][0].y, (double)v[t][0].z, (double)v[t][0].w};  // 0.0 + x == x
 #pragma unroll
-        for (int c = 0; c < 4; ++c) kk[c] = kFast ? make_key_fast(tot[c]) : make_key_generic(tot[c]);
-      };
-      const int G = items >> 3, R = items & 7;  // full groups of 8 items, items of the last partial group
-      for (int g = warp; g < G; g += 2 * kWarps) {
-        const bool has_b = g + kWarps < G;  // warp-uniform
-        float4 va[kL], vb[kL];
-        int IA, jA, IB = 0, jB = 0;
-        loads(true, 8 * g + q8, IA, jA, va);
-        if (has_b) loads(true, 8 * (g + kWarps) + q8, IB, jB, vb);
-        uint32_t ka[4], kb[4];
-        keys(va, ka);
-        transpose_store(true, IA, jA, ka);
-        if (has_b) {
-          keys(vb, kb);
-          transpose_store(true, IB, jB, kb);
+          for (int l = 1; l < kL; ++l) {
+            tot[0] += (double)v[t][l].x;
+            tot[1] += (double)v[t][l].y;
+            tot[2] += (double)v[t][l].z;
+            tot[3] += (double)v[t][l].w;
+          }
+          uint4 kk;
+          kk.x = kFast ? make_key_fast(tot[0]) : make_key_generic(tot[0]);
+          kk.y = kFast ? make_key_fast(tot[1]) : make_key_generic(tot[1]);
+          kk.z = kFast ? make_key_fast(tot[2]) : make_key_generic(tot[2]);
+          kk.w = kFast ? make_key_fast(tot[3]) : make_key_generic(tot[3]);
+          *reinterpret_cast<uint4*>(Sw + so[t]) = kk;
         }
       }
-      if (R && warp == (G & (kWarps - 1))) {
-        const bool valid = q8 < R;
-        float4 va[kL];
-        int IA, jA;
-        loads(valid, valid ? 8 * G + q8 : items - 1, IA, jA, va);  // idle lanes repeat the last item (in bounds), no store
-        uint32_t ka[4];
-        keys(va, ka);
-        transpose_store(valid, IA, jA, ka);
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int x = lane + 32 * u;  // task 4 ja + x
+        if (x < cnt4) {
+          const int jt = 4 * ja + x;
+          const uint4 o = make_uint4(Sw[jt], Sw[m + jt], Sw[2 * m + jt], Sw[3 * m + jt]);
+          *reinterpret_cast<uint4*>(KT + jt * kKP + ((I ^ (jt & 3)) << 2)) = o;
+        }
       }
+      __syncwarp();
+    };
+    auto run = [&](auto tag) {
+      const int full = n4 / kWarps;  // rounds in which every warp has a whole agent group
+      for (int r = 0; r < full; ++r) unit(tag, r * kWarps + warp, 0, m4, true);
+      // the remaining groups are split by task range over the warps, so that no warp works a whole extra round
+      const int len = (m4 + kWarps - 1) / kWarps, ja = warp * len, mine = min(len, m4 - ja);
+      for (int I = full * kWarps; I < n4; ++I)
+        if (mine > 0) unit(tag, I, ja, mine, false);
     };
     if (Leff == kL && k_nonneg) run(std::true_type{});
     else run(std::false_type{});
@@ -397,6 +417,10 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   }
   __syncthreads();
 
+  SAP_STOP_AFTER(2)
+#ifdef SAP_ABLATE
+  if (p.debug_skip_redo >= 20 && p.debug_skip_redo < 30) return;
+#endif
   // exact float64 window sum (the reference's beta.sum(-1), :190) from global memory, for uncertified lists only
   auto tot64 = [&](int a, int j) {
     double s = 0.0;
@@ -546,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     *reinterpret_cast<uint4*>(sMask + i * 4) = make_uint4(w0, w1, w2, w3);
   }
 
+  SAP_STOP_AFTER(3)
   // ------------------------------------------------------------------ 6. rivals (:203-206)
   // Four lanes per list, 64 lists per pass.  Lane s of list i owns the rival columns s + 4 c (agents 4 s + 16 c .. + 3):
   // for every top task of i (a row of KT) it loads those columns with 128-bit loads and keeps the running maximum.
@@ -668,6 +693,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   }
   __syncthreads();
 
+  SAP_STOP_AFTER(4)
   // ------------------------------------------------------------------ 7. rivals' other top tasks (:212-217)
   // The 5 best tasks of rival r outside D[i] under (value desc, idx desc) are the first 5 entries of E[r] not in
   // D[i]; the reference lists them ascending, so they are stored reversed.
@@ -696,6 +722,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   }
   __syncthreads();
 
+  SAP_STOP_AFTER(5)
   // ------------------------------------------------------------------ 8a. benefits of the window -> shared memory
   // Second read of the window (L2-resident: this CTA streamed it a few microseconds ago), rounded to fp16:
   // planes 0 and 1 of a pair side by side in one word, plane 2 in a separate plane.
@@ -732,6 +759,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   }
   __syncthreads();
 
+  SAP_STOP_AFTER(6)
   // ------------------------------------------------------------------ 8b. gather rows into shared memory, store
   // Row layout (:225): [own top tasks 10 x 3 | rival p on my top tasks 10 x (10 x 3) | rival p's other tasks
   // 10 x (5 x 3) | flags 10] = 32 slots of 15 halves + 10 flags.  Lane -> slot:
@@ -793,13 +821,22 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     const uint32_t bytes = (uint32_t)rows * kRowBytes;
     // the obs rows leave shared memory with ONE TMA bulk store issued by thread 0; meanwhile all threads widen the
     // same rows to fp32 for the agent network (128-bit stores)
+#ifdef SAP_ABLATE
+    if (p.debug_skip_redo == 7) {  // gather only: no stores
+      __syncthreads();
+      continue;
+    }
+    const bool ain_on_ = ain_on && p.debug_skip_redo != 8;  // 8: fp16 obs store only, no fp32 agent-input copy
+#else
+    const bool ain_on_ = ain_on;
+#endif
     if (tid == 0) {
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
                    "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes), "l"(pol_drop)
                    : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (ain_on) {
+    if (ain_on_) {
       float* adst = ain + (size_t)r0 * kObs;
       const int chunks = (int)(bytes >> 4);
 #pragma unroll 4
@@ -854,6 +891,10 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
     configured = true;
   }
   *handled = 1;
+  {
+    const char* la = getenv("SAP_F2_LOOKAHEAD");  // blocks of L2 look-ahead (measured: no gain at 4096 x 100 x 100, off by default)
+    p.lookahead = la ? atoi(la) : 0;
+  }
   sap_real_fast2_kernel<<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_fast2_kernel");
   return SAP_OK;

@@ -134,6 +134,8 @@ def run_point(th, lib_mod, B, n, opts, peak):
            "hbm_gbps": B_run * bytes_step / env_ms / 1e6, "hbm_frac": B_run * bytes_step / env_ms / 1e6 / peak}
     del planes, obs_t, ain, scratch
     th.cuda.empty_cache()
+    if opts.env_only:
+        return rec
     # selector: masked eps-greedy over q[B, n, m] (all actions available), Philox draws in-kernel
     Bs = max(1, min(B_run, int(opts.mem_gb * 1e9 // (n * m * 5 + n * 8))))
     q = th.randn(Bs, n, m, device=dev, generator=g)
@@ -202,6 +204,7 @@ def main():
     ap.add_argument("--ns", type=str, default=None, help="comma list of n = m values (default: the C5 grid)")
     ap.add_argument("--Bs", type=str, default=None, help="comma list of env counts (default: the C5 grid)")
     ap.add_argument("--rounds", type=int, default=3)
+    ap.add_argument("--env-only", action="store_true", help="time the env kernel only (kernel tuning runs)")
     ap.add_argument("--mem-gb", type=float, default=80.0)
     opts = ap.parse_args()
     import torch as th
@@ -234,6 +237,10 @@ def main():
           + (" 1-core numpy env-steps/s |" if opts.cpu else ""))
     print("|---|---|---|---|---|---|---|---|---|---|---|" + ("---|" if opts.cpu else ""))
     for r in recs:
+        if opts.env_only:
+            print(f"| {r['env']} | {r['n']} | {r['B']} ({r['B_run']}) | {r['env_kernel_ms']:.4f} | {r['env_steps_per_s']:.3g} | "
+                  f"{r['agent_steps_per_s']:.3g} | {r['hbm_gbps']:.0f} | {r['hbm_frac']:.2f} |")
+            continue
         row = (f"| {r['env']} | {r['n']} | {r['B']} ({r['B_run']}) | {r['env_kernel_ms']:.4f} | {r['env_steps_per_s']:.3g} | "
                f"{r['agent_steps_per_s']:.3g} | {r['hbm_gbps']:.0f} | {r['hbm_frac']:.2f} | {r['select_kernel_ms']:.4f} | "
                f"{r['select_hbm_frac']:.2f} | {r['lsa_us_per_env']:.2f} |")
