@@ -142,6 +142,20 @@ int sap_real_step(const SapEnvDims* dims, const float* planes, const float* plan
 /* number of scratch doubles sap_real_reset / sap_real_step need for these dims (0: none) */
 int64_t sap_real_scratch_doubles(const SapEnvDims* dims);
 
+/* Kernel selection of sap_real_reset / sap_real_step.  AUTO picks by shape: the one-CTA-per-env kernels when the env
+ * state fits one SM's shared memory (second generation for the shipped configuration M = N = 10, L = 3, fp16 scheme at
+ * 64 < n <= 128; first generation otherwise), the generic kernel for unusual M / N / L, the multi-CTA path for large
+ * shapes.  All paths produce identical bytes; the override exists so that tests and profiles can run EVERY path on one
+ * shape.  Process-wide; returns the previous value (-1 for an unknown value). */
+enum {
+  SAP_REAL_PATH_AUTO = 0,
+  SAP_REAL_PATH_GENERIC = 1,
+  SAP_REAL_PATH_LARGE_KEYED = 2,
+  SAP_REAL_PATH_LARGE_EXACT = 3,
+  SAP_REAL_PATH_FAST_GEN1 = 4
+};
+int32_t sap_real_select_kernel(int32_t which);
+
 /* ---- MockConstellationEnv ---------------------------------------------------------------
  * sap_mock_reset = MockConstellationEnv.reset (mock_constellation_env.py:94-114); prev0[B,n]
  *                  replaces the np.random.choice draw at :105 (injected).
@@ -215,6 +229,17 @@ int sap_lsa_maximize(const float* q, const float* z, const float* std_per_env, i
  *   The layer itself stays a torch matmul (modules/agents/rnn_agent.py:22-31: F.relu(self.fc1(inputs))); for the
  *   first layer `mm` + this kernel is one pass cheaper than cuBLAS's beta*C epilogue and bit-identical to it. */
 int sap_bias_act(float* x, const float* bias, int64_t rows, int32_t cols, int32_t relu, void* stream);
+/* sap_split_bias_act = epilogue of the OPT-IN split-precision first layer (args.agent_fc1 = "fp16_split"): the fp32
+ *   weight of fc1 is split into `terms` fp16 pieces, W = W_0 + scale W_1 (+ scale^2 W_2), the fp16 observation rows
+ *   (exact: the buffer holds fp16, basic_controller.py:82 only widens them) are multiplied by [W_0 | W_1 | W_2] in ONE
+ *   fp16 tensor-core GEMM with fp32 accumulation, and this kernel folds the pieces:
+ *   out[r, c] = act(sum_k scale^k y_cat[r, k * cols + c] + bias[c]).  Products are exact in fp32; the result differs
+ *   from the fp32 sgemm of the default path only by accumulation order (tests hold it to 2e-6 relative). */
+int sap_split_bias_act(const float* y_cat, int32_t terms, float scale, const float* bias, float* out, int64_t rows,
+                       int32_t cols, int32_t relu, void* stream);
+/* 1 when sap_real_step / sap_real_reset accept an fp16 `agent_in` staging field for these dims (the one-CTA-per-env
+ * kernel of the shipped configuration does: it bulk-stores the fp16 rows a second time instead of widening them). */
+int sap_real_agent_in_f16_ok(const SapEnvDims* dims);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,9 @@ SIGNATURES = {
     "sap_onehot": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _P]),
     "sap_real_beta_window": (C.c_int, [_DIMS, _P, _P, _P, _I32, _P]),
     "sap_bias_act": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
+    "sap_split_bias_act": (C.c_int, [_P, _I32, _F32, _P, _P, _I64, _I32, _I32, _P]),
+    "sap_real_agent_in_f16_ok": (C.c_int, [_DIMS]),
+    "sap_real_select_kernel": (C.c_int32, [_I32]),
     "sap_lsa_maximize": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "sap_sample_categorical": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
 }
@@ -127,3 +130,24 @@ def field_of(t, B_T_leading: bool = True) -> SapField:
         inner *= s
     f.ptr, f.env_stride, f.t_stride, f.dtype = t.data_ptr(), t.stride(0), t.stride(1), sap_dtype(t.dtype)
     return f
+
+
+REAL_PATH_AUTO, REAL_PATH_GENERIC, REAL_PATH_LARGE_KEYED, REAL_PATH_LARGE_EXACT, REAL_PATH_FAST_GEN1 = range(5)
+
+
+class select_real_kernel:
+    """Context manager around ``sap_real_select_kernel``: run the real-env step on one named kernel path (tests and
+    profiles run every path on the same shape; production code leaves the choice to the library)."""
+
+    def __init__(self, which):
+        self.which = int(which)
+
+    def __enter__(self):
+        self.prev = load().sap_real_select_kernel(self.which)
+        if self.prev < 0:
+            raise ValueError(f"unknown real-env kernel path {self.which}")
+        return self
+
+    def __exit__(self, *exc):
+        load().sap_real_select_kernel(self.prev)
+        return False

@@ -317,6 +317,59 @@ extern "C" int sap_benefit_generate(float* planes_Tnm, int32_t B, int32_t n, int
   return SAP_OK;
 }
 
+// out[r, c] = act(sum_k scale^k * y[r, k * cols + c] + bias[c]): the epilogue of a split-precision layer whose weight
+// was split into `terms` fp16 pieces (W = W_0 + scale W_1 + scale^2 W_2) multiplied side by side by one tensor-core GEMM
+__global__ void __launch_bounds__(kThreads) sap_split_bias_act_kernel(const float* __restrict__ y, int terms, float scale,
+                                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                                      int64_t rows, int cols, int relu) {
+  const int cols4 = cols >> 2;
+  const int64_t total4 = rows * cols4;
+  const float s2 = scale * scale;
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total4; e += (int64_t)gridDim.x * kThreads) {
+    const int64_t r = e / cols4;
+    const int c4 = (int)(e - r * cols4);
+    const float4* row = reinterpret_cast<const float4*>(y + r * (int64_t)terms * cols);
+    float4 v = __ldcs(row + c4);  // streamed: every element is read once
+    const float4 v1 = __ldcs(row + cols4 + c4);
+    v.x = __fmaf_rn(scale, v1.x, v.x);
+    v.y = __fmaf_rn(scale, v1.y, v.y);
+    v.z = __fmaf_rn(scale, v1.z, v.z);
+    v.w = __fmaf_rn(scale, v1.w, v.w);
+    if (terms == 3) {
+      const float4 v2 = __ldcs(row + 2 * cols4 + c4);
+      v.x = __fmaf_rn(s2, v2.x, v.x);
+      v.y = __fmaf_rn(s2, v2.y, v.y);
+      v.z = __fmaf_rn(s2, v2.z, v.z);
+      v.w = __fmaf_rn(s2, v2.w, v.w);
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    v.x = __fadd_rn(v.x, b.x);
+    v.y = __fadd_rn(v.y, b.y);
+    v.z = __fadd_rn(v.z, b.z);
+    v.w = __fadd_rn(v.w, b.w);
+    if (relu) {
+      v.x = v.x < 0.f ? 0.f : v.x;
+      v.y = v.y < 0.f ? 0.f : v.y;
+      v.z = v.z < 0.f ? 0.f : v.z;
+      v.w = v.w < 0.f ? 0.f : v.w;
+    }
+    reinterpret_cast<float4*>(out)[e] = v;
+  }
+}
+
+extern "C" int sap_split_bias_act(const float* y_cat, int32_t terms, float scale, const float* bias, float* out, int64_t rows,
+                                  int32_t cols, int32_t relu, void* stream) {
+  SAP_REQUIRE(y_cat && bias && out, SAP_E_NULL, "sap_split_bias_act: y/bias/out is null");
+  SAP_REQUIRE(rows >= 0 && cols > 0 && (terms == 2 || terms == 3), SAP_E_DIMS, "sap_split_bias_act: bad dims / terms");
+  SAP_REQUIRE(cols % 4 == 0 && sap_aligned16(y_cat) && sap_aligned16(bias) && sap_aligned16(out), SAP_E_CONSTRAINT,
+              "sap_split_bias_act: cols must be a multiple of 4 and the pointers 16-byte aligned");
+  if (rows == 0) return SAP_OK;
+  sap_split_bias_act_kernel<<<grid_for(rows * (cols >> 2)), kThreads, 0, (cudaStream_t)stream>>>(y_cat, terms, scale, bias, out,
+                                                                                               rows, cols, relu);
+  SAP_CUDA_LAUNCH_CHECK("sap_split_bias_act_kernel");
+  return SAP_OK;
+}
+
 extern "C" int sap_bias_act(float* x, const float* bias, int64_t rows, int32_t cols, int32_t relu, void* stream) {
   SAP_REQUIRE(x && bias, SAP_E_NULL, "sap_bias_act: x/bias is null");
   SAP_REQUIRE(rows >= 0 && cols > 0, SAP_E_DIMS, "sap_bias_act: bad dims");

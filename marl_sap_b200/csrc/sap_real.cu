@@ -10,6 +10,8 @@
 // stable total orders of sap_common.cuh, so results equal the reference's on fp32-representable inputs.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "sap_real.cuh"
 
 namespace {
@@ -293,21 +295,30 @@ int validate(const SapEnvDims* d, const SapBatchView* view) {
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
+// kernel selection override (sap_real_select_kernel): 0 = automatic
+std::atomic<int> g_real_path{0};
+
 int launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
-  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: "1" generic kernel, "2" / "3" multi-CTA large path (keyed / exact)
+  const int path = g_real_path.load(std::memory_order_relaxed);
 #ifdef SAP_ABLATE
   const char* skip = getenv("SAP_DEBUG_SKIP_REDO");
   p.debug_skip_redo = skip ? atoi(skip) : 0;  // timing ablations (profiling builds only: -DSAP_ABLATE)
 #else
   p.debug_skip_redo = 0;
 #endif
-  if (force && (force[0] == '2' || force[0] == '3')) return sap_real_large_launch(p, stream);
-  if (!(force && force[0] == '1')) {
+  if (path != SAP_REAL_PATH_AUTO && path != SAP_REAL_PATH_FAST_GEN1)  // every other kernel widens into an fp32 agent_in
+    SAP_REQUIRE(!p.view.agent_in.ptr || p.view.agent_in.dtype == SAP_F32, SAP_E_DTYPE, "sap_real: agent_in must be f32");
+  if (path == SAP_REAL_PATH_LARGE_KEYED || path == SAP_REAL_PATH_LARGE_EXACT) {
+    p.large_exact = path == SAP_REAL_PATH_LARGE_EXACT;
+    return sap_real_large_launch(p, stream);
+  }
+  if (path != SAP_REAL_PATH_GENERIC) {
     int handled = 0;
-    const int rc = sap_real_fast_try(p, stream, &handled);
+    const int rc = sap_real_fast_try(p, stream, &handled, path == SAP_REAL_PATH_FAST_GEN1);
     if (rc != SAP_OK || handled) return rc;
   }
+  SAP_REQUIRE(!p.view.agent_in.ptr || p.view.agent_in.dtype == SAP_F32, SAP_E_DTYPE, "sap_real: agent_in must be f32");
   p.ms = (d.m & 1) ? d.m : d.m + 1;
   size_t with_tot = smem_layout(d, p.ms, true, nullptr, nullptr);
   p.tot_in_smem = with_tot <= kMaxSmem;
@@ -329,10 +340,15 @@ int launch(RealParams& p, void* stream) {
 
 }  // namespace
 
+extern "C" int32_t sap_real_select_kernel(int32_t which) {
+  if (which < SAP_REAL_PATH_AUTO || which > SAP_REAL_PATH_FAST_GEN1) return -1;
+  return g_real_path.exchange(which);
+}
+
 extern "C" int64_t sap_real_scratch_doubles(const SapEnvDims* d) {
   if (!d) return 0;
-  const char* force = getenv("SAP_REAL_FORCE_GENERIC");
-  if (force && (force[0] == '2' || force[0] == '3')) return sap_real_large_scratch_doubles(*d);
+  const int path = g_real_path.load(std::memory_order_relaxed);
+  if (path == SAP_REAL_PATH_LARGE_KEYED || path == SAP_REAL_PATH_LARGE_EXACT) return sap_real_large_scratch_doubles(*d);
   int ms = (d->m & 1) ? d->m : d->m + 1;
   if (smem_layout(*d, ms, true, nullptr, nullptr) <= kMaxSmem) return 0;
   return sap_real_large_scratch_doubles(*d);

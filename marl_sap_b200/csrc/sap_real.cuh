@@ -22,6 +22,7 @@ struct RealParams {
   int tot_in_smem;
   int ms;  // row stride of tot (odd -> conflict-free column walks)
   int lookahead;  // sap_real_fast2: blocks of L2 look-ahead for the benefit window (0 = off)
+  int large_exact;  // multi-CTA path: exact float64 selection even where the keyed lists would apply (selector override)
 };
 
 
@@ -96,7 +97,7 @@ __device__ __forceinline__ void warp_select_cached(int len, int count, bool idx_
 
 // Launches the shared-memory-resident fast kernel when the problem fits it.
 // Returns SAP_OK / error like every entry point; *handled = 0 means "not eligible, use the generic kernel".
-int sap_real_fast_try(RealParams& p, void* stream, int* handled);
+int sap_real_fast_try(RealParams& p, void* stream, int* handled, bool gen1_only = false);
 // Second-generation kernel for the shipped configuration (M = N = 10, L = 3, fp16) at 64 < n <= 128 (sap_real_fast2.cu).
 int sap_real_fast2_try(RealParams& p, void* stream, int* handled);
 

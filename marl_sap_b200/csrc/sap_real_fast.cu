@@ -911,14 +911,11 @@ int launch_fast(RealParams& p, void* stream, size_t bytes) {
 
 }  // namespace
 
-int sap_real_fast_try(RealParams& p, void* stream, int* handled) {
+int sap_real_fast_try(RealParams& p, void* stream, int* handled, bool gen1_only) {
   *handled = 0;
-  {
-    const char* v1 = getenv("SAP_REAL_FAST_V1");  // A/B switch while the second-generation kernel is being measured
-    if (!(v1 && v1[0] == '1')) {
-      const int rc = sap_real_fast2_try(p, stream, handled);
-      if (rc != SAP_OK || *handled) return rc;
-    }
+  if (!gen1_only) {  // the second-generation kernel takes the shipped configuration at 64 < n <= 128
+    const int rc = sap_real_fast2_try(p, stream, handled);
+    if (rc != SAP_OK || *handled) return rc;
   }
   const SapEnvDims& d = p.d;
   const int H = d.M / 2;

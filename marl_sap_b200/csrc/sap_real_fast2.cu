@@ -254,7 +254,11 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     for (int e = tid; e < nm; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
   }
   __half* obs_out = reinterpret_cast<__half*>(vw.obs.ptr) + sap_field_off(vw.obs, b, t_slot);
-  float* ain = vw.agent_in.ptr ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
+  // agent-input staging rows of this env: fp32 (widened here) or fp16 (the same bytes, bulk-stored a second time)
+  const bool ain_half = vw.agent_in.ptr && vw.agent_in.dtype == SAP_F16;
+  float* ain = vw.agent_in.ptr && !ain_half ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride
+                                            : nullptr;
+  __half* ain16 = ain_half ? reinterpret_cast<__half*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
   if (done) {  // :226-228
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     uint4* o4 = reinterpret_cast<uint4*>(obs_out);
@@ -262,6 +266,10 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     if (ain) {
       uint4* a4 = reinterpret_cast<uint4*>(ain);
       for (int e = tid; e < (n * kObs * 4) >> 4; e += kThreads) a4[e] = z;
+    }
+    if (ain16) {
+      uint4* a4 = reinterpret_cast<uint4*>(ain16);
+      for (int e = tid; e < (n * kRowBytes) >> 4; e += kThreads) a4[e] = z;
     }
     if (vw.beta.ptr) {
       const int64_t bb = sap_field_off(vw.beta, b, t_slot);
@@ -834,6 +842,10 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
                    "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes), "l"(pol_drop)
                    : "memory");
+      if (ain16)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ain16 + (size_t)r0 * kObs),
+                     "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes)
+                     : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (ain_on_) {
@@ -860,25 +872,37 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
 
 }  // namespace
 
+static bool fast2_dims_ok(const SapEnvDims& d) {
+  return d.M == kM && d.N == kN && d.L == kL && d.n > 64 && d.n <= 128 && d.m <= 128 && !(d.n & 3) && !(d.m & 3) && d.m >= d.n &&
+         f2_layout(d.n, d.m).total <= kMaxSmem;
+}
+
+extern "C" int sap_real_agent_in_f16_ok(const SapEnvDims* dims) { return dims && fast2_dims_ok(*dims) ? 1 : 0; }
+
 int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
   *handled = 0;
   const SapEnvDims& d = p.d;
   const SapBatchView& vw = p.view;
-  if (d.M != kM || d.N != kN || d.L != kL || p.prios || vw.obs.dtype != SAP_F16) return SAP_OK;
-  if (d.n <= 64 || d.n > 128 || d.m > 128 || (d.n & 3) || (d.m & 3) || d.m < d.n) return SAP_OK;
+  if (!fast2_dims_ok(d) || p.prios || vw.obs.dtype != SAP_F16) return SAP_OK;
   if (!p.plane_stats || (reinterpret_cast<uintptr_t>(p.plane_stats) & 7)) return SAP_OK;
   if (!sap_aligned16(p.planes)) return SAP_OK;
   // every observation block of 8 rows must start 16-byte aligned (TMA bulk store, 128-bit agent-input stores)
   if (!sap_aligned16(vw.obs.ptr) || ((vw.obs.env_stride * 2) & 15) || ((vw.obs.t_stride * 2) & 15)) return SAP_OK;
   if (vw.agent_in.ptr) {
-    if (vw.agent_in.dtype != SAP_F32) {
-      sap_set_error("sap_real: agent_in must be f32");
+    if (vw.agent_in.dtype != SAP_F32 && vw.agent_in.dtype != SAP_F16) {
+      sap_set_error("sap_real: agent_in must be f32 (or f16 on the one-CTA-per-env kernel of the shipped configuration)");
       return SAP_E_DTYPE;
     }
-    if (vw.agent_in.t_stride != kObs || !sap_aligned16(vw.agent_in.ptr) || ((vw.agent_in.env_stride * 4) & 15)) return SAP_OK;
+    const int esz = vw.agent_in.dtype == SAP_F32 ? 4 : 2;
+    if (vw.agent_in.t_stride != kObs || !sap_aligned16(vw.agent_in.ptr) || ((vw.agent_in.env_stride * esz) & 15)) {
+      if (esz == 2) {
+        sap_set_error("sap_real: an f16 agent_in must be [B, n, obs] contiguous and 16-byte aligned");
+        return SAP_E_CONSTRAINT;
+      }
+      return SAP_OK;
+    }
   }
   const F2Layout f = f2_layout(d.n, d.m);
-  if (f.total > kMaxSmem) return SAP_OK;
   static thread_local bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(sap_real_fast2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);

@@ -816,7 +816,6 @@ int sap_real_large_launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
   SAP_REQUIRE(p.scratch, SAP_E_SMEM, "sap_real: this problem size needs scratch of sap_real_scratch_doubles() doubles");
   SAP_REQUIRE(d.n <= 512 && d.m <= 512, SAP_E_DIMS, "sap_real (large path): n, m must be <= 512");
-  const char* force = getenv("SAP_REAL_FORCE_GENERIC");  // test hook: "3" = exact mode on keyed-eligible shapes
-  if (large_keyed(d) && !(force && force[0] == '3')) return launch_mode<true>(p, (cudaStream_t)stream);
+  if (large_keyed(d) && !p.large_exact) return launch_mode<true>(p, (cudaStream_t)stream);  // large_exact: selector override
   return launch_mode<false>(p, (cudaStream_t)stream);
 }

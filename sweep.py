@@ -80,15 +80,18 @@ def run_point(th, lib_mod, B, n, opts, peak):
     term_t = th.empty(B_run, 1, 1, dtype=th.uint8, device=dev).expand(B_run, Tp + 1, 1)
     fill_t = th.empty(B_run, 1, 1, dtype=th.int64, device=dev).expand(B_run, Tp + 1, 1)
     pa_t = th.empty(B_run, 1, n, dtype=idt, device=dev).expand(B_run, Tp + 1, n)
-    ain = th.empty(B_run, n, obs, dtype=th.float32, device=dev)
+    ain_mode = "f32" if mock else opts.agent_in
+    ain = th.empty(B_run, n, obs, dtype=th.float16 if ain_mode == "f16" else th.float32, device=dev)
     view = lib_mod.SapBatchView()
     view.obs, view.rewards, view.actions = lib_mod.field_of(obs_t), lib_mod.field_of(rew_t), lib_mod.field_of(act_t)
     view.terminated, view.filled = lib_mod.field_of(term_t), lib_mod.field_of(fill_t)
     if not mock:
         view.prev_assigns = lib_mod.field_of(pa_t)
     f = lib_mod.SapField()
-    f.ptr, f.env_stride, f.t_stride, f.dtype = ain.data_ptr(), n * obs, obs, lib_mod.SAP_F32
-    view.agent_in = f
+    f.ptr, f.env_stride, f.t_stride = ain.data_ptr(), n * obs, obs
+    f.dtype = lib_mod.SAP_F16 if ain_mode == "f16" else lib_mod.SAP_F32
+    if ain_mode != "none":
+        view.agent_in = f
     dims = lib_mod.SapEnvDims(B_run, n, m, Tp, L, M, N, 0)
     scratch = None
     if not mock:
@@ -126,12 +129,15 @@ def run_point(th, lib_mod, B, n, opts, peak):
         if rnd:
             ms.append(t)
     env_ms = sorted(ms)[len(ms) // 2]
-    bytes_step = n * m * L * 4 + n * obs * (e_obs + 4) + n * 16 + 16
+    e_ain = {"f32": 4, "f16": 2, "none": 0}[ain_mode]
+    bytes_step = n * m * L * 4 + n * obs * (e_obs + e_ain) + n * 16 + 16
+    bytes_8d = n * m * L * 4 + n * obs * 4 + n * 16 + 16   # window + fp32 obs + scalars
     rec = {"B": B, "B_run": B_run, "n": n, "m": m, "env": "mock" if mock else "real", "obs_size": obs,
            "env_kernel_ms": round(env_ms, 5), "env_steps_per_s": B_run / env_ms * 1e3,
            "agent_steps_per_s": B_run * n / env_ms * 1e3,
            "algorithmic_bytes_per_env_step": bytes_step,
-           "hbm_gbps": B_run * bytes_step / env_ms / 1e6, "hbm_frac": B_run * bytes_step / env_ms / 1e6 / peak}
+           "hbm_gbps": B_run * bytes_step / env_ms / 1e6, "hbm_frac": B_run * bytes_step / env_ms / 1e6 / peak,
+           "agent_in": ain_mode, "hbm_frac_8d": B_run * bytes_8d / env_ms / 1e6 / peak}
     del planes, obs_t, ain, scratch
     th.cuda.empty_cache()
     if opts.env_only:
@@ -205,6 +211,10 @@ def main():
     ap.add_argument("--Bs", type=str, default=None, help="comma list of env counts (default: the C5 grid)")
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--env-only", action="store_true", help="time the env kernel only (kernel tuning runs)")
+    ap.add_argument("--kernel-path", type=int, default=0,
+                    help="real-env kernel override (sap_real_select_kernel): 0 auto, 1 generic, 2 / 3 multi-CTA, 4 first-generation")
+    ap.add_argument("--agent-in", default="f32", choices=["f32", "f16", "none"],
+                    help="agent-input staging the env kernel writes next to the obs rows")
     ap.add_argument("--mem-gb", type=float, default=80.0)
     opts = ap.parse_args()
     import torch as th
@@ -213,6 +223,8 @@ def main():
 
     if not th.cuda.is_available():
         raise SystemExit("sweep.py needs a CUDA device (there is no CPU path)")
+    if opts.kernel_path:
+        assert lib_mod.load().sap_real_select_kernel(opts.kernel_path) >= 0
     peak, peak_src = hbm_peak()
     Bs = [256, 4096] if opts.quick else [256, 1024, 4096, 16384, 65536]
     ns = [10, 100] if opts.quick else [10, 50, 100, 200, 500]

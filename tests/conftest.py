@@ -21,3 +21,19 @@ def golden_path(name):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def real_kernel_path():
+    """Run the real-env step on a named kernel path for the rest of the test (``sap_real_select_kernel``):
+    0 automatic, 1 generic one-CTA-per-env kernel, 2 / 3 multi-CTA path (keyed lists / exact float64 selection),
+    4 first-generation shared-memory kernel.  Reset to automatic afterwards."""
+    from marl_sap_b200 import _lib
+
+    lib = _lib.load()
+
+    def select(which):
+        assert lib.sap_real_select_kernel(int(which)) >= 0
+
+    yield select
+    lib.sap_real_select_kernel(0)

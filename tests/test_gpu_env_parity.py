@@ -41,12 +41,12 @@ def _cast(x64, dtype):
 @pytest.mark.parametrize("real_dtype", [th.float16, th.float32])
 @pytest.mark.parametrize("shared", [True, False])
 @pytest.mark.parametrize("generic", ["0", "1", "2", "3"])
-def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, monkeypatch):
+def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, real_kernel_path):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
-    # "0": shared-memory fast path, "1": generic one-CTA-per-env kernel, "2" / "3": multi-CTA path of the large shapes
-    # (keyed lists with certificates / exact float64 selection)
-    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
+    # "0": automatic (shared-memory fast path), "1": generic one-CTA-per-env kernel, "2" / "3": multi-CTA path of the large
+    # shapes (keyed lists with certificates / exact float64 selection)
+    real_kernel_path(generic)
 
     g = _load(name)
     B = 3
@@ -92,10 +92,10 @@ def test_real_env_matches_reference_golden(name, real_dtype, shared, generic, mo
     dict(B=2, n=12, m=200, T=3, L=3, M=10, N=10, gen="const", seed=8),
 ])
 @pytest.mark.parametrize("generic", ["0", "1", "2", "3"])
-def test_real_env_matches_oracle(cfg, generic, monkeypatch):
+def test_real_env_matches_oracle(cfg, generic, real_kernel_path):
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
-    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
+    real_kernel_path(generic)
     rng = np.random.default_rng(cfg["seed"])
     B, n, m, T, L, M, N = (cfg[k] for k in ("B", "n", "m", "T", "L", "M", "N"))
     if cfg["gen"] == "dense":
@@ -310,9 +310,10 @@ def test_single_env_facade_kat1():
     np.testing.assert_allclose(bh[..., 0], g["beta"][0][..., 0] - 0.5 * (1 - np.eye(4)) * (g["beta"][0].sum(-1) > 1e-12))
 
 
-def test_real_env_full_size_fast_equals_generic(monkeypatch):
-    """BASELINE shape 100 x 100 (M = N = 10, L = 3, fp16 scheme) at a few hundred envs: the shared-memory fast kernel, the
-    generic float64 kernel and the multi-CTA large-shape path must produce identical bytes (obs, rewards, top-M, agent input) step after step."""
+def test_real_env_full_size_fast_equals_generic(real_kernel_path):
+    """BASELINE shape 100 x 100 (M = N = 10, L = 3, fp16 scheme) at a few hundred envs: both generations of the shared-memory
+    kernel, the generic float64 kernel and the multi-CTA large-shape path (both modes) must produce identical bytes (obs,
+    rewards, top-M, agent input) step after step."""
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
     B, n, m, T, L, M, N = 296, 100, 100, 6, 3, 10, 10
@@ -322,8 +323,8 @@ def test_real_env_full_size_fast_equals_generic(monkeypatch):
     S[:40] = (S[:40] * 8).round() / 8  # coarse grid: duplicate sums above zero
     acts = [th.randint(0, m, (B, n), generator=g).cuda() for _ in range(T)]
     outs = []
-    for generic in ("1", "2", "3", "0"):
-        monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", generic)
+    for generic in ("1", "2", "3", "4", "0"):
+        real_kernel_path(generic)
         env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S.cuda())
         batch = _batch_for(env, B, lazy=("beta", "avail_actions", "actions_onehot"))
         batch.agent_in = th.zeros(B, n, env.obs_size, device="cuda")
@@ -335,9 +336,9 @@ def test_real_env_full_size_fast_equals_generic(monkeypatch):
             ain.append(batch.agent_in.clone())
             tops.append(env.top.clone())
         outs.append((batch["obs"].clone(), batch["rewards"].clone(), th.stack(ain), th.stack(tops[:-1]), env.ep_return.clone()))
-    for a, b, c, e in zip(*outs):
-        assert th.equal(a, b) and th.equal(a, c) and th.equal(a, e)
-    obs, _, ain, _, _ = outs[3]
+    for a, b, c, e, g in zip(*outs):
+        assert th.equal(a, b) and th.equal(a, c) and th.equal(a, e) and th.equal(a, g)
+    obs, _, ain, _, _ = outs[4]
     assert th.equal(ain, obs.permute(1, 0, 2, 3).float())  # agent_in == float(obs[:, t]) for every t
 
 
@@ -370,11 +371,11 @@ def test_real_env_constellation_scale_matches_oracle():
     dict(B=2, n=200, m=200, T=3, L=3, M=10, N=10, prios=False, dtype=th.float16, gen="ties", seed=25),  # natural large path, tie-heavy
     dict(B=1, n=511, m=511, T=2, L=2, M=10, N=15, prios=False, dtype=th.float16, gen="dense", seed=26),  # largest keyed shape
 ])
-def test_real_env_multi_cta_path_matches_oracle(cfg, monkeypatch):
+def test_real_env_multi_cta_path_matches_oracle(cfg, real_kernel_path):
     """The multi-CTA path of the large shapes (csrc/sap_real_large.cu) on ragged and extreme shapes, both of its modes."""
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
 
-    monkeypatch.setenv("SAP_REAL_FORCE_GENERIC", "2")
+    real_kernel_path(2)
     rng = np.random.default_rng(cfg["seed"])
     B, n, m, T, L, M, N = (cfg[k] for k in ("B", "n", "m", "T", "L", "M", "N"))
     if cfg["gen"] == "dense":
