@@ -102,11 +102,11 @@ class EpisodeBatch:
                 _lib.require_cuda(td[name], name)
                 setattr(view, name, _lib.field_of(td[name]))
         ai = getattr(self, "agent_in", None)
-        if ai is not None:  # [B, n, row] f32 staging of the agent network's input (see SapBatchView.agent_in)
-            _lib.require_cuda(ai, "agent_in")
-            assert ai.dtype == th.float32 and ai.dim() == 3 and ai.stride(2) == 1
+        if ai is not None:  # [B, n, row] staging of the agent network's input (see SapBatchView.agent_in): f32, or f16
+            _lib.require_cuda(ai, "agent_in")   # rows (packed or padded to a multiple of 8 columns) for the split-precision fc1
+            assert ai.dtype in (th.float32, th.float16) and ai.dim() == 3 and ai.stride(2) == 1
             f = _lib.SapField()
-            f.ptr, f.env_stride, f.t_stride, f.dtype = ai.data_ptr(), ai.stride(0), ai.stride(1), _lib.SAP_F32
+            f.ptr, f.env_stride, f.t_stride, f.dtype = ai.data_ptr(), ai.stride(0), ai.stride(1), _lib.sap_dtype(ai.dtype)
             view.agent_in = f
         return view
 

@@ -259,6 +259,10 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   float* ain = vw.agent_in.ptr && !ain_half ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride
                                             : nullptr;
   __half* ain16 = ain_half ? reinterpret_cast<__half*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
+  // fp16 staging rows are either packed (pitch = obs size: one more bulk store of the same bytes) or padded to a pitch
+  // that a tensor-core GEMM can read with 128-bit loads (496 halves for 490): then the rows are copied word by word
+  const int ain16_pitch = ain_half ? (int)vw.agent_in.t_stride : 0;
+  const bool ain16_bulk = ain_half && ain16_pitch == kObs;
   if (done) {  // :226-228
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     uint4* o4 = reinterpret_cast<uint4*>(obs_out);
@@ -267,9 +271,9 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
       uint4* a4 = reinterpret_cast<uint4*>(ain);
       for (int e = tid; e < (n * kObs * 4) >> 4; e += kThreads) a4[e] = z;
     }
-    if (ain16) {
-      uint4* a4 = reinterpret_cast<uint4*>(ain16);
-      for (int e = tid; e < (n * kRowBytes) >> 4; e += kThreads) a4[e] = z;
+    if (ain16) {  // packed or padded rows: the pad columns stay as the host initialised them (zeros)
+      uint32_t* a2 = reinterpret_cast<uint32_t*>(ain16);
+      for (int e = tid; e < n * (ain16_pitch >> 1); e += kThreads) a2[e] = 0u;
     }
     if (vw.beta.ptr) {
       const int64_t bb = sap_field_off(vw.beta, b, t_slot);
@@ -842,7 +846,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
                    "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes), "l"(pol_drop)
                    : "memory");
-      if (ain16)
+      if (ain16_bulk)
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ain16 + (size_t)r0 * kObs),
                      "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes)
                      : "memory");
@@ -862,6 +866,14 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
         stg_hint4(o, *reinterpret_cast<const uint4*>(&lo4), pol_drop);
         stg_hint4(o + 4, *reinterpret_cast<const uint4*>(&hi4), pol_drop);
       }
+    }
+    if (ain16 && !ain16_bulk) {  // padded fp16 rows: 245 words per row, coalesced 32-bit stores
+      constexpr int kRowWords = kRowBytes / 4;
+      const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(stage);
+      uint32_t* adst = reinterpret_cast<uint32_t*>(ain16 + (size_t)r0 * ain16_pitch);
+      for (int r = warp; r < rows; r += kWarps)
+#pragma unroll
+        for (int w = lane; w < kRowWords; w += 32) adst[r * (ain16_pitch >> 1) + w] = ssrc[r * kRowWords + w];
     }
     // the staging rows may be overwritten once the bulk store has finished READING them
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -894,9 +906,10 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
       return SAP_E_DTYPE;
     }
     const int esz = vw.agent_in.dtype == SAP_F32 ? 4 : 2;
-    if (vw.agent_in.t_stride != kObs || !sap_aligned16(vw.agent_in.ptr) || ((vw.agent_in.env_stride * esz) & 15)) {
+    const bool padded16 = esz == 2 && vw.agent_in.t_stride > kObs && !(vw.agent_in.t_stride & 1);  // padded fp16 rows
+    if ((vw.agent_in.t_stride != kObs && !padded16) || !sap_aligned16(vw.agent_in.ptr) || ((vw.agent_in.env_stride * esz) & 15)) {
       if (esz == 2) {
-        sap_set_error("sap_real: an f16 agent_in must be [B, n, obs] contiguous and 16-byte aligned");
+        sap_set_error("sap_real: an f16 agent_in must be [B, n, pitch >= obs] with an even pitch and 16-byte aligned envs");
         return SAP_E_CONSTRAINT;
       }
       return SAP_OK;

@@ -156,7 +156,18 @@ class CudaVecRunner:
             row = self.env.obs_size
             row += self.env.m if getattr(self.args, "obs_last_action", False) else 0
             row += self.env.n if getattr(self.args, "obs_agent_id", False) else 0
-            self.agent_in = th.zeros(self.batch_size, self.env.n, row, dtype=th.float32, device=self.device)
+            dtype = th.float32
+            # opt-in (args.agent_fc1 = "fp16_split"): the agent's first layer reads the fp16 observation rows themselves
+            # (split-precision tensor-core GEMM, modules/agents); the env kernel then stages fp16 rows, padded to a
+            # multiple of 8 columns, instead of widening every row to fp32
+            if getattr(self.args, "agent_fc1", "fp32") == "fp16_split":
+                ok = self.env.kind == "real" and scheme["obs"]["dtype"] == th.float16 and \
+                    bool(self.env.lib.sap_real_agent_in_f16_ok(self.env.dims()))
+                if not ok:
+                    raise ValueError("agent_fc1='fp16_split' needs the real env with its fp16 scheme at a shape the "
+                                     "one-CTA-per-env kernel takes (M = N = 10, L = 3, 64 < n <= 128, m <= 128)")
+                dtype, row = th.float16, (row + 7) // 8 * 8
+            self.agent_in = th.zeros(self.batch_size, self.env.n, row, dtype=dtype, device=self.device)
 
     def get_env(self):
         """The reference returns worker 0's env, pickled through the Pipe (parallel_runner.py:246-247, 281-282): a COPY

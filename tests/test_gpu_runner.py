@@ -442,3 +442,119 @@ def test_rollout_diagnostics_match_the_learner_loops():
     assert calc_raw_benefits(th.tensor(beta).cuda(), a) == pytest.approx(want, rel=1e-9)
     assert calc_raw_benefits(th.tensor(beta).cuda().unsqueeze(-1).expand(-1, -1, -1, -1, 3), a) == pytest.approx(want, rel=1e-9)
     assert calc_raw_benefits_from_planes(th.tensor(beta).cuda(), a) == pytest.approx(want, rel=1e-9)
+
+
+def test_agent_fc1_split_precision_matches_fp32():
+    """Opt-in first layer (args.agent_fc1 = "fp16_split"): fp16 rows against [W_0 | 2^-11 W_1 | 2^-22 W_2] on the tensor
+    cores + sap_split_bias_act == relu(F.linear(x.float(), W, b)) to accumulation-order accuracy (2e-6 relative)."""
+    from marl_sap_b200.modules.agents import RNNAgent
+
+    th.manual_seed(4)
+    args = SimpleNamespace(hidden_dim=64, use_rnn=False, m=100, agent_fc1_terms=3)
+    agent = RNNAgent(490, args).cuda()
+    rows = 4096
+    x16 = th.zeros(rows, 496, dtype=th.float16, device="cuda")
+    x16[:, :490] = (th.rand(rows, 490, device="cuda") * 3).half()
+    x16[:, :490][th.rand(rows, 490, device="cuda") < 0.3] = 0
+    with th.no_grad():
+        want = th.relu(th.nn.functional.linear(x16[:, :490].double(), agent.fc1.weight.double(), agent.fc1.bias.double()))
+        got = agent._linear_fp16_split(agent.fc1, x16, relu=True)
+        ref32 = th.relu(th.nn.functional.linear(x16[:, :490].float(), agent.fc1.weight, agent.fc1.bias))
+        scale = want.abs().max().item()
+        err_split = (got.double() - want).abs().max().item() / scale
+        err_fp32 = (ref32.double() - want).abs().max().item() / scale
+        assert err_split < 2e-6, (err_split, err_fp32)
+        # two pieces: 22 mantissa bits of W
+        agent.args.agent_fc1_terms = 2
+        got2 = agent._linear_fp16_split(agent.fc1, x16, relu=True)
+        assert (got2.double() - want).abs().max().item() / scale < 2e-5
+        # whole forward: fp16 rows in, same Q as the fp32 path
+        agent.args.agent_fc1_terms = 3
+        q16, _ = agent(x16, agent.init_hidden().expand(rows, -1))
+        q32, _ = agent(x16[:, :490].float(), agent.init_hidden().expand(rows, -1))
+        assert (q16 - q32).abs().max().item() < 5e-6 * max(1.0, q32.abs().max().item())
+    # an in-place weight update invalidates the cached pieces
+    with th.no_grad():
+        agent.fc1.weight.mul_(0.5)
+        got3 = agent._linear_fp16_split(agent.fc1, x16, relu=False)
+        want3 = th.nn.functional.linear(x16[:, :490].double(), agent.fc1.weight.double(), agent.fc1.bias.double())
+        assert (got3.double() - want3).abs().max().item() / want3.abs().max().item() < 2e-6
+
+
+@pytest.mark.parametrize("extra", [False, True])
+def test_runner_fp16_split_agent_matches_default(extra):
+    """The opt-in rollout (fp16 staging rows, split-precision fc1) against the default one (fp32 staging rows, sgemm) at
+    the bench shape: identical observations / rewards as long as the actions agree, and Q-values equal to 1e-5."""
+    rng = np.random.default_rng(23)
+    B, n, m, T, L, M, N = 6, 100, 100, 4, 3, 10, 10
+    S = O.gen_dense(rng, B, n, m, T)
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=0.5, sat_prox_mat=S, graphs=1)
+    draws = {"u_explore": rng.random((T, B, n), dtype=np.float32), "u_action": rng.random((T, B, n), dtype=np.float32)}
+    out = {}
+    for mode in ("fp32", "fp16_split"):
+        args = make_args("real_constellation_env", env_args, B, agent_fc1=mode, obs_agent_id=extra, obs_last_action=extra,
+                         epsilon_start=0.3, epsilon_finish=0.3)
+        runner, mac, buffer, _ = build(args)
+        assert runner.agent_in.dtype == (th.float32 if mode == "fp32" else th.float16)
+        assert runner.agent_in.shape[-1] == ((490 + (200 if extra else 0) + 7) // 8 * 8 if mode == "fp16_split" else 490 + (200 if extra else 0))
+        DrawInjector(mac.action_selector, draws)
+        qs = []
+        orig = mac.forward
+
+        def fwd(*a, _o=orig, _q=qs, **k):
+            q = _o(*a, **k)
+            _q.append(q.clone())
+            return q
+
+        mac.forward = fwd
+        with th.no_grad():
+            batch = runner.run(test_mode=False)
+        out[mode] = (batch["obs"].clone(), batch["actions"].clone(), batch["rewards"].clone(), th.stack(qs))
+    (o32, a32, r32, q32), (o16, a16, r16, q16) = out["fp32"], out["fp16_split"]
+    same = (a32 == a16).all(dim=2).all(dim=2)  # [B, T+1]: envs whose joint action agrees at every step so far
+    assert same[:, 0].all() or (q32[0] - q16[0]).abs().max() < 1e-5
+    assert (q32[0] - q16[0]).abs().max().item() < 1e-5 * max(1.0, q32[0].abs().max().item())
+    agree = same.cumprod(dim=1).bool()
+    assert agree[:, 0].float().mean() > 0.8  # near-ties may flip a greedy pick; the bulk must agree
+    for b in range(B):
+        for t in range(T):
+            if agree[b, :t + 1].all():
+                assert th.equal(o32[b, t + 1], o16[b, t + 1]) and th.equal(r32[b, t], r16[b, t])
+
+
+def test_runner_graph_refuses_jumpstart_and_tracks_buffers():
+    """CUDA-graph rollout: a MAC that decides on the host (JumpstartMAC) is never captured; a BasicMAC capture is keyed on
+    every buffer address and keeps its buffers alive; test-mode episodes never roll out over replay rows."""
+    rng = np.random.default_rng(5)
+    B, n, m, T, L = 3, 6, 8, 5, 2
+    S = O.gen_ref_like(rng, B, n, m, T)
+    env_args = dict(n=n, m=m, T=T, L=L, lambda_=0.5, sat_prox_mat=S)
+    args = make_args("mock_constellation_env", env_args, B, use_cuda_graph=True)
+    runner, mac, buffer, _ = build(args)
+    runner.attach_replay(buffer)
+    prev0 = np.stack([rng.permutation(m)[:n] for _ in range(B)])
+    with th.no_grad():
+        b1 = runner.run(test_mode=False, prev0=prev0)
+        buffer.insert_episode_batch(b1)
+        b2 = runner.run(test_mode=False, prev0=prev0)   # second episode: captured
+        buffer.insert_episode_batch(b2)
+        assert len(runner._graphs) == 1
+        (key, entry), = runner._graphs.items()
+        assert entry[1] is b2 and len(key) >= len(b2.data.transition_data) + 3
+        rows_before = {k: v.clone() for k, v in buffer.data.transition_data.items()}
+        bt = runner.run(test_mode=True, prev0=prev0)    # test episode: private batch, ring untouched
+        assert getattr(bt, "_ring_owner", None) is None
+        for k, v in buffer.data.transition_data.items():
+            assert th.equal(v, rows_before[k]), k
+    # JumpstartMAC: refused
+    from marl_sap_b200.controllers import REGISTRY as mac_REGISTRY
+
+    args2 = make_args("mock_constellation_env", env_args, B, use_cuda_graph=True, mac="jumpstart_mac",
+                      jumpstart_action_selector="haa_selector", jumpstart_epsilon_start=0.5, jumpstart_epsilon_finish=0.5,
+                      jumpstart_epsilon_anneal_time=1, jumpstart_evaluation_epsilon=0.0)
+    runner2, mac2, _, _ = build(args2)
+    assert isinstance(mac2, mac_REGISTRY["jumpstart_mac"]) and not mac2.graph_capturable
+    with th.no_grad():
+        for _ in range(3):
+            runner2.run(test_mode=False, prev0=prev0)
+    assert not getattr(runner2, "_graphs", {})
