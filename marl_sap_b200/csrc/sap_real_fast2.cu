@@ -218,10 +218,20 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     if (lane == 0) sRed[warp] = local_ret;
     if (vw.actions_onehot.ptr) {
       const int64_t base = sap_field_off(vw.actions_onehot, b, k_old);
+      const bool v16 = vw.actions_onehot.dtype == SAP_I16 &&
+                       ((reinterpret_cast<uintptr_t>(vw.actions_onehot.ptr) + 2 * base) & 7) == 0;
       for (int i = warp; i < n; i += kWarps) {
         const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
-        for (int j = lane; j < m; j += 32)
-          sap_store_int(vw.actions_onehot.ptr, base + (int64_t)i * m + j, vw.actions_onehot.dtype, a == j ? 1 : 0);
+        if (v16) {  // four int16 flags per store (m % 4 == 0)
+          uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<int16_t*>(vw.actions_onehot.ptr) + base + (int64_t)i * m);
+          for (int j4 = lane; j4 < m >> 2; j4 += 32) {
+            const int d = a - 4 * j4;
+            o[j4] = make_uint2(d == 0 ? 1u : (d == 1 ? 0x10000u : 0u), d == 2 ? 1u : (d == 3 ? 0x10000u : 0u));
+          }
+        } else {
+          for (int j = lane; j < m; j += 32)
+            sap_store_int(vw.actions_onehot.ptr, base + (int64_t)i * m + j, vw.actions_onehot.dtype, a == j ? 1 : 0);
+        }
       }
     }
     if (p.counts_out)
@@ -249,9 +259,14 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   if (vw.prev_assigns.ptr && tid < n)
     sap_store_int(vw.prev_assigns.ptr, sap_field_off(vw.prev_assigns, b, t_slot) + tid, vw.prev_assigns.dtype,
                   p.is_reset ? tid : a_mine);
-  if (vw.avail_actions.ptr) {
+  if (vw.avail_actions.ptr) {  // eager field: every action available (:267-273)
     const int64_t base = sap_field_off(vw.avail_actions, b, t_slot);
-    for (int e = tid; e < nm; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
+    if (vw.avail_actions.dtype == SAP_U8 && ((reinterpret_cast<uintptr_t>(vw.avail_actions.ptr) + base) & 15) == 0) {
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(vw.avail_actions.ptr) + base);  // nm % 16 == 0
+      for (int e = tid; e < nm >> 4; e += kThreads) o[e] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    } else {
+      for (int e = tid; e < nm; e += kThreads) sap_store_int(vw.avail_actions.ptr, base + e, vw.avail_actions.dtype, 1);
+    }
   }
   __half* obs_out = reinterpret_cast<__half*>(vw.obs.ptr) + sap_field_off(vw.obs, b, t_slot);
   // agent-input staging rows of this env: fp32 (widened here) or fp16 (the same bytes, bulk-stored a second time)
@@ -419,7 +434,9 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     if (Leff == kL && k_nonneg) run(std::true_type{});
     else run(std::false_type{});
   }
-  if (vw.beta.ptr) {  // eager `beta` buffer field (off the hot path: the runners keep it lazy)
+  const bool beta_fast = vw.beta.ptr && vw.beta.dtype == SAP_F16 &&
+                         ((reinterpret_cast<uintptr_t>(vw.beta.ptr) + 2 * sap_field_off(vw.beta, b, t_slot)) & 7) == 0;
+  if (vw.beta.ptr && !beta_fast) {  // eager `beta` buffer field in another dtype than the scheme's fp16: scalar stores
     const int64_t bb = sap_field_off(vw.beta, b, t_slot);
     for (int i = warp; i < n; i += kWarps)
       for (int j = lane; j < m; j += 32)
@@ -746,6 +763,16 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
       *reinterpret_cast<uint4*>(t01 + (size_t)e4 * 4) = *reinterpret_cast<const uint4*>(h);
       const __half2 g2[2] = {__floats2half2_rn(v[2].x, v[2].y), __floats2half2_rn(v[2].z, v[2].w)};
       *reinterpret_cast<uint2*>(t2 + (size_t)e4 * 4) = *reinterpret_cast<const uint2*>(g2);
+      if (beta_fast) {  // eager `beta` field [n][m][3] fp16: the same rounded values, 4 pairs = 24 bytes
+        const uint32_t* h32 = reinterpret_cast<const uint32_t*>(h);
+        const uint32_t* g32 = reinterpret_cast<const uint32_t*>(g2);
+        uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<__half*>(vw.beta.ptr) + sap_field_off(vw.beta, b, t_slot) +
+                                            (int64_t)e4 * 12);
+        // halves: p0.0 p0.1 p0.2 p1.0 | p1.1 p1.2 p2.0 p2.1 | p2.2 p3.0 p3.1 p3.2
+        o[0] = make_uint2(h32[0], __byte_perm(g32[0], h32[1], 0x5410));
+        o[1] = make_uint2(__byte_perm(h32[1], g32[0], 0x7632), h32[2]);
+        o[2] = make_uint2(__byte_perm(g32[1], h32[3], 0x5410), __byte_perm(h32[3], g32[1], 0x7632));
+      }
     };
     auto run = [&](auto tag) {
       constexpr bool kFull = decltype(tag)::value;

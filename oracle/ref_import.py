@@ -21,7 +21,16 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MARL_SAP_REFERENCE", "/root/reference")
+def _reference_root() -> str:
+    """`/root/reference` in the build container; on the GPU box the copy `oracle/make_ref.py` left under `oracle/_ref`."""
+    cands = [os.environ.get("MARL_SAP_REFERENCE"), "/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "src", "envs")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _reference_root()
 REFERENCE_SRC = os.path.join(REFERENCE_ROOT, "src")
 
 
