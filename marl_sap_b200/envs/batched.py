@@ -77,6 +77,12 @@ class _BatchedEnvBase:
         self.t_host = 0  # host mirror of k (all envs step in lockstep)
         self.launches_per_step = 1  # kernels one reset()/step() call enqueues (4 on the multi-CTA path of large shapes)
 
+    def __deepcopy__(self, memo):
+        """A batched env is device state (benefit planes, counters, the loaded library): callers that deep-copy an
+        object graph holding one - the reference's learners do ``copy.deepcopy(mac)`` for their target network, and the
+        MAC's jump-start selector is bound to the runner's env - get the SAME env back, not a second copy of the planes."""
+        return self
+
     # ------------------------------------------------------------------ benefits
     def load_benefits(self, sat_prox_mat):
         """Install benefit tensors given in the REFERENCE layout: [n, m, T] (shared by all B envs, like

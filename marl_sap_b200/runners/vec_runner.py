@@ -297,13 +297,36 @@ class CudaVecRunner:
         self.reset(test_mode=test_mode, **reset_kwargs)
         if not (getattr(self.args, "use_cuda_graph", False) and self._rollout_graph(test_mode)):
             self._rollout_loop(test_mode)
-        if self.compat_quirks and "terminated" in self.batch.data.transition_data:
-            # parallel_runner.py:181-187: `terminated` <- truthiness of the non-empty reward list of every env
-            self.batch.data.transition_data["terminated"][:, :self.T] = True
+        if self.compat_quirks:
+            self._apply_parallel_runner_quirks(test_mode)
         self.kernel_launches += (1 + self.env.launches_per_step) * self.T  # selector + env kernel(s) per timestep
         self.last_episode_returns = self.env.ep_return.clone()
         self._finish_run(test_mode)
         return self.batch
+
+    def _apply_parallel_runner_quirks(self, test_mode):
+        """What the reference ParallelRunner stores beyond EpisodeRunner semantics (golden
+        tests/golden/runner_parallel.npz), reproduced only under ``compat_parallel_runner_quirks``:
+
+        * parallel_runner.py:131-139: the loop selects actions once more at t = T (for envs it has not yet noticed to be
+          finished) and stores them - plus their one-hot - in slot T before it breaks;
+        * parallel_runner.py:181-187: ``terminated`` is assigned from the truthiness of the reward LIST collected so far
+          in this timestep, not from the env: False for the first env of the batch (the list is still empty), True for
+          every other env, at every step t < T."""
+        td = self.batch.data.transition_data
+        B, n, T = self.batch_size, self.env.n, self.T
+        actions = self.mac.select_actions(self.batch, t_ep=T, t_env=self.t_env, test_mode=test_mode)
+        self.kernel_launches += 1
+        if "actions" in td and td["actions"].shape[-1] == 1:
+            td["actions"][:, T] = actions.view(B, n, 1).to(td["actions"].dtype)
+            if "actions_onehot" in td:
+                oh = td["actions_onehot"][:, T]
+                oh.zero_()
+                oh.scatter_(2, actions.view(B, n, 1).long(), 1)
+        if "terminated" in td:
+            td["terminated"][:, :T] = True
+            if self.env_offset == 0:
+                td["terminated"][0, :T] = False
 
     # ------------------------------------------------------------------ statistics (A.6 of SURVEY.md)
     def _finish_run(self, test_mode):

@@ -490,6 +490,7 @@ def main():
     golden_policy_selectors(R)
     golden_buffer(R)
     golden_runner(R)
+    golden_parallel_runner(R)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
@@ -569,8 +570,80 @@ def golden_runner(R):
                             t_env_after=runner.t_env, return_mean=log.stats["return_mean"][-1][1], **extra_out, **out)
 
 
+def golden_parallel_runner(R):
+    """The reference's ParallelRunner (runners/parallel_runner.py:12-243: one forked env process per env, pickled pre-/post-
+    transition data over Pipes) + BasicMAC + RNNAgent + epsilon_greedy with B = 4 envs and injected selector draws.  Keeps
+    what that runner really writes, quirks included: `terminated` comes from the truthiness of the reward
+    list collected so far (:181-187: False for the first env of the batch, True for every other env, at every step), and one
+    extra action selection is made and stored at t = T (:131-139) before the loop notices that every env has finished."""
+    import torch as th
+    from types import SimpleNamespace as SN
+
+    class Log:
+        def __init__(self):
+            self.stats = {}
+
+        def log_stat(self, k, v, t):
+            self.stats.setdefault(k, []).append((t, float(v)))
+
+    import contextlib
+    import io
+
+    B, n, m, T, M, N, L = 4, 8, 12, 10, 4, 3, 3
+    for seed in range(200):
+        rng = np.random.default_rng(5000 + seed)
+        S = O.gen_dense(rng, 1, n, m, T)[0]
+        env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, L=L, lambda_=0.5, N=N, M=M,
+                        sat_prox_mat=S.astype(np.float64), graphs=1, seed=0)
+        args = SN(env="real_constellation_env", env_args=env_args, batch_size_run=B, use_mps_action_selection=True, device="cpu",
+                  mac="basic_mac", render=False, test_nepisode=B, runner_log_interval=1, agent="rnn", hidden_dim=64,
+                  use_rnn=False, agent_output_type="q", action_selector="epsilon_greedy", epsilon_start=0.4,
+                  epsilon_finish=0.4, epsilon_anneal_time=1, evaluation_epsilon=0.0, obs_agent_id=True,
+                  obs_last_action=True, n=n, m=m, T=T)
+        log = Log()
+        with contextlib.redirect_stdout(io.StringIO()):
+            runner = R.parallel_runner.ParallelRunner(args, log)
+            env = runner.get_env()
+        groups = {"agents": n}
+        buffer = R.episode_buffer.ReplayBuffer(env.scheme, groups, 2 * B, T + 1, preprocess=env.preprocess, device="cpu")
+        th.manual_seed(seed)
+        mac = R.basic_controller.BasicMAC(buffer.scheme, groups, args)
+        with contextlib.redirect_stdout(io.StringIO()):
+            runner.setup(scheme=env.scheme, groups=groups, preprocess=env.preprocess, mac=mac)
+        u_explore = rng.random((T + 1, B, n), dtype=np.float32)   # T + 1 selections: the extra one at t = T
+        u_action = rng.random((T + 1, B, n), dtype=np.float32)
+        gaps, step = [], [0]
+        sel = mac.action_selector
+        orig = sel.select_action
+
+        def wrapped(agent_inputs, avail_actions, t_env, test_mode=False, beta=None):
+            top2 = th.topk(agent_inputs, 2, dim=-1).values
+            gaps.append(float((top2[..., 0] - top2[..., 1]).min()))
+            with _inject(th, R, [u_explore[step[0]]], u_action[step[0]]):
+                a = orig(agent_inputs, avail_actions, t_env, test_mode=test_mode, beta=beta)
+            step[0] += 1
+            return a
+
+        sel.select_action = wrapped
+        with th.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            batch = runner.run(test_mode=False)
+            runner.close_env()
+        assert step[0] == T + 1
+        if min(gaps) > 1e-3:
+            break
+    else:
+        raise RuntimeError("no seed with a safe Q gap")
+    out = {f"td_{k}": v.numpy().copy() for k, v in batch.data.transition_data.items()}
+    out.update({f"w_{k}": v.numpy().copy() for k, v in mac.agent.state_dict().items()})
+    np.savez_compressed(os.path.join(HERE, "runner_parallel.npz"), S=S, B=B, n=n, m=m, T=T, L=L, lambda_=0.5, M=M, N=N,
+                        u_explore=u_explore, u_action=u_action, eps=0.4, min_gap=min(gaps), t_env_after=runner.t_env,
+                        return_mean=log.stats["return_mean"][-1][1], return_std=log.stats["return_std"][-1][1], **out)
+
+
 if __name__ == "__main__":
     if "--runner-only" in sys.argv:
         golden_runner(ref_import.ref_modules())
+    elif "--parallel-only" in sys.argv:
+        golden_parallel_runner(ref_import.ref_modules())
     else:
         main()

@@ -558,3 +558,42 @@ def test_runner_graph_refuses_jumpstart_and_tracks_buffers():
         for _ in range(3):
             runner2.run(test_mode=False, prev0=prev0)
     assert not getattr(runner2, "_graphs", {})
+
+
+@pytest.mark.parametrize("compat", [True, False])
+def test_parallel_runner_matches_reference_parallel_runner_golden(compat):
+    """REGISTRY["parallel"] with B = 4 envs against the batch the reference's own ParallelRunner produced
+    (tests/golden/runner_parallel.npz: forked env workers, injected draws).  Every field the reference's bugs do not touch
+    is bit-identical; with ``compat_parallel_runner_quirks`` the two quirky ones are too (`terminated` from the list
+    truthiness, the extra selection stored at t = T); without it they follow EpisodeRunner semantics."""
+    import os
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "runner_parallel.npz")))
+    B, n, m, T = int(g["B"]), int(g["n"]), int(g["m"]), int(g["T"])
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=int(g["N"]), M=int(g["M"]), L=int(g["L"]),
+                    lambda_=float(g["lambda_"]), sat_prox_mat=g["S"].astype(np.float64), graphs=1, seed=0)
+    args = make_args("real_constellation_env", env_args, B, obs_agent_id=True, obs_last_action=True, epsilon_start=0.4,
+                     epsilon_finish=0.4, epsilon_anneal_time=1, compat_parallel_runner_quirks=compat)
+    runner, mac, buffer, logger = build(args)
+    mac.agent.load_state_dict({k[2:]: th.tensor(v) for k, v in g.items() if k.startswith("w_")})
+    DrawInjector(mac.action_selector, {"u_explore": g["u_explore"], "u_action": g["u_action"]})
+    env = runner.get_env()   # a12: the single-env facade with the reference env API, not just a shape record
+    assert hasattr(env, "beta_hat") and hasattr(env, "step") and (env.n, env.m, env.T) == (n, m, T)
+    with th.no_grad():
+        batch = runner.run(test_mode=False)
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    for k in ("obs", "rewards", "beta", "prev_assigns", "avail_actions", "filled"):
+        assert th.equal(td[k], th.tensor(g["td_" + k])), k
+    assert th.equal(td["actions"][:, :T], th.tensor(g["td_actions"][:, :T]))
+    assert th.equal(td["actions_onehot"][:, :T], th.tensor(g["td_actions_onehot"][:, :T]))
+    if compat:
+        assert th.equal(td["actions"], th.tensor(g["td_actions"]))                 # incl. the selection stored at t = T
+        assert th.equal(td["actions_onehot"], th.tensor(g["td_actions_onehot"]))
+        assert th.equal(td["terminated"], th.tensor(g["td_terminated"]))           # env 0: never, others: always
+    else:
+        assert not td["actions"][:, T].any() and not td["actions_onehot"][:, T].any()
+        want = th.zeros(B, T + 1, 1, dtype=th.bool)
+        want[:, T - 1] = True
+        assert th.equal(td["terminated"], want)
+    assert runner.t_env == int(g["t_env_after"])
+    assert logger.stats["return_mean"][-1][1] == pytest.approx(float(g["return_mean"]), rel=1e-9)

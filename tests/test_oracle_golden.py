@@ -171,3 +171,38 @@ def test_bids_as_actions_oracle_matches_reference():
     for t, bids in enumerate(g["bids"]):
         r, _ = ms.step(O.lsa_maximize(bids[None])[0])
         np.testing.assert_array_equal(r[0], g["mock_rewards"][t])
+
+
+def test_oracle_batched_rollout_matches_reference_parallel_runner():
+    """B = 4 envs: the oracle's vectorised rollout (and its epsilon-greedy selector, fed the recorded draws and the Q-values
+    of the recorded agent) against the batch the reference's own ParallelRunner wrote (runner_parallel.npz)."""
+    import torch as th
+
+    g = _load("runner_parallel.npz")
+    B, n, m, T = int(g["B"]), int(g["n"]), int(g["m"]), int(g["T"])
+    S = np.broadcast_to(g["S"].astype(np.float64), (B, n, m, T)).copy()
+    st = O.RealState(S, int(g["L"]), int(g["M"]), int(g["N"]), float(g["lambda_"]))
+    W = {k[2:]: th.tensor(v) for k, v in g.items() if k.startswith("w_")}
+    last = [np.zeros((B, n, m), dtype=np.float32)]
+
+    def policy(t, pre):
+        obs = th.tensor(pre["obs"], dtype=th.float16).float().reshape(B * n, -1)
+        x = th.cat([obs, th.tensor(last[0]).reshape(B * n, -1), th.eye(n).unsqueeze(0).expand(B, -1, -1).reshape(B * n, -1)], 1)
+        h = th.relu(th.nn.functional.linear(x, W["fc1.weight"], W["fc1.bias"]))
+        h = th.relu(th.nn.functional.linear(h, W["rnn.weight"], W["rnn.bias"]))
+        q = th.nn.functional.linear(h, W["fc2.weight"], W["fc2.bias"]).reshape(B, n, m).numpy()
+        a = O.select_epsilon_greedy(q, np.ones((B, n, m), bool), float(g["eps"]), g["u_explore"][t], g["u_action"][t])
+        last[0] = O.one_hot(a, m, np.float32)
+        return a
+
+    want = O.rollout(st, policy, "real")
+    np.testing.assert_array_equal(want["actions"][:, :T], g["td_actions"][:, :T, :, 0])
+    np.testing.assert_array_equal(want["obs"].astype(np.float16), g["td_obs"])
+    np.testing.assert_array_equal(want["rewards"].astype(np.float16), g["td_rewards"])
+    np.testing.assert_array_equal(want["beta"].astype(np.float16), g["td_beta"])
+    np.testing.assert_array_equal(want["prev_assigns"], g["td_prev_assigns"])
+    np.testing.assert_array_equal(want["filled"], g["td_filled"][..., 0])
+    # the reference ParallelRunner's two quirks (SURVEY.md Q4), as recorded
+    assert not g["td_terminated"][0].any() and g["td_terminated"][1:, :T].all() and not g["td_terminated"][:, T].any()
+    assert g["td_actions"][:, T].any()
+    assert np.mean(want["rewards"].sum((1, 2))) == pytest.approx(float(g["return_mean"]), rel=1e-12)
