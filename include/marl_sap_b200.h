@@ -212,6 +212,12 @@ int sap_onehot(const void* actions, int32_t actions_dtype, void* onehot, int32_t
                void* stream);
 int sap_real_beta_window(const SapEnvDims* dims, const float* planes, const float* task_prios, void* beta,
                          int32_t dtype, void* stream);
+/* sap_real_beta_rows = the same field for a SAMPLED batch: dims->B batch rows, time steps [t0, t0 + t_count), batch row b
+ *   reading plane row plane_rows[b] of `planes` [*, T, n, m] (null: b itself / the shared row).  This is what lets a replay
+ *   buffer that does not store `beta` (components/episode_buffer.py:264-271 returns it as a stored field) hand it out for
+ *   any episode it still holds. */
+int sap_real_beta_rows(const SapEnvDims* dims, const float* planes, const float* task_prios, const int64_t* plane_rows,
+                       int32_t t0, int32_t t_count, void* beta, int32_t dtype, void* stream);
 
 /* ---- assignment selectors -------------------------------------------------
  * sap_lsa_maximize = the per-env body of SequentialAssignmentProblemSelector.select_action

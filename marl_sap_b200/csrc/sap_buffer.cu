@@ -160,18 +160,22 @@ __global__ void __launch_bounds__(kThreads) sap_bias_act_kernel(float* __restric
   }
 }
 
-// beta field [B, T+1, n, m, L] rebuilt from planes [B, T, n, m]
+// beta field [B, t_count, n, m, L] (time steps t0 .. t0 + t_count - 1) rebuilt from planes [*, T, n, m]; batch row b reads
+// plane row rows[b] (rows == null: b itself, or 0 when the planes are shared)
 __global__ void __launch_bounds__(kThreads) sap_beta_window_kernel(SapEnvDims d, const float* __restrict__ planes,
-                                                                   const float* __restrict__ prios, void* beta, int dtype) {
+                                                                   const float* __restrict__ prios,
+                                                                   const int64_t* __restrict__ rows, int t0, int t_count,
+                                                                   void* beta, int dtype) {
   const int64_t nm = (int64_t)d.n * d.m;
-  const int64_t total = (int64_t)d.B * (d.T + 1) * nm;
+  const int64_t total = (int64_t)d.B * t_count * nm;
   for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
     const int64_t bt = e / nm, x = e - bt * nm;
-    const int b = (int)(bt / (d.T + 1)), t = (int)(bt - (int64_t)b * (d.T + 1));
+    const int b = (int)(bt / t_count), t = t0 + (int)(bt - (int64_t)b * t_count);
     const int j = (int)(x % d.m);
     const double pr = prios ? (double)prios[j] : 1.0;
+    const int64_t prow = rows ? rows[b] : (d.shared_planes ? 0 : b);
     for (int l = 0; l < d.L; ++l) {
-      const double v = (t + l < d.T) ? (double)planes[((int64_t)(d.shared_planes ? 0 : b) * d.T + t + l) * nm + x] * pr : 0.0;
+      const double v = (t + l < d.T) ? (double)planes[(prow * d.T + t + l) * nm + x] * pr : 0.0;
       sap_store_real(beta, e * d.L + l, dtype, v);
     }
   }
@@ -382,14 +386,23 @@ extern "C" int sap_bias_act(float* x, const float* bias, int64_t rows, int32_t c
   return SAP_OK;
 }
 
-extern "C" int sap_real_beta_window(const SapEnvDims* dims, const float* planes, const float* task_prios, void* beta,
-                                    int32_t dtype, void* stream) {
-  SAP_REQUIRE(dims && planes && beta, SAP_E_NULL, "sap_real_beta_window: null pointer");
-  SAP_REQUIRE(dtype == SAP_F32 || dtype == SAP_F16, SAP_E_DTYPE, "sap_real_beta_window: beta must be f32|f16");
-  SAP_REQUIRE(dims->B > 0 && dims->n > 0 && dims->m > 0 && dims->T > 0 && dims->L > 0, SAP_E_DIMS,
-              "sap_real_beta_window: bad dims");
-  const int64_t total = (int64_t)dims->B * (dims->T + 1) * dims->n * dims->m;
-  sap_beta_window_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(*dims, planes, task_prios, beta, dtype);
+extern "C" int sap_real_beta_rows(const SapEnvDims* dims, const float* planes, const float* task_prios,
+                                  const int64_t* plane_rows, int32_t t0, int32_t t_count, void* beta, int32_t dtype,
+                                  void* stream) {
+  SAP_REQUIRE(dims && planes && beta, SAP_E_NULL, "sap_real_beta_rows: null pointer");
+  SAP_REQUIRE(dtype == SAP_F32 || dtype == SAP_F16, SAP_E_DTYPE, "sap_real_beta_rows: beta must be f32|f16");
+  SAP_REQUIRE(dims->B > 0 && dims->n > 0 && dims->m > 0 && dims->T > 0 && dims->L > 0, SAP_E_DIMS, "sap_real_beta_rows: bad dims");
+  SAP_REQUIRE(t0 >= 0 && t_count > 0 && t0 + t_count <= dims->T + 1, SAP_E_DIMS,
+              "sap_real_beta_rows: time steps [%d, %d) outside [0, T + 1 = %d]", t0, t0 + t_count, dims->T + 1);
+  const int64_t total = (int64_t)dims->B * t_count * dims->n * dims->m;
+  sap_beta_window_kernel<<<grid_for(total), kThreads, 0, (cudaStream_t)stream>>>(*dims, planes, task_prios, plane_rows, t0,
+                                                                                 t_count, beta, dtype);
   SAP_CUDA_LAUNCH_CHECK("sap_beta_window_kernel");
   return SAP_OK;
+}
+
+extern "C" int sap_real_beta_window(const SapEnvDims* dims, const float* planes, const float* task_prios, void* beta,
+                                    int32_t dtype, void* stream) {
+  SAP_REQUIRE(dims, SAP_E_NULL, "sap_real_beta_window: null pointer");
+  return sap_real_beta_rows(dims, planes, task_prios, nullptr, 0, dims->T + 1, beta, dtype, stream);
 }

@@ -74,6 +74,7 @@ class _BatchedEnvBase:
         self.plane_stats = None
         self.shared_planes = False
         self._staging = None
+        self._benefit_source = None  # planes by generation, for replay buffers that rebuild `beta` lazily
         self.t_host = 0  # host mirror of k (all envs step in lockstep)
         self.launches_per_step = 1  # kernels one reset()/step() call enqueues (4 on the multi-CTA path of large shapes)
 
@@ -82,6 +83,24 @@ class _BatchedEnvBase:
         object graph holding one - the reference's learners do ``copy.deepcopy(mac)`` for their target network, and the
         MAC's jump-start selector is bound to the runner's env - get the SAME env back, not a second copy of the planes."""
         return self
+
+    def benefit_source(self):
+        """The ``BenefitSource`` through which episode batches with a lazy ``beta`` find the planes they were rolled out on
+        (components/episode_buffer.py).  Planes a source holds are never overwritten in place: ``load_benefits`` /
+        ``generate_benefits`` then write a fresh tensor, so that stored episodes keep reading the benefits they saw."""
+        if self._benefit_source is None:
+            from ..components.episode_buffer import BenefitSource
+
+            self._benefit_source = BenefitSource(self.kind, self.n, self.m, self.T, self.L)
+        return self._benefit_source
+
+    def register_planes(self):
+        """(source, generation) of the planes the next episode runs on."""
+        src = self.benefit_source()
+        return src, src.register(self.planes, getattr(self, "task_prios", None), self.shared_planes)
+
+    def _planes_held(self):
+        return self._benefit_source is not None and self.planes is not None and self._benefit_source.holds(self.planes)
 
     # ------------------------------------------------------------------ benefits
     def load_benefits(self, sat_prox_mat):
@@ -99,7 +118,7 @@ class _BatchedEnvBase:
             raise ValueError(f"sat_prox_mat must be [n,m,T]=[{self.n},{self.m},{self.T}] or [B,n,m,T] with B={self.B}, "
                              f"got {tuple(S.shape)}")
         S = S.contiguous()
-        if self.planes is None or self.planes.shape[0] != Bp:
+        if self.planes is None or self.planes.shape[0] != Bp or self._planes_held():
             self.planes = th.empty(Bp, self.T, self.n, self.m, dtype=th.float32, device=self.device)
         stream = _lib.stream_ptr(self.device)
         if S.is_cuda:
@@ -246,7 +265,7 @@ class BatchedMockConstellationEnv(_BatchedEnvBase):
 
     def generate_benefits(self, width_min, width_max):
         """``generate_benefits_over_time`` for all B envs at once, straight into the planes (``sap_benefit_generate``)."""
-        if self.planes is None or self.planes.shape[0] != self.B:
+        if self.planes is None or self.planes.shape[0] != self.B or self._planes_held():
             self.planes = th.empty(self.B, self.T, self.n, self.m, dtype=th.float32, device=self.device)
             self.shared_planes = False
         _lib.check(self.lib.sap_benefit_generate(self.planes.data_ptr(), self.B, self.n, self.m, self.T, float(width_min),

@@ -221,13 +221,14 @@ class CudaVecRunner:
         else:
             self.batch = self.new_batch()
             self._batch = self.batch
-        if "beta" in self.lazy and self.env.kind == "real":
-            dtype = self.batch.scheme["beta"]["dtype"]
-            self.batch.set_lazy_provider("beta", lambda _b, env=self.env, dtype=dtype: env.beta_field(dtype))
         if self.env.kind == "real":
             self.batch.top_agent_tasks = self.env.top
         self.batch.agent_in = getattr(self, "agent_in", None)
         self.env.reset(self.batch, **reset_kwargs)
+        if "beta" in self.lazy:
+            # a lazily rebuilt `beta`: the batch rows remember which planes (row, generation) they were rolled out on
+            source, generation = self.env.register_planes()
+            self.batch.bind_benefit_source(source, generation)
         self.batch.agent_in_t = 0
         self.kernel_launches += self.env.launches_per_step
         self.t = 0

@@ -597,3 +597,76 @@ def test_parallel_runner_matches_reference_parallel_runner_golden(compat):
         assert th.equal(td["terminated"], want)
     assert runner.t_env == int(g["t_env_after"])
     assert logger.stats["return_mean"][-1][1] == pytest.approx(float(g["return_mean"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("env_name", ["real_constellation_env", "mock_constellation_env"])
+def test_lazy_replay_buffer_rebuilds_beta_for_every_stored_episode(env_name):
+    """A ReplayBuffer that does not store `beta` (lazy) still returns the right `beta` for every episode it holds - from
+    `buffer["beta"]`, from `sample` / `gather` and from time slices - also after the env's benefits were replaced between
+    episodes, and it drops the planes of a generation once the ring has overwritten every episode that used them."""
+    from marl_sap_b200.components.episode_buffer import ReplayBuffer
+
+    rng = np.random.default_rng(31)
+    B, n, m, T, L, M, N = 3, 12, 16, 6, 3, 4, 3
+    real = env_name == "real_constellation_env"
+    S = [O.gen_dense(rng, B, n, m, T) for _ in range(3)]
+    if real:
+        env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=0.5, sat_prox_mat=S[0], graphs=1)
+    else:
+        env_args = dict(n=n, m=m, T=T, L=L, lambda_=0.5, sat_prox_mat=S[0])
+    lazy = ("beta", "avail_actions", "actions_onehot")
+    args = make_args(env_name, env_args, B, lazy_buffer_fields=lazy)
+    runner, mac, _, _ = build(args)
+    env = runner.get_env()
+    buf = ReplayBuffer(env.scheme, {"agents": n}, 2 * B, T + 1, preprocess=env.preprocess, device="cuda", lazy=lazy)
+    assert "beta" not in buf.data.transition_data
+    runner.attach_replay(buf)
+    dt = th.float16 if real else th.float32
+
+    def want_beta(Sx):
+        st = O.RealState(Sx.astype(np.float64), L, M, N, 0.5) if real else O.MockState(Sx.astype(np.float64), L, 0.5)
+        acts = rng.integers(0, m, size=(T, B, n))
+        kw = {} if real else {"prev0": np.stack([rng.permutation(m)[:n] for _ in range(B)])}
+        return th.tensor(O.rollout(st, lambda t, pre: acts[t], "real" if real else "mock", **kw)["beta"], dtype=dt)
+
+    wants = [want_beta(s) for s in S]
+    kw = {} if real else {"prev0": np.stack([rng.permutation(m)[:n] for _ in range(B)])}
+    with th.no_grad():
+        buf.insert_episode_batch(runner.run(test_mode=False, **kw))
+        runner.env.load_benefits(S[1])                      # the env's benefits change between the episodes
+        ep2 = runner.run(test_mode=False, **kw)
+        assert th.equal(ep2["beta"].cpu(), wants[1])        # the runner's own batch
+        buf.insert_episode_batch(ep2)
+    both = th.cat([wants[0], wants[1]])
+    assert th.equal(buf["beta"].cpu(), both)
+    assert th.equal(buf.sample(2 * B)["beta"].cpu(), both)
+    ids = [4, 1, 3]
+    picked = buf.gather(ids)
+    assert th.equal(picked["beta"].cpu(), both[ids])
+    assert th.equal(picked[:, 2:5]["beta"].cpu(), both[ids][:, 2:5])
+    assert th.equal(buf[1:5, 1:]["beta"].cpu(), both[1:5, 1:])
+    assert bool(picked["avail_actions"].all()) and picked["actions_onehot"].shape == (3, T + 1, n, m)
+    src = buf.benefit_source
+    assert len(src.generations) == 2
+    with th.no_grad():
+        runner.env.load_benefits(S[2])
+        buf.insert_episode_batch(runner.run(test_mode=False, **kw))   # wraps: overwrites the rows of the first episode
+    assert th.equal(buf["beta"].cpu(), th.cat([wants[2], wants[1]]))
+    assert len(src.generations) == 2 and 0 not in src.generations   # generation 0 is no longer referenced: dropped
+
+
+def test_replay_insert_of_a_stale_ring_view_does_not_alias():
+    """insert_episode_batch of a view_next() batch taken BEFORE the ring moved on: source and destination rows alias the
+    same storage, so the insert goes through a private copy instead of an overlapping row copy."""
+    from marl_sap_b200.components.episode_buffer import ReplayBuffer
+
+    scheme = {"obs": {"vshape": 5, "group": "agents", "dtype": th.float32}, "rewards": {"vshape": (1,), "dtype": th.float32}}
+    buf = ReplayBuffer(scheme, {"agents": 2}, 6, 4, device="cuda")
+    v = buf.view_next(3)                      # rows 0..2
+    v.data.transition_data["obs"].copy_(th.arange(3 * 4 * 2 * 5, dtype=th.float32, device="cuda").view(3, 4, 2, 5))
+    other = ReplayBuffer(scheme, {"agents": 2}, 2, 4, device="cuda")
+    buf.insert_episode_batch(other[0:2])      # the ring moves on by two rows (host path: views)
+    assert buf.buffer_index == 2
+    keep = v["obs"].clone()
+    buf.insert_episode_batch(v)               # stale view: lands in rows 2..4, overlapping its own storage (rows 0..2)
+    assert th.equal(buf["obs"][2:5], keep) and buf.buffer_index == 5
