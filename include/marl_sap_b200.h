@@ -156,6 +156,37 @@ enum {
 };
 int32_t sap_real_select_kernel(int32_t which);
 
+/* ---- RealPowerConstellationEnv / InterferenceConstellationEnv --------------------
+ * The real env plus a float64 power state per agent (envs/real_power_constellation_env.py:135-183, :243-250, :310-355;
+ * envs/interference_constellation_env.py:309-353).  One env step is
+ *     [sap_interference_rewards]  ->  sap_power_pre  ->  sap_real_step_ex  ->  sap_power_post
+ * sap_real_reset_ex / sap_real_step_ex = sap_real_reset / sap_real_step on the generic one-CTA-per-env kernel with
+ *   prev0[B,n]   (reset) the caller's draw for `np.random.choice(m, n, replace=False)` (:130),
+ *   dead[B,n]    (step) agents whose reward is forced to 0 (out of power: :157-165 and the zeroed beta_hat of :351-355),
+ *   nbr_out[B,n,N] the rival indices of the new observation (the power columns are taken at these agents),
+ *   obs_row      elements between consecutive agents' observation rows (base size + N + 1 for these envs).
+ * sap_power_pre  = dead mask from the old power, then the power update of :172-180 (float64: 1 - 5 * 0.2 = 5.55e-17 is
+ *   `> 0` for the reward branch but `< 1e-12` for beta_hat).  Must run before the env kernel (old k, old window).
+ * sap_power_post = the N + 1 power columns of every new observation row (:243-247), the `power_states` buffer field and
+ *   the same columns of the agent-input rows; rows of finished envs stay zero.
+ * sap_interference_rewards = interference_reward_function (:309-353): rewards of the step into `rewards` (slot k[b]) and
+ *   their sum into ep_return; the env kernel is then called with view.rewards unset and a scratch ep_return. */
+int sap_real_reset_ex(const SapEnvDims* dims, const float* planes, const float* plane_stats, const float* task_prios,
+                      int32_t* k, int32_t* prev, double* ep_return, const SapBatchView* view, int32_t* top_out,
+                      const int64_t* prev0, int32_t* nbr_out, int32_t obs_row, void* stream);
+int sap_real_step_ex(const SapEnvDims* dims, const float* planes, const float* plane_stats, const float* task_prios,
+                     const float* T_trans, double lambda_, const int64_t* actions, int32_t* k, int32_t* prev,
+                     double* ep_return, int32_t* counts_out, const SapBatchView* view, int32_t* top_out,
+                     const uint8_t* dead, int32_t* nbr_out, int32_t obs_row, void* stream);
+int sap_power_pre(const SapEnvDims* dims, const float* planes, const float* task_prios, const int64_t* actions,
+                  const int32_t* k, double* power, uint8_t* dead_out, void* stream);
+int sap_power_post(const SapEnvDims* dims, const int32_t* k, const double* power, const int32_t* nbr,
+                   const SapBatchView* view, const SapField* power_states, int32_t base_cols, int32_t obs_row, void* stream);
+int sap_interference_rewards(const SapEnvDims* dims, const float* planes, const float* task_prios,
+                             const float* neighbor_matrix, const int32_t* sat_freq_bands, int32_t bands_per_env,
+                             double lambda_, const int64_t* actions, const int32_t* k, const int32_t* prev,
+                             const double* power, double* ep_return, const SapField* rewards, void* stream);
+
 /* ---- MockConstellationEnv ---------------------------------------------------------------
  * sap_mock_reset = MockConstellationEnv.reset (mock_constellation_env.py:94-114); prev0[B,n]
  *                  replaces the np.random.choice draw at :105 (injected).

@@ -57,6 +57,11 @@ SIGNATURES = {
     "sap_real_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_step": (C.c_int, [_DIMS, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_scratch_doubles": (C.c_int64, [_DIMS]),
+    "sap_real_reset_ex": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P, _I32, _P]),
+    "sap_real_step_ex": (C.c_int, [_DIMS, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P, _I32, _P]),
+    "sap_power_pre": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _P]),
+    "sap_power_post": (C.c_int, [_DIMS, _P, _P, _P, _VIEW, C.POINTER(SapField), _I32, _I32, _P]),
+    "sap_interference_rewards": (C.c_int, [_DIMS, _P, _P, _P, _P, _I32, _F64, _P, _P, _P, _P, _P, C.POINTER(SapField), _P]),
     "sap_mock_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _VIEW, _P]),
     "sap_mock_step": (C.c_int, [_DIMS, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P]),
     "sap_select_epsilon_greedy": (C.c_int, [_P, _P, _I32, _I32, _I32, _F32, _P, _U64, _P, _P, _P, _P, _P, _P]),

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
   const int n = d.n, m = d.m, T = d.T, L = d.L, M = d.M, N = d.N, H = d.M / 2, K2 = d.M + d.M / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int obs_size = M * L + N * M * L + N * H * L + M;
+  const int obs_row = p.obs_row > 0 ? p.obs_row : obs_size;  // power envs append N + 1 columns to every row
   Smem s;
   smem_layout(d, p.ms, true, &s, smem_raw);
   double* tot = s.tot;
@@ -106,7 +107,8 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
       const double pen = p.ttrans ? (double)p.ttrans[(size_t)pv * m + a] : (a != pv ? 1.0 : 0.0);  // :304-314
       const double meaningful = sum > 1e-12 ? 1.0 : 0.0;                                           // :317
       const double bh = b0 - p.lambda_ * (pen * meaningful);                                      // :320-324
-      const double r = bh > 0.0 ? bh / (double)s.cnt[a] : bh;                                      // :154-160
+      double r = bh > 0.0 ? bh / (double)s.cnt[a] : bh;                                            // :154-160
+      if (p.dead && p.dead[(size_t)b * n + i]) r = 0.0;  // real_power_constellation_env.py:157-165, :351-355
       local_ret += r;
       if (vw.rewards.ptr) sap_store_real(vw.rewards.ptr, sap_field_off(vw.rewards, b, k_old) + i, vw.rewards.dtype, r);
       if (vw.actions.ptr) sap_store_int(vw.actions.ptr, sap_field_off(vw.actions, b, k_old) + i, vw.actions.dtype, a);
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
         sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, k_new >= T);  // :164
     }
   } else {
-    for (int i = tid; i < n; i += kThreads) p.prev[(size_t)b * n + i] = i;  // :129
+    for (int i = tid; i < n; i += kThreads)   // :129 (power envs: a random permutation drawn by the caller)
+      p.prev[(size_t)b * n + i] = p.prev0 ? (int)p.prev0[(size_t)b * n + i] : i;
     if (tid == 0) {
       p.k[b] = 0;
       p.ep_return[b] = 0.0;
@@ -163,10 +166,10 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
   float* ain = vw.agent_in.ptr ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
   const int64_t ain_row = vw.agent_in.t_stride;
   if (done) {  // :226-228  beta := 0, obs := 0
-    for (int e = tid; e < n * obs_size; e += kThreads) sap_store_real(vw.obs.ptr, obs_base + e, vw.obs.dtype, 0.0);
+    for (int e = tid; e < n * obs_row; e += kThreads) sap_store_real(vw.obs.ptr, obs_base + e, vw.obs.dtype, 0.0);
     if (ain)
       for (int i = warp; i < n; i += kWarps)
-        for (int c = lane; c < obs_size; c += 32) ain[i * ain_row + c] = 0.f;
+        for (int c = lane; c < obs_row; c += 32) ain[i * ain_row + c] = 0.f;
     if (vw.beta.ptr) {
       const int64_t bb = sap_field_off(vw.beta, b, t_slot);
       for (int e = tid; e < n * m * L; e += kThreads) sap_store_real(vw.beta.ptr, bb + e, vw.beta.dtype, 0.0);
@@ -239,7 +242,9 @@ __global__ void __launch_bounds__(kThreads) sap_real_kernel(RealParams p) {
   // ------------------------------------------------------------------ gather + write obs (:199-225)
   const int npairs = M + N * M + N * H;
   for (int i = warp; i < n; i += kWarps) {
-    const int64_t out = obs_base + (int64_t)i * obs_size;
+    const int64_t out = obs_base + (int64_t)i * obs_row;
+    if (p.nbr_out)
+      for (int q = lane; q < N; q += 32) p.nbr_out[((size_t)b * n + i) * N + q] = s.nbr[i * N + q];
     for (int pp = lane; pp < npairs; pp += 32) {
       int a, j;
       if (pp < M) {
@@ -307,13 +312,20 @@ int launch(RealParams& p, void* stream) {
 #else
   p.debug_skip_redo = 0;
 #endif
-  if (path != SAP_REAL_PATH_AUTO && path != SAP_REAL_PATH_FAST_GEN1)  // every other kernel widens into an fp32 agent_in
+  const bool extras = p.dead || p.nbr_out || p.prev0 || p.obs_row > 0;  // power / interference envs: generic kernel only
+  if (extras) {
+    p.ms = (d.m & 1) ? d.m : d.m + 1;
+    SAP_REQUIRE(smem_layout(d, p.ms, true, nullptr, nullptr) <= kMaxSmem, SAP_E_CONSTRAINT,
+                "sap_real: the power / interference envs run on the one-CTA-per-env generic kernel, which needs the window "
+                "sums of an env in shared memory (n=%d m=%d does not fit)", d.n, d.m);
+  }
+  if (!extras && path != SAP_REAL_PATH_AUTO && path != SAP_REAL_PATH_FAST_GEN1)  // every other kernel widens into an fp32 agent_in
     SAP_REQUIRE(!p.view.agent_in.ptr || p.view.agent_in.dtype == SAP_F32, SAP_E_DTYPE, "sap_real: agent_in must be f32");
-  if (path == SAP_REAL_PATH_LARGE_KEYED || path == SAP_REAL_PATH_LARGE_EXACT) {
+  if (!extras && (path == SAP_REAL_PATH_LARGE_KEYED || path == SAP_REAL_PATH_LARGE_EXACT)) {
     p.large_exact = path == SAP_REAL_PATH_LARGE_EXACT;
     return sap_real_large_launch(p, stream);
   }
-  if (path != SAP_REAL_PATH_GENERIC) {
+  if (!extras && path != SAP_REAL_PATH_GENERIC) {
     int handled = 0;
     const int rc = sap_real_fast_try(p, stream, &handled, path == SAP_REAL_PATH_FAST_GEN1);
     if (rc != SAP_OK || handled) return rc;
@@ -322,7 +334,7 @@ int launch(RealParams& p, void* stream) {
   p.ms = (d.m & 1) ? d.m : d.m + 1;
   size_t with_tot = smem_layout(d, p.ms, true, nullptr, nullptr);
   p.tot_in_smem = with_tot <= kMaxSmem;
-  if (!p.tot_in_smem) return sap_real_large_launch(p, stream);  // one env over many CTAs (sap_real_large.cu)
+  if (!p.tot_in_smem && !extras) return sap_real_large_launch(p, stream);  // one env over many CTAs (sap_real_large.cu)
   const size_t bytes = with_tot;
   static thread_local size_t configured = 0;
   if (bytes > configured) {
@@ -372,6 +384,63 @@ extern "C" int sap_real_reset(const SapEnvDims* dims, const float* planes, const
   p.top_out = top_out;
   p.scratch = scratch;
   p.is_reset = 1;
+  return launch(p, stream);
+}
+
+extern "C" int sap_real_reset_ex(const SapEnvDims* dims, const float* planes, const float* plane_stats,
+                                 const float* task_prios, int32_t* k, int32_t* prev, double* ep_return,
+                                 const SapBatchView* view, int32_t* top_out, const int64_t* prev0, int32_t* nbr_out,
+                                 int32_t obs_row, void* stream) {
+  int rc = validate(dims, view);
+  if (rc) return rc;
+  SAP_REQUIRE(planes && k && prev && ep_return, SAP_E_NULL, "sap_real_reset_ex: planes/k/prev/ep_return is null");
+  SAP_REQUIRE(obs_row >= 0, SAP_E_DIMS, "sap_real_reset_ex: negative obs_row");
+  RealParams p{};
+  p.d = *dims;
+  p.planes = planes;
+  p.plane_stats = plane_stats;
+  p.prios = task_prios;
+  p.k = k;
+  p.prev = prev;
+  p.ep_return = ep_return;
+  p.view = *view;
+  p.top_out = top_out;
+  p.prev0 = prev0;
+  p.nbr_out = nbr_out;
+  // a positive obs_row marks the call as one of the power-type envs: always the generic kernel (launch())
+  p.obs_row = obs_row > 0 ? obs_row : dims->M * dims->L + dims->N * dims->M * dims->L + dims->N * (dims->M / 2) * dims->L + dims->M;
+  p.is_reset = 1;
+  return launch(p, stream);
+}
+
+extern "C" int sap_real_step_ex(const SapEnvDims* dims, const float* planes, const float* plane_stats,
+                                const float* task_prios, const float* T_trans, double lambda_, const int64_t* actions,
+                                int32_t* k, int32_t* prev, double* ep_return, int32_t* counts_out,
+                                const SapBatchView* view, int32_t* top_out, const uint8_t* dead, int32_t* nbr_out,
+                                int32_t obs_row, void* stream) {
+  int rc = validate(dims, view);
+  if (rc) return rc;
+  SAP_REQUIRE(planes && k && prev && ep_return && actions, SAP_E_NULL,
+              "sap_real_step_ex: planes/k/prev/ep_return/actions is null");
+  SAP_REQUIRE(obs_row >= 0, SAP_E_DIMS, "sap_real_step_ex: negative obs_row");
+  RealParams p{};
+  p.d = *dims;
+  p.planes = planes;
+  p.plane_stats = plane_stats;
+  p.prios = task_prios;
+  p.ttrans = T_trans;
+  p.lambda_ = lambda_;
+  p.actions = actions;
+  p.k = k;
+  p.prev = prev;
+  p.ep_return = ep_return;
+  p.counts_out = counts_out;
+  p.view = *view;
+  p.top_out = top_out;
+  p.dead = dead;
+  p.nbr_out = nbr_out;
+  p.obs_row = obs_row > 0 ? obs_row : dims->M * dims->L + dims->N * dims->M * dims->L + dims->N * (dims->M / 2) * dims->L + dims->M;
+  p.is_reset = 0;
   return launch(p, stream);
 }
 

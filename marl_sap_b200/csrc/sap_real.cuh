@@ -22,6 +22,11 @@ struct RealParams {
   int tot_in_smem;
   int ms;  // row stride of tot (odd -> conflict-free column walks)
   int lookahead;  // sap_real_fast2: blocks of L2 look-ahead for the benefit window (0 = off)
+  // power / interference envs (generic kernel only)
+  const uint8_t* dead;    // [B,n] agents whose reward is 0 this step (out of power), or null
+  int32_t* nbr_out;       // [B,n,N] rival indices of the new observation, or null
+  const int64_t* prev0;   // reset only: [B,n] initial prev_assigns instead of arange(n), or null
+  int obs_row;            // elements between consecutive agents' observation rows (0 = obs_size: packed)
   int large_exact;  // multi-CTA path: exact float64 selection even where the keyed lists would apply (selector override)
 };
 

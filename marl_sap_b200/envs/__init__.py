@@ -5,8 +5,9 @@ kernels.  ``BATCHED[name]`` is the batched device env the runners use for thousa
 """
 from functools import partial
 
-from .batched import BatchedMockConstellationEnv, BatchedRealConstellationEnv
-from .single import MockConstellationEnv, RealConstellationEnv
+from .batched import (BatchedInterferenceConstellationEnv, BatchedMockConstellationEnv, BatchedRealConstellationEnv,
+                      BatchedRealPowerConstellationEnv)
+from .single import InterferenceConstellationEnv, MockConstellationEnv, RealConstellationEnv, RealPowerConstellationEnv
 
 
 def env_fn(env, **kwargs):
@@ -23,8 +24,8 @@ REGISTRY = {}
 REGISTRY["mock_constellation_env"] = partial(env_fn, env=MockConstellationEnv)
 REGISTRY["real_constellation_env"] = partial(env_fn, env=RealConstellationEnv)
 # keys the reference registers that are outside SURVEY.md section 8 (a)-(e)
-REGISTRY["real_power_constellation_env"] = _not_on_path("real_power_constellation_env", "next row 2 (fp64 power state)")
-REGISTRY["interference_constellation_env"] = _not_on_path("interference_constellation_env", "next row 2 (needs h3 hex grid)")
+REGISTRY["real_power_constellation_env"] = partial(env_fn, env=RealPowerConstellationEnv)
+REGISTRY["interference_constellation_env"] = partial(env_fn, env=InterferenceConstellationEnv)
 REGISTRY["dictator_env"] = _not_on_path("dictator_env", "3x3 toy env")
 REGISTRY["benefit_obs_env"] = _not_on_path("benefit_obs_env", "stale in the reference (no scheme)")
 REGISTRY["power_constellation_env"] = _not_on_path("power_constellation_env", "stale in the reference (no scheme)")
@@ -32,4 +33,6 @@ REGISTRY["power_constellation_env"] = _not_on_path("power_constellation_env", "s
 BATCHED = {
     "mock_constellation_env": BatchedMockConstellationEnv,
     "real_constellation_env": BatchedRealConstellationEnv,
+    "real_power_constellation_env": BatchedRealPowerConstellationEnv,
+    "interference_constellation_env": BatchedInterferenceConstellationEnv,
 }

@@ -247,6 +247,120 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
         return out
 
 
+def power_scheme(n, m, L, obs_size):
+    """real_power_constellation_env.py:95-116 / interference_constellation_env.py:70-98: the real scheme + power_states."""
+    scheme, preprocess = real_scheme(n, m, L, obs_size)
+    scheme["power_states"] = {"vshape": (n,), "dtype": th.float16, "part_of_state": True}
+    return scheme, preprocess
+
+
+class BatchedRealPowerConstellationEnv(BatchedRealConstellationEnv):
+    """B RealPowerConstellationEnv instances (/root/reference/src/envs/real_power_constellation_env.py:17-358).
+
+    One step = ``sap_power_pre`` (who is out of power, then the float64 power update) -> ``sap_real_step_ex`` (the real
+    env's step + observation kernel with a zero reward for dead agents, the rival indices exported and N + 1 free columns
+    behind every observation row) -> ``sap_power_post`` (power columns, ``power_states`` field).  ``reset`` takes the
+    ``prev_assigns`` draw (``np.random.choice(m, n, replace=False)``, :130) as ``prev0`` like the mock env."""
+
+    kind = "real"
+
+    def __init__(self, B, n, m, T, L, M, N, lambda_, sat_prox_mat=None, task_prios=None, T_trans=None, device=None, T_ctor=None):
+        super().__init__(B, n, m, T, L, M, N, lambda_, sat_prox_mat=sat_prox_mat, task_prios=task_prios, T_trans=T_trans,
+                         device=device, T_ctor=T_ctor)
+        if self.scratch is not None:
+            raise NotImplementedError(f"power / interference envs run on the one-CTA-per-env kernel: n={n}, m={m} does not fit "
+                                      "one SM's shared memory (the multi-CTA path has no power columns yet)")
+        self.base_obs_size = self.obs_size
+        self.obs_size = self.base_obs_size + N + 1                      # :291-293
+        self.scheme, self.preprocess = power_scheme(n, m, self.L, self.obs_size)
+        self.power = th.ones(B, n, dtype=th.float64, device=self.device)
+        self.dead = th.zeros(B, n, dtype=th.uint8, device=self.device)
+        self.nbr = th.zeros(B, n, N, dtype=th.int32, device=self.device)
+        self.launches_per_step = 3
+
+    def draw_prev_assigns(self):
+        if self.m < self.n:
+            raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+        return np.stack([np.random.choice(self.m, self.n, replace=False) for _ in range(self.B)]).astype(np.int64)
+
+    def _post(self, batch, view):
+        pf = _lib.field_of(batch.data.transition_data["power_states"]) if "power_states" in batch.data.transition_data \
+            else _lib.SapField()
+        _lib.check(self.lib.sap_power_post(self.dims(), _lib.ptr(self.k), _lib.ptr(self.power), _lib.ptr(self.nbr), view, pf,
+                                           self.base_obs_size, self.obs_size, _lib.stream_ptr(self.device)), "sap_power_post")
+
+    def reset(self, batch, prev0=None):
+        self._check_batch(batch)
+        if prev0 is None:
+            prev0 = self.draw_prev_assigns()
+        prev0 = th.as_tensor(np.asarray(prev0), dtype=th.int64).reshape(self.B, self.n).contiguous().to(self.device)
+        self.power.fill_(1.0)                                            # :131
+        view = batch.kernel_view()
+        _lib.check(self.lib.sap_real_reset_ex(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
+                                              _lib.ptr(self.task_prios), _lib.ptr(self.k), _lib.ptr(self.prev),
+                                              _lib.ptr(self.ep_return), view, _lib.ptr(self.top), prev0.data_ptr(),
+                                              _lib.ptr(self.nbr), self.obs_size, _lib.stream_ptr(self.device)),
+                   "sap_real_reset_ex")
+        self._post(batch, view)
+        self.t_host = 0
+
+    def _rewards_before_step(self, actions, view, batch):
+        """Power env: the env kernel computes the rewards itself, with the dead mask."""
+        return self.dead, self.ep_return
+
+    def step(self, actions, batch):
+        view = batch.kernel_view()
+        actions = self._actions_for_step(actions, view, batch)
+        stream = _lib.stream_ptr(self.device)
+        dead, ep_return = self._rewards_before_step(actions, view, batch)
+        _lib.check(self.lib.sap_power_pre(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios), actions.data_ptr(),
+                                          _lib.ptr(self.k), _lib.ptr(self.power), _lib.ptr(self.dead), stream), "sap_power_pre")
+        _lib.check(self.lib.sap_real_step_ex(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
+                                             _lib.ptr(self.task_prios), _lib.ptr(self.T_trans), self.lambda_,
+                                             actions.data_ptr(), _lib.ptr(self.k), _lib.ptr(self.prev), _lib.ptr(ep_return),
+                                             _lib.ptr(self.counts), view, _lib.ptr(self.top), _lib.ptr(dead),
+                                             _lib.ptr(self.nbr), self.obs_size, stream), "sap_real_step_ex")
+        self._post(batch, view)
+        self.t_host += 1
+        return self.t_host >= self.T
+
+
+class BatchedInterferenceConstellationEnv(BatchedRealPowerConstellationEnv):
+    """B InterferenceConstellationEnv instances (/root/reference/src/envs/interference_constellation_env.py:17-406): the
+    power env whose reward is ``interference_reward_function`` (:309-353, ``sap_interference_rewards``).  The reference builds
+    its proximity tensor and region neighbour matrix from the orbit simulator (out of scope); here they are arguments."""
+
+    def __init__(self, B, n, m, T, L, M, N, lambda_, sat_prox_mat, neighbor_matrix, sat_freq_bands, task_prios=None,
+                 device=None, T_ctor=None):
+        super().__init__(B, n, m, T, L, M, N, lambda_, sat_prox_mat=sat_prox_mat, task_prios=task_prios, device=device,
+                         T_ctor=T_ctor)
+        nb = th.as_tensor(np.asarray(neighbor_matrix), dtype=th.float32)
+        if tuple(nb.shape) != (m, m):
+            raise ValueError(f"neighbor_matrix must be [m, m] = [{m}, {m}], got {tuple(nb.shape)}")
+        self.neighbor = nb.contiguous().to(self.device)
+        bands = th.as_tensor(np.asarray(sat_freq_bands), dtype=th.int32)
+        if tuple(bands.shape) not in ((n,), (B, n)):
+            raise ValueError(f"sat_freq_bands must be [n] or [B, n], got {tuple(bands.shape)}")
+        self.bands_per_env = bands.dim() == 2
+        self.bands = bands.contiguous().to(self.device)
+        self._scratch_return = th.zeros(B, dtype=th.float64, device=self.device)
+        self.launches_per_step = 4
+
+    def _rewards_before_step(self, actions, view, batch):
+        rf = view.rewards
+        _lib.check(self.lib.sap_interference_rewards(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios),
+                                                     _lib.ptr(self.neighbor), _lib.ptr(self.bands), int(self.bands_per_env),
+                                                     self.lambda_, actions.data_ptr(), _lib.ptr(self.k), _lib.ptr(self.prev),
+                                                     _lib.ptr(self.power), _lib.ptr(self.ep_return), rf,
+                                                     _lib.stream_ptr(self.device)), "sap_interference_rewards")
+        view.rewards = _lib.SapField()   # the env kernel must not overwrite them; its own return goes to a scratch buffer
+        return None, self._scratch_return
+
+    def reset(self, batch, prev0=None):
+        super().reset(batch, prev0)
+        self.ep_return.zero_()
+
+
 class BatchedMockConstellationEnv(_BatchedEnvBase):
     kind = "mock"
 

@@ -17,8 +17,8 @@ import numpy as np
 import torch as th
 
 from ..components.episode_buffer import EpisodeBatch
-from .batched import (BatchedMockConstellationEnv, BatchedRealConstellationEnv, mock_scheme, real_obs_size,
-                      real_scheme)
+from .batched import (BatchedInterferenceConstellationEnv, BatchedMockConstellationEnv, BatchedRealConstellationEnv,
+                      BatchedRealPowerConstellationEnv, mock_scheme, power_scheme, real_obs_size, real_scheme)
 
 
 def generate_benefits_over_time(n, m, T, width_min, width_max, scale_min=0.25, scale_max=2):
@@ -189,6 +189,93 @@ class RealConstellationEnv(_SingleEnvBase):
         out = beta.astype(np.float64, copy=True)
         out[..., 0] = out[..., 0] - self.lambda_ * (pen * (beta.sum(-1) > 1e-12))
         return out[0] if squeeze else out
+
+
+class RealPowerConstellationEnv(RealConstellationEnv):
+    """/root/reference/src/envs/real_power_constellation_env.py:17-358 behind the same facade: per-agent power states
+    (float64 on the device), N + 1 power columns per observation, ``power_states`` in the pre-transition data."""
+
+    def __init__(self, num_planes, num_sats_per_plane, m, T, N, M, L, lambda_, sat_prox_mat=None, graphs=None,
+                 bids_as_actions=False, seed=None, T_trans=None, task_prios=None, device=None):
+        if bids_as_actions:
+            raise NotImplementedError("bids_as_actions is built for the real and mock envs only")
+        super().__init__(num_planes, num_sats_per_plane, m, T, N, M, L, lambda_, sat_prox_mat=sat_prox_mat, graphs=graphs,
+                         seed=seed, T_trans=T_trans, task_prios=task_prios, device=device)
+        if task_prios is None:   # :70: a quarter of the tasks are high priority, drawn with the global numpy RNG
+            self.task_prios_arg = np.random.choice([1, 1, 1, 5], size=self.m, replace=True).astype(np.float64)
+        self.power_states = np.ones(self.n)
+        self.obs_space_size = real_obs_size(self.M, self.N, self.L) + self.N + 1
+        self.scheme, self.preprocess = power_scheme(self.n, self.m, self.L, self.obs_space_size)
+
+    def _make_impl(self):
+        return BatchedRealPowerConstellationEnv(1, self.n, self.m, self.T, self.L, self.M, self.N, self.lambda_,
+                                                sat_prox_mat=self.sat_prox_mat, task_prios=self.task_prios_arg,
+                                                T_trans=self.T_trans, device=self._device)
+
+    def reset(self):
+        impl, batch = self._device_state()
+        self.prev_assigns = np.random.choice(self.m, self.n, replace=False)   # :130
+        impl.reset(batch, prev0=self.prev_assigns[None])
+        self.k, self.done = 0, False
+        self._refresh(batch)
+        return self.get_obs()
+
+    def _refresh(self, batch):
+        super()._refresh(batch)
+        self.power_states = self._impl.power[0].cpu().numpy().copy()
+
+    def get_pretransition_data(self):
+        out = super().get_pretransition_data()
+        out["power_states"] = [self.power_states]                              # :268
+        return out
+
+    def beta_hat(self, beta, prev_assigns, power_states):
+        """:310-355: the real env's beta_hat, zeroed for agents whose power is below 1e-12."""
+        out = super().beta_hat(beta, prev_assigns)
+        pw = power_states.cpu().numpy() if isinstance(power_states, th.Tensor) else np.asarray(power_states)
+        squeeze = out.ndim == 3
+        if squeeze:
+            out = out[None]
+        pw = pw.reshape(out.shape[0], self.n)
+        out = np.where((pw < 1e-12)[:, :, None, None], 0.0, out)
+        return out[0] if squeeze else out
+
+
+class InterferenceConstellationEnv(RealPowerConstellationEnv):
+    """/root/reference/src/envs/interference_constellation_env.py:17-406.  The reference derives its proximity tensor and
+    the region neighbour matrix from the orbit simulator (poliastro / h3: out of scope); this facade takes them as
+    ``sat_prox_mat`` and ``neighbor_matrix`` and keeps the rest of the constructor (``res`` is accepted and ignored)."""
+
+    def __init__(self, num_planes, num_sats_per_plane, res, T, N, M, L, lambda_, task_prios=None, sat_freq_bands=None,
+                 bids_as_actions=False, seed=None, sat_prox_mat=None, neighbor_matrix=None, device=None):
+        if sat_prox_mat is None or neighbor_matrix is None:
+            raise NotImplementedError("coverage-task proximities and the region neighbour matrix come from the orbit simulator "
+                                      "(HighPerformanceConstellationSim, out of scope): pass sat_prox_mat=[n,m,T] and "
+                                      "neighbor_matrix=[m,m] (interference_constellation_env.py:54-61)")
+        m = np.asarray(sat_prox_mat).shape[1]
+        self.beam_types = 7
+        self.constant_setup = task_prios is not None and sat_freq_bands is not None                 # :69-76
+        if not self.constant_setup:
+            task_prios = np.random.choice([1, 1, 1, 5], size=m, replace=True)
+            sat_freq_bands = np.random.choice(list(range(self.beam_types)), size=np.asarray(sat_prox_mat).shape[0], replace=True)
+        self.res = res
+        self.neighbor_matrix = np.asarray(neighbor_matrix, dtype=np.float64)
+        self.sat_freq_bands = np.asarray(sat_freq_bands)
+        super().__init__(num_planes, num_sats_per_plane, m, T, N, M, L, lambda_, sat_prox_mat=sat_prox_mat, graphs=[1],
+                         bids_as_actions=bids_as_actions, seed=seed, task_prios=np.asarray(task_prios, dtype=np.float64),
+                         device=device)
+
+    def _make_impl(self):
+        return BatchedInterferenceConstellationEnv(1, self.n, self.m, self.T, self.L, self.M, self.N, self.lambda_,
+                                                   self.sat_prox_mat, self.neighbor_matrix, self.sat_freq_bands,
+                                                   task_prios=self.task_prios_arg, device=self._device)
+
+    def reset(self):
+        if not self.constant_setup:                                            # :132-141: new priorities and bands per episode
+            self.task_prios_arg = np.random.choice([1, 1, 1, 5], size=self.m, replace=True).astype(np.float64)
+            self.sat_freq_bands = np.random.choice(list(range(self.beam_types)), size=self.n, replace=True)
+            self._impl = None
+        return super().reset()
 
 
 class MockConstellationEnv(_SingleEnvBase):

@@ -59,10 +59,19 @@ def build_batched_env(env_name, env_args, B, device):
                                   "the orbit simulator that would produce it is out of scope (DESIGN.md)")
     shape = tuple(S.shape)
     n, m, T = shape[-3:]
-    if env_name == "real_constellation_env":
+    if env_name in ("real_constellation_env", "real_power_constellation_env"):
+        prios = ea.get("task_prios")
+        if prios is None and env_name == "real_power_constellation_env":   # real_power_constellation_env.py:70
+            prios = np.random.choice([1, 1, 1, 5], size=m, replace=True).astype(np.float64)
         env = batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["M"], ea["N"], ea["lambda_"], sat_prox_mat=S,
-                                         task_prios=ea.get("task_prios"), T_trans=ea.get("T_trans"), device=device,
+                                         task_prios=prios, T_trans=ea.get("T_trans"), device=device,
                                          T_ctor=ea.get("T", T))
+    elif env_name == "interference_constellation_env":
+        if ea.get("neighbor_matrix") is None or ea.get("task_prios") is None or ea.get("sat_freq_bands") is None:
+            raise NotImplementedError("the batched interference env needs env_args['neighbor_matrix'], ['task_prios'] and "
+                                      "['sat_freq_bands'] (the reference derives / redraws them per env on the host)")
+        env = batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["M"], ea["N"], ea["lambda_"], S, ea["neighbor_matrix"],
+                                         ea["sat_freq_bands"], task_prios=ea["task_prios"], device=device, T_ctor=ea.get("T", T))
     else:
         env = batched_REGISTRY[env_name](B, n, m, T, ea["L"], ea["lambda_"], sat_prox_mat=S, T_trans=ea.get("T_trans"),
                                          device=device)

@@ -191,6 +191,102 @@ class RealState:
                 "avail_actions": np.ones((self.B, self.n, self.m), dtype=bool)}
 
 
+# ------------------------------------------------------------------ RealPowerConstellationEnv / InterferenceConstellationEnv
+def power_update(power: np.ndarray, beta0_chosen: np.ndarray) -> np.ndarray:
+    """real_power_constellation_env.py:172-180 (interference_constellation_env.py: same block): a live agent (power > 0)
+    spends 0.2 on a task it can see (benefit > 1e-12) and recharges 0.1 (capped at 1) otherwise; a dead agent stays as it
+    is.  float64 throughout: 1 - 5 * 0.2 leaves 5.55e-17, which is > 0 here but < 1e-12 in beta_hat."""
+    alive = power > 0
+    spent = power - 0.2
+    charged = np.minimum(power + 0.1, 1.0)
+    return np.where(alive, np.where(beta0_chosen > 1e-12, spent, charged), power)
+
+
+class PowerState(RealState):
+    """B RealPowerConstellationEnv instances (real_power_constellation_env.py:118-355): the real env plus a float64
+    power state per agent, a zero reward / zero beta_hat for agents out of power, and N + 1 power values appended to every
+    observation row.  ``prev0`` replaces the np.random.choice draw of reset (:130)."""
+
+    def __init__(self, S, L, M, N, lambda_, task_prios=None, T_trans=None, T_ctor=None):
+        super().__init__(S, L, M, N, lambda_, task_prios, T_trans, T_ctor)
+        self.obs_size = real_obs_size(M, N, self.L) + N + 1                     # :291-293
+        self.power = np.ones((self.B, self.n))
+
+    def _obs(self):
+        obs, _, nbrs, _ = real_build_obs(self.beta, self.prev, self.M, self.N, return_indices=True)
+        bi = np.arange(self.B)[:, None, None]
+        tail = np.concatenate([self.power[:, :, None], self.power[bi, nbrs]], axis=-1)   # :243-247
+        return np.concatenate([obs, tail], axis=-1)
+
+    def reset(self, prev0=None):
+        self.k, self.done = 0, False
+        self.beta = real_window(self.S, 0, self.L, self.task_prios)
+        self.prev = (np.broadcast_to(np.arange(self.n), (self.B, self.n)) if prev0 is None else np.asarray(prev0)).copy()
+        self.power = np.ones((self.B, self.n))                                    # :131
+        self.obs = self._obs()
+        return self.obs
+
+    def _rewards(self, a, cnt):
+        bh = real_beta_hat_chosen(self.beta, self.prev, a, self.lambda_, self.T_trans)
+        bh = np.where(self.power < 1e-12, 0.0, bh)                                # :351-355 (beta_hat zeroed)
+        return np.where(self.power > 0, _split_rewards(bh, a, cnt), 0.0)          # :157-165
+
+    def step(self, actions):
+        a = np.asarray(actions, dtype=np.int64)
+        cnt = _counts(a, self.m)                                                  # every agent counts, dead or not (:147-149)
+        rewards = self._rewards(a, cnt)
+        bi = np.arange(self.B)[:, None]
+        beta0 = self.beta[bi, np.arange(self.n)[None, :], a, 0]
+        self.k += 1
+        self.done = self.k >= self.T
+        self.power = power_update(self.power, beta0)                              # :172-180
+        self.prev = a.copy()
+        if self.done:
+            self.beta = np.zeros((self.B, self.n, self.m, self.L))
+            self.obs = np.zeros((self.B, self.n, self.obs_size))
+        else:
+            self.beta = real_window(self.S, self.k, self.L, self.task_prios)
+            self.obs = self._obs()
+        self.last_counts = cnt
+        return rewards, self.done
+
+    def pretransition(self):
+        out = super().pretransition()
+        out["power_states"] = self.power.copy()                                   # :268
+        return out
+
+
+class InterferenceState(PowerState):
+    """B InterferenceConstellationEnv instances: the power env whose reward is interference_reward_function
+    (interference_constellation_env.py:309-353): agents in the same frequency band that serve neighbouring regions halve
+    each other's benefit, only "applicable" agents (alive and on a task they can see) count for splitting, interference and
+    the hand-over penalty."""
+
+    def __init__(self, S, L, M, N, lambda_, neighbor_matrix, sat_freq_bands, task_prios=None):
+        super().__init__(S, L, M, N, lambda_, task_prios)
+        self.neighbor = np.asarray(neighbor_matrix, dtype=np.float64)
+        self.bands = np.asarray(sat_freq_bands, dtype=np.int64)
+        if self.bands.ndim == 1:
+            self.bands = np.broadcast_to(self.bands, (self.B, self.n))
+
+    def _rewards(self, a, cnt_all):
+        B, n = self.B, self.n
+        bi = np.arange(B)[:, None]
+        beta0 = self.beta[bi, np.arange(n)[None, :], a, 0]
+        applicable = ((self.power > 0) & ~(beta0 < 1e-12)).astype(np.float64)      # :314-316
+        cnt = np.zeros((B, self.m))
+        for b in range(B):
+            np.add.at(cnt[b], a[b], applicable[b])                                # :318-321
+        same_band = self.bands[:, :, None] == self.bands[:, None, :]              # [B, i, i']
+        nb = self.neighbor[a[:, :, None], a[:, None, :]]                          # neighbor[a_i, a_i']
+        conflicts = (nb * same_band * applicable[:, None, :]).sum(-1) - 1.0       # :331 (beams do not self-conflict)
+        r = beta0 * 0.5 ** conflicts                                              # :332
+        c = cnt[bi, a]
+        r = np.where(c > 0, r / np.where(c > 0, c, 1.0), r)                      # :344-345
+        r = np.where((applicable > 0) & (self.prev != a), r - self.lambda_, r)    # :348-349
+        return r
+
+
 # ------------------------------------------------------------------ MockConstellationEnv
 def mock_obs(S: np.ndarray, k: int, L: int, curr_assignment: np.ndarray) -> np.ndarray:
     """obs_i = [curr_assignment[i,:] | S[i,:,k] | ... | S[i,:,k+L-1]] zero-padded past T
@@ -396,7 +492,7 @@ def rollout(state, policy, scheme_kind: str, prev0=None):
     (A.5 timeline): obs, beta, prev_assigns (real only), actions, rewards, terminated, filled.
     """
     B, n, m, T = state.B, state.n, state.m, state.T
-    if scheme_kind == "real":
+    if scheme_kind == "real" and prev0 is None:
         state.reset()
     else:
         state.reset(prev0)
@@ -412,12 +508,16 @@ def rollout(state, policy, scheme_kind: str, prev0=None):
     }
     if scheme_kind == "real":
         out["prev_assigns"] = np.zeros((B, T + 1, n), dtype=np.int64)
+    if "power_states" in pre:
+        out["power_states"] = np.zeros((B, T + 1, n))
     t, done = 0, False
     while not done:
         pre = state.pretransition()
         out["obs"][:, t], out["beta"][:, t], out["filled"][:, t] = pre["obs"], pre["beta"], 1
         if scheme_kind == "real":
             out["prev_assigns"][:, t] = pre["prev_assigns"]
+        if "power_states" in pre:
+            out["power_states"][:, t] = pre["power_states"]
         a = np.asarray(policy(t, pre), dtype=np.int64)
         r, done = state.step(a)
         out["actions"][:, t], out["rewards"][:, t], out["terminated"][:, t] = a, r, done
@@ -427,6 +527,8 @@ def rollout(state, policy, scheme_kind: str, prev0=None):
     out["obs"][:, t], out["beta"][:, t], out["filled"][:, t] = pre["obs"], pre["beta"], 1
     if scheme_kind == "real":
         out["prev_assigns"][:, t] = pre["prev_assigns"]
+    if "power_states" in pre:
+        out["power_states"][:, t] = pre["power_states"]
     return out
 
 

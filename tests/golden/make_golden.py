@@ -13,6 +13,7 @@ a CPU-dependent tie order); tie-free cases run it untouched.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import sys
 from types import SimpleNamespace
@@ -491,6 +492,7 @@ def main():
     golden_buffer(R)
     golden_runner(R)
     golden_parallel_runner(R)
+    golden_power_envs(R)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
@@ -570,6 +572,83 @@ def golden_runner(R):
                             t_env_after=runner.t_env, return_mean=log.stats["return_mean"][-1][1], **extra_out, **out)
 
 
+def _drive_power_like(env, T, actions, stable):
+    """reset + T steps of a power-type reference env; returns what the buffer would receive, plus the reset draw."""
+    with (ref_import.stable_argsort() if stable else contextlib.nullcontext()):
+        env.reset()
+        prev0 = np.array(env.prev_assigns).copy()
+        rec = {k: [] for k in ("obs", "beta", "prev", "power", "rewards", "done")}
+
+        def snap():
+            pre = env.get_pretransition_data()
+            rec["obs"].append(np.array(pre["obs"][0], dtype=np.float64))
+            rec["beta"].append(np.array(pre["beta"][0], dtype=np.float64))
+            rec["prev"].append(np.array(pre["prev_assigns"][0]).astype(np.int64))
+            rec["power"].append(np.array(pre["power_states"][0], dtype=np.float64))
+
+        snap()
+        for t in range(T):
+            r, d, _ = env.step(actions[t])
+            rec["rewards"].append(np.array(r, dtype=np.float64))
+            rec["done"].append(bool(d))
+            snap()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["prev0"] = prev0
+    return out
+
+
+def golden_power_envs(R):
+    """RealPowerConstellationEnv (envs/real_power_constellation_env.py) and InterferenceConstellationEnv
+    (envs/interference_constellation_env.py), unmodified.  Benefits carry inactive tasks (zeros) so that agents recharge
+    as well as drain; the episode is long enough for agents to run out of power through the 5.55e-17 residue
+    (SURVEY.md Q9).  The interference env builds itself from the orbit simulator only, so the simulator class in its
+    module namespace is replaced by a stand-in that hands out a given proximity tensor and neighbour matrix."""
+    import importlib
+
+    power_mod = importlib.import_module("envs.real_power_constellation_env")
+    inter_mod = importlib.import_module("envs.interference_constellation_env")
+    rng = np.random.default_rng(77)
+    n, m, T, L, M, N, lam = 8, 12, 14, 3, 4, 3, 0.5
+    S = O.gen_dense(rng, 1, n, m, T)[0]
+    S[:, ::4] = 0.0                      # tasks nobody can see: choosing them recharges
+    S[2] *= (rng.random(m) < 0.5)[:, None]  # an agent with many invisible tasks
+    prios = rng.choice([1.0, 1.0, 1.0, 5.0], size=m)
+    acts = rng.integers(0, m, size=(T, n))
+    acts[:, :3] = acts[:, :1]            # conflicts
+    acts[:, 5] = 1                       # an agent that always works a visible task: dies at t = 5, goes negative
+    np.random.seed(11)
+    env = power_mod.RealPowerConstellationEnv(1, n, m, T, N, M, L, lam, sat_prox_mat=S.astype(np.float64), graphs=1,
+                                              task_prios=prios)
+    out = _drive_power_like(env, T, acts, stable=True)   # zero-benefit tasks tie: stable rule (SURVEY.md Q1)
+    np.savez_compressed(os.path.join(HERE, "power_env.npz"), S=S, n=n, m=m, T=T, L=L, M=M, N=N, lambda_=lam, task_prios=prios,
+                        actions=acts, obs_size=env.get_obs_size(), **out)
+
+    # ---- interference env
+    neighbor = (rng.random((m, m)) < 0.3).astype(np.float64)
+    neighbor = np.maximum(neighbor, neighbor.T)
+    np.fill_diagonal(neighbor, 1.0)      # a region neighbours itself (the "- 1" of :331 removes the self-conflict)
+    bands = rng.integers(0, 3, size=n)
+
+    class _Sim:
+        def __init__(self, num_planes, num_sats_per_plane, T=None):
+            self.neighbor_matrix, self.graphs = neighbor, [1]
+
+        def get_proximities_for_coverage_tasks(self, res):
+            return S.astype(np.float64)
+
+    saved = inter_mod.HighPerformanceConstellationSim
+    inter_mod.HighPerformanceConstellationSim = _Sim
+    try:
+        np.random.seed(12)
+        ienv = inter_mod.InterferenceConstellationEnv(1, n, 2, T, N, M, L, lam, task_prios=prios, sat_freq_bands=bands)
+        iout = _drive_power_like(ienv, T, acts, stable=True)
+    finally:
+        inter_mod.HighPerformanceConstellationSim = saved
+    np.savez_compressed(os.path.join(HERE, "interference_env.npz"), S=S, n=n, m=m, T=T, L=L, M=M, N=N, lambda_=lam,
+                        task_prios=prios, actions=acts, neighbor_matrix=neighbor, sat_freq_bands=bands,
+                        obs_size=ienv.get_obs_size(), **iout)
+
+
 def golden_parallel_runner(R):
     """The reference's ParallelRunner (runners/parallel_runner.py:12-243: one forked env process per env, pickled pre-/post-
     transition data over Pipes) + BasicMAC + RNNAgent + epsilon_greedy with B = 4 envs and injected selector draws.  Keeps
@@ -643,6 +722,8 @@ def golden_parallel_runner(R):
 if __name__ == "__main__":
     if "--runner-only" in sys.argv:
         golden_runner(ref_import.ref_modules())
+    elif "--power-only" in sys.argv:
+        golden_power_envs(ref_import.ref_modules())
     elif "--parallel-only" in sys.argv:
         golden_parallel_runner(ref_import.ref_modules())
     else:

@@ -618,3 +618,103 @@ def test_real_env_fast2_matches_oracle(n, m, gen, opts):
         assert th.equal(batch["beta"].cpu(), _cast(want["beta"], th.float16))
         assert bool(batch["avail_actions"].all())
         assert th.equal(batch["actions_onehot"][:, :T].cpu(), _cast(O.one_hot(np.moveaxis(acts, 0, 1), m, np.int16), th.int16))
+
+
+@pytest.mark.parametrize("name", ["power_env.npz", "interference_env.npz"])
+def test_power_and_interference_envs_match_reference_golden(name):
+    """RealPowerConstellationEnv / InterferenceConstellationEnv through the batched device envs and the
+    reference-API facades, against vectors recorded from the unmodified reference classes: observations with the N + 1
+    power columns, rewards (zero / interference rule for agents out of power), prev_assigns, the power_states field and the
+    float64 power trajectory itself (the 5.55e-17 residue and the -0.2 it becomes)."""
+    from marl_sap_b200.envs import REGISTRY
+    from marl_sap_b200.envs.batched import BatchedInterferenceConstellationEnv, BatchedRealPowerConstellationEnv
+
+    g = _load(name)
+    S = g["S"]
+    n, m, T = S.shape
+    L, M, N, lam = int(g["L"]), int(g["M"]), int(g["N"]), float(g["lambda_"])
+    B = 3
+    if name.startswith("power"):
+        env = BatchedRealPowerConstellationEnv(B, n, m, T, L, M, N, lam, sat_prox_mat=S, task_prios=g["task_prios"])
+    else:
+        env = BatchedInterferenceConstellationEnv(B, n, m, T, L, M, N, lam, S, g["neighbor_matrix"], g["sat_freq_bands"],
+                                                  task_prios=g["task_prios"])
+    assert env.obs_size == int(g["obs_size"])
+    batch = _batch_for(env, B)
+    batch.agent_in = th.zeros(B, n, env.obs_size, device="cuda")
+    env.reset(batch, prev0=np.broadcast_to(g["prev0"], (B, n)).copy())
+    acts = g["actions"]
+    powers = [env.power.cpu().numpy().copy()]
+    for t in range(T):
+        done = env.step(th.tensor(np.broadcast_to(acts[t], (B, n)).copy(), device="cuda"), batch)
+        assert done == bool(g["done"][t])
+        powers.append(env.power.cpu().numpy().copy())
+        assert th.equal(batch.agent_in, batch["obs"][:, t + 1].float())
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    for b in range(B):
+        assert th.equal(td["obs"][b], _cast(g["obs"], th.float16)), f"obs mismatch env {b}"
+        assert th.equal(td["beta"][b], _cast(g["beta"], th.float16))
+        assert th.equal(td["prev_assigns"][b], _cast(g["prev"], th.int16))
+        assert th.equal(td["rewards"][b, :T], _cast(g["rewards"], th.float16))
+        assert th.equal(td["power_states"][b], _cast(g["power"], th.float16))
+        assert td["terminated"][b, :T, 0].tolist() == [bool(d) for d in g["done"]]
+        np.testing.assert_array_equal(np.stack(powers)[:, b], g["power"])            # float64, bit for bit
+    np.testing.assert_allclose(env.ep_return.cpu().numpy(), np.full(B, g["rewards"].sum()), rtol=1e-12)
+    # the reference-API facade (REGISTRY object driven like the reference env)
+    np.random.seed(0)
+    if name.startswith("power"):
+        fac = REGISTRY["real_power_constellation_env"](num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=lam,
+                                                       sat_prox_mat=S.astype(np.float64), graphs=1, task_prios=g["task_prios"])
+    else:
+        fac = REGISTRY["interference_constellation_env"](num_planes=1, num_sats_per_plane=n, res=2, T=T, N=N, M=M, L=L,
+                                                         lambda_=lam, task_prios=g["task_prios"],
+                                                         sat_freq_bands=g["sat_freq_bands"], sat_prox_mat=S.astype(np.float64),
+                                                         neighbor_matrix=g["neighbor_matrix"])
+    assert fac.scheme["power_states"]["vshape"] == (n,) and fac.get_obs_size() == int(g["obs_size"])
+    fac.reset()
+    pre = fac.get_pretransition_data()
+    assert set(pre) == {"beta", "obs", "prev_assigns", "avail_actions", "power_states"}
+    np.testing.assert_array_equal(pre["power_states"][0], np.ones(n))
+    r, d, info = fac.step(list(acts[0]))
+    assert len(r) == n and d is False and info == {}
+    bh = fac.beta_hat(pre["beta"][0], pre["prev_assigns"][0], np.array([0.0] + [1.0] * (n - 1)))
+    assert not bh[0].any() and bh[1:].any()
+
+
+@pytest.mark.parametrize("kind", ["power", "interference"])
+def test_power_and_interference_envs_match_oracle(kind):
+    """Seeded batches (distinct benefits per env, priorities, conflicts, agents that die and recharge) against the oracle."""
+    from marl_sap_b200.envs.batched import BatchedInterferenceConstellationEnv, BatchedRealPowerConstellationEnv
+
+    rng = np.random.default_rng(41)
+    B, n, m, T, L, M, N, lam = 4, 20, 30, 12, 3, 10, 10, 0.5
+    S = O.gen_ref_like(rng, B, n, m, T) + O.gen_dense(rng, B, n, m, T) * (rng.random((B, n, m, 1)) < 0.5)
+    S = S.astype(np.float32)
+    prios = rng.choice([1.0, 1.0, 1.0, 5.0], size=m)
+    acts = rng.integers(0, m, size=(T, B, n))
+    acts[:, :, : n // 3] = acts[:, :, :1]
+    acts[:, :, n // 3] = np.argmax(S.sum(-1)[:, n // 3], axis=-1)[None]   # an agent that keeps working its best task
+    prev0 = np.stack([rng.permutation(m)[:n] for _ in range(B)])
+    if kind == "power":
+        st = O.PowerState(S.astype(np.float64), L, M, N, lam, task_prios=prios)
+        env = BatchedRealPowerConstellationEnv(B, n, m, T, L, M, N, lam, sat_prox_mat=S, task_prios=prios)
+    else:
+        nb = (rng.random((m, m)) < 0.2).astype(np.float64)
+        nb = np.maximum(nb, nb.T)
+        np.fill_diagonal(nb, 1.0)
+        bands = rng.integers(0, 4, size=(B, n))
+        st = O.InterferenceState(S.astype(np.float64), L, M, N, lam, nb, bands, task_prios=prios)
+        env = BatchedInterferenceConstellationEnv(B, n, m, T, L, M, N, lam, S, nb, bands, task_prios=prios)
+    want = O.rollout(st, lambda t, pre: acts[t], "real", prev0=prev0)
+    batch = _batch_for(env, B, th.float32)
+    env.reset(batch, prev0=prev0)
+    for t in range(T):
+        env.step(th.tensor(acts[t], device="cuda"), batch)
+    td = {k: v.cpu() for k, v in batch.data.transition_data.items()}
+    assert th.equal(td["obs"], _cast(want["obs"], th.float32))
+    assert th.equal(td["rewards"], _cast(want["rewards"], th.float32))
+    assert th.equal(td["prev_assigns"], _cast(want["prev_assigns"], th.int16))
+    assert th.equal(td["power_states"], _cast(want["power_states"], th.float16))
+    np.testing.assert_array_equal(env.power.cpu().numpy(), want["power_states"][:, T])
+    np.testing.assert_allclose(env.ep_return.cpu().numpy(), want["rewards"].sum((1, 2)), rtol=1e-12)
+    assert (want["power_states"] <= 0).any()

@@ -206,3 +206,27 @@ def test_oracle_batched_rollout_matches_reference_parallel_runner():
     assert not g["td_terminated"][0].any() and g["td_terminated"][1:, :T].all() and not g["td_terminated"][:, T].any()
     assert g["td_actions"][:, T].any()
     assert np.mean(want["rewards"].sum((1, 2))) == pytest.approx(float(g["return_mean"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("name", ["power_env.npz", "interference_env.npz"])
+def test_power_and_interference_oracle_matches_reference(name):
+    """RealPowerConstellationEnv / InterferenceConstellationEnv: obs with the N + 1 power tail,
+    rewards, the float64 power trajectory (incl. the 5.55e-17 residue that is `> 0` but `< 1e-12`, and the -0.2 it turns
+    into) and done flags, against the unmodified reference classes."""
+    g = _load(name)
+    S = g["S"].astype(np.float64)[None]
+    L, M, N, lam = int(g["L"]), int(g["M"]), int(g["N"]), float(g["lambda_"])
+    if name.startswith("power"):
+        st = O.PowerState(S, L, M, N, lam, task_prios=g["task_prios"])
+    else:
+        st = O.InterferenceState(S, L, M, N, lam, g["neighbor_matrix"], g["sat_freq_bands"], task_prios=g["task_prios"])
+    assert st.obs_size == int(g["obs_size"])
+    acts = g["actions"]
+    want = O.rollout(st, lambda t, pre: acts[t][None], "real", prev0=g["prev0"][None])
+    np.testing.assert_array_equal(want["obs"][0], g["obs"])
+    np.testing.assert_array_equal(want["beta"][0], g["beta"])
+    np.testing.assert_array_equal(want["prev_assigns"][0], g["prev"])
+    np.testing.assert_array_equal(want["power_states"][0], g["power"])          # bit-exact float64
+    np.testing.assert_allclose(want["rewards"][0, :acts.shape[0]], g["rewards"], rtol=1e-15, atol=0)
+    assert want["terminated"][0, :acts.shape[0]].tolist() == [bool(d) for d in g["done"]]
+    assert (g["power"][:, 5] < 0).any() and np.any((g["power"] > 0) & (g["power"] < 1e-12))
