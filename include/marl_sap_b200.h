@@ -187,6 +187,15 @@ int sap_interference_rewards(const SapEnvDims* dims, const float* planes, const 
                              double lambda_, const int64_t* actions, const int32_t* k, const int32_t* prev,
                              const double* power, double* ep_return, const SapField* rewards, void* stream);
 
+/* ---- constellation proximities -------------------------------------------------
+ * sap_proximities_fov = calc_fov_based_proximities_fast (envs/HighPerformanceConstellationSim.py:308-327) over every
+ *   (satellite, task, time step): what get_proximities_for_random_tasks / _for_coverage_tasks (:91-270) produce, given the
+ *   propagated satellite positions sat_r[n,3,T] (km, float64, the simulator's sat_rs_over_time layout) and the task
+ *   positions task_r[m,3].  Writes the env kernels' plane layout planes[T,n,m] (fp32) and / or the reference layout
+ *   prox[n,m,T] (float64).  gaussian_sigma_2 = -(fov^2) / (2 ln 0.05) in the reference (:100-101). */
+int sap_proximities_fov(const double* sat_r_n3T, const double* task_r_m3, int32_t n, int32_t m, int32_t T, double fov,
+                        double gaussian_sigma_2, float* planes_Tnm, double* prox_nmT, void* stream);
+
 /* ---- MockConstellationEnv ---------------------------------------------------------------
  * sap_mock_reset = MockConstellationEnv.reset (mock_constellation_env.py:94-114); prev0[B,n]
  *                  replaces the np.random.choice draw at :105 (injected).

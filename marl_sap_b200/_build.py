@@ -20,7 +20,7 @@ OBJ = os.path.join(PKG, "build")
 LIB_PATH = os.path.join(PKG, "libmarl_sap_b200.so")
 STAMP = os.path.join(OBJ, "libmarl_sap_b200.stamp")
 SOURCES = ["sap_real.cu", "sap_real_fast.cu", "sap_real_fast2.cu", "sap_real_large.cu", "sap_mock.cu", "sap_select.cu",
-           "sap_lsa.cu", "sap_buffer.cu", "sap_power.cu"]
+           "sap_lsa.cu", "sap_buffer.cu", "sap_power.cu", "sap_proximity.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "sap_real_reset": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_step": (C.c_int, [_DIMS, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_scratch_doubles": (C.c_int64, [_DIMS]),
+    "sap_proximities_fov": (C.c_int, [_P, _P, _I32, _I32, _I32, _F64, _F64, _P, _P, _P]),
     "sap_real_reset_ex": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P, _I32, _P]),
     "sap_real_step_ex": (C.c_int, [_DIMS, _P, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P, _I32, _P]),
     "sap_power_pre": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _P, _P]),

@@ -8,8 +8,11 @@ Like the reference it works on the ``beta`` / ``prev_assigns`` state fields of t
 already rounded to the scheme dtype; when the runner has bound its batched env (``bind_env``) the same values are
 taken from the env's planes instead of materialising the lazy ``beta`` field.
 
-HAALSelector ("haal_selector", :54-145) searches over time-interval sequences with deep-copied envs; not built
-(DESIGN.md section 9).
+HAALSelector ("haal_selector", :54-145): look-ahead over every way to cut the next L steps into intervals.  The
+reference deep-copies the env per sequence and steps the copies on the host; here the "copies" are three small device
+tensors per sequence (step counter, prev_assigns, accumulated reward) for ALL envs of the batch at once, the rewards of a
+simulated step are a dozen array ops on the benefit planes (the reward rule of real_constellation_env.py:135-160), and every
+interval's assignment is one launch of the batched assignment kernel.
 """
 from __future__ import annotations
 
@@ -77,9 +80,91 @@ class HAASelector:
         return lsa_maximize(beta_hat_now(beta, prev, float(lam), T_trans).float())
 
 
-def _haal(args):
-    raise NotImplementedError("haal_selector (look-ahead over time-interval sequences with deep-copied envs) is not built "
-                              "yet (DESIGN.md, 'out of scope')")
+def time_interval_sequences(L):
+    """utils/methods.py:309-349: every split of steps 0 .. L-1 into consecutive intervals, in the reference's order."""
+    out = []
+
+    def rec(seq, start):
+        if start == L:
+            out.append(tuple(seq))
+            return
+        for end in range(start, L):
+            rec(seq + [(start, end)], end + 1)
+
+    rec([], 0)
+    return out
 
 
-REGISTRY = {"haa_selector": HAASelector, "haal_selector": _haal}
+class HAALSelector:
+    """non_rl_selectors.py:54-145 on the runner's batched real env (``bind_env``).  The reference asserts the episode
+    runner because it deep-copies one live env per batch element; the batched version has no such limit."""
+
+    def __init__(self, args):
+        self.args = args
+        self.envs = None
+        self._env = None
+
+    def bind_env(self, env):
+        self._env = env
+
+    @staticmethod
+    def _window(env, k):
+        """beta of step k in float64 [B, n, m, L] (real_constellation_env.py:167-170), straight from the planes."""
+        L = env.L
+        win = env.planes[:, k:k + L].double()
+        if win.shape[1] < L:
+            win = th.cat([win, win.new_zeros(win.shape[0], L - win.shape[1], env.n, env.m)], dim=1)
+        beta = win.permute(0, 2, 3, 1)
+        if env.task_prios is not None:
+            beta = beta * env.task_prios.double().view(1, 1, -1, 1)
+        return beta.expand(env.B, -1, -1, -1) if beta.shape[0] == 1 and env.B > 1 else beta
+
+    @staticmethod
+    def _beta_hat(env, beta, prev):
+        out = beta.clone()
+        out[..., 0] = beta_hat_now(beta, prev, env.lambda_, env.T_trans)
+        return out
+
+    @staticmethod
+    def _step_reward(env, beta, prev, a):
+        """sum_i reward_i of one env step (:145-160): conflict counts, beta_hat at the chosen entries, split if positive."""
+        B, n, m = env.B, env.n, env.m
+        cnt = th.zeros(B, m, dtype=th.float64, device=a.device).scatter_add_(1, a, th.ones(B, n, dtype=th.float64, device=a.device))
+        chosen = beta.gather(2, a.view(B, n, 1, 1).expand(-1, -1, 1, beta.shape[-1])).squeeze(2)   # [B, n, L]
+        if env.T_trans is None:
+            pen = (a != prev).double()
+        else:
+            pen = env.T_trans.double()[prev, a]
+        bh = chosen[..., 0] - env.lambda_ * pen * (chosen.sum(-1) > 1e-12).double()
+        r = th.where(bh > 0, bh / cnt.gather(1, a), bh)
+        return r.sum(1)
+
+    def select_action(self, batch=None, t=None):
+        env = self._env
+        if env is None or env.kind != "real":
+            raise RuntimeError("haal_selector needs the runner's batched real env (runner.setup binds it)")
+        k0 = env.t_host
+        eff = min(env.L, env.T - k0)
+        best_val, best = None, None
+        for tis in time_interval_sequences(eff):
+            k, prev = k0, env.prev.long()
+            val = th.zeros(env.B, dtype=th.float64, device=env.device)
+            first = None
+            for i, (t0, t1) in enumerate(tis):
+                total = self._beta_hat(env, self._window(env, k), prev).sum(-1)
+                a = lsa_maximize(total.float().contiguous())
+                for _ in range(t1 - t0 + 1):
+                    val = val + self._step_reward(env, self._window(env, k), prev, a)
+                    k, prev = k + 1, a
+                if i == 0:
+                    first = a
+            if best is None:
+                best_val, best = val, first
+            else:
+                better = val > best_val                       # strict: the first sequence wins ties (:109-112)
+                best_val = th.where(better, val, best_val)
+                best = th.where(better.unsqueeze(1), first, best)
+        return best
+
+
+REGISTRY = {"haa_selector": HAASelector, "haal_selector": HAALSelector}

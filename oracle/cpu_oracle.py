@@ -468,6 +468,54 @@ def haa_actions(beta: np.ndarray, prev: np.ndarray, lambda_: float, T_trans=None
     return np.stack([linear_sum_assignment(bh[e], maximize=True)[1] for e in range(bh.shape[0])]).astype(np.int64)
 
 
+def time_interval_sequences(L: int):
+    """GENERATE_ALL_TIME_INTERVALS + BUILD_TIME_INTERVAL_SEQUENCES (utils/methods.py:309-349): every way to cut the next L
+    steps into consecutive intervals, in the reference's enumeration order (depth first, shorter first interval first)."""
+    out = []
+
+    def rec(seq, start):
+        if start == L:
+            out.append(tuple(seq))
+            return
+        for end in range(start, L):
+            rec(seq + [(start, end)], end + 1)
+
+    rec([], 0)
+    return out
+
+
+def haal_actions(S, k, prev, L, lambda_, task_prios=None, T_trans=None):
+    """HAALSelector.select_action (non_rl_selectors.py:54-118) for B real envs at step k: for every time-interval sequence,
+    roll a copy of the env forward - per interval the optimal assignment of sum_l beta_hat(beta, prev)[..., l], held for
+    the whole interval - and keep the first-interval assignment of the sequence with the largest summed reward (the first
+    such sequence on ties).  Envs are float64 throughout, like the deep-copied reference envs."""
+    from scipy.optimize import linear_sum_assignment
+
+    S = np.asarray(S, dtype=np.float64)
+    B, n, m, T = S.shape
+    eff = min(L, T - k)
+    picks = np.zeros((B, n), dtype=np.int64)
+    for b in range(B):
+        best_val, best = -np.inf, None
+        for tis in time_interval_sequences(eff):
+            kk, pv, val, first = k, np.asarray(prev[b], dtype=np.int64), 0.0, None
+            for i, (t0, t1) in enumerate(tis):
+                beta = real_window(S[b:b + 1], kk, L, task_prios)
+                total = real_beta_hat_full(beta, pv[None], lambda_, T_trans).sum(-1)[0]
+                a = linear_sum_assignment(total, maximize=True)[1]
+                for _ in range(t1 - t0 + 1):
+                    beta = real_window(S[b:b + 1], kk, L, task_prios)
+                    bh = real_beta_hat_chosen(beta, pv[None], a[None], lambda_, T_trans)
+                    val += float(_split_rewards(bh, a[None], _counts(a[None], m)).sum())
+                    kk, pv = kk + 1, a
+                if i == 0:
+                    first = a
+            if val > best_val:
+                best_val, best = val, first
+        picks[b] = best
+    return picks
+
+
 def filtered_benefit_matrix(q: np.ndarray, top: np.ndarray, m: int, u_tie: np.ndarray) -> np.ndarray:
     """filtered_sap_selectors.py:43-57: baseline + U * 1e-8 everywhere, the top-M tasks get their own Q-values (fp32)."""
     B, n, _ = q.shape

@@ -390,6 +390,36 @@ def golden_haa(R):
                         follow=follow)
 
 
+def golden_haal(R):
+    """HAALSelector (non_rl_selectors.py:54-145) of the unmodified reference: at every step of a short episode its pick for
+    the live env (look-ahead over all time-interval sequences with deep-copied envs and scipy assignments)."""
+    import importlib
+
+    import torch as th
+
+    non_rl = importlib.import_module("action_selectors.non_rl_selectors")
+    rng = np.random.default_rng(78)
+    n, m, T, L, M, N, lam = 6, 9, 7, 3, 4, 3, 0.5
+    S = O.gen_dense(rng, 1, n, m, T)[0]
+    prios = rng.choice([1.0, 2.0], size=m)
+    env = R.real_env.RealConstellationEnv(1, n, m=m, T=T, N=N, M=M, L=L, lambda_=lam, sat_prox_mat=S.astype(np.float64),
+                                          graphs=1, task_prios=prios)
+    args = SimpleNamespace(use_mps_action_selection=False, device="cpu", runner="episode")
+    sel = non_rl.HAALSelector(args)
+    sel.envs = [env]
+    batch = R.episode_buffer.EpisodeBatch(env.scheme, {"agents": n}, 1, T + 1, preprocess=env.preprocess, device="cpu")
+    env.reset()
+    picks, prevs, follow = [], [], rng.integers(0, m, size=(T, n))
+    for t in range(T):
+        batch.update(env.get_pretransition_data(), ts=t)
+        prevs.append(np.array(env.prev_assigns).astype(np.int64))
+        a = sel.select_action(batch[:, t]).numpy().astype(np.int64)[0]
+        picks.append(a)
+        env.step(a if t % 2 == 0 else follow[t])
+    np.savez_compressed(os.path.join(HERE, "haal.npz"), S=S, L=L, M=M, N=N, lambda_=lam, task_prios=prios,
+                        haal_actions=np.stack(picks), prev=np.stack(prevs), follow=follow)
+
+
 class _inject:
     """Feed injected uniforms to th.rand_like (in call order) and replace Categorical.sample by the
     rank-select contract of oracle.random_available_action."""
@@ -487,12 +517,14 @@ def main():
     golden_selectors(R)
     golden_sap_selectors(R)
     golden_haa(R)
+    golden_haal(R)
     golden_bids(R)
     golden_policy_selectors(R)
     golden_buffer(R)
     golden_runner(R)
     golden_parallel_runner(R)
     golden_power_envs(R)
+    golden_proximities(R)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
@@ -649,6 +681,47 @@ def golden_power_envs(R):
                         obs_size=ienv.get_obs_size(), **iout)
 
 
+def golden_proximities(R=None):
+    """calc_fov_based_proximities_fast (envs/HighPerformanceConstellationSim.py:308-327), the reference's own function: the
+    module needs poliastro at import time, so the function's source is cut out of the unmodified file with ``ast`` and
+    executed on its own (it is pure numpy).  Satellites on circular 550 km tracks, some passing over tasks."""
+    import ast
+
+    with open(os.path.join(ref_import.REFERENCE_SRC, "envs", "HighPerformanceConstellationSim.py")) as fh:
+        tree = ast.parse(fh.read())
+    fn = [x for x in tree.body if isinstance(x, ast.FunctionDef) and x.name == "calc_fov_based_proximities_fast"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "HighPerformanceConstellationSim.py", "exec"), ns)
+    f = ns["calc_fov_based_proximities_fast"]
+    rng = np.random.default_rng(5)
+    n, m, T = 12, 20, 9
+
+    def unit(k):
+        v = rng.standard_normal((k, 3))
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+    task = unit(m) * 6371.0
+    base = unit(n)
+    base[:6] = task[:6] / 6371.0 + 0.05 * rng.standard_normal((6, 3))
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    axis = unit(n)
+    sat = np.zeros((n, 3, T))
+    for i in range(n):
+        for k in range(T):
+            ang = 0.01 * k
+            v = base[i] * np.cos(ang) + np.cross(axis[i], base[i]) * np.sin(ang) + axis[i] * np.dot(axis[i], base[i]) * (1 - np.cos(ang))
+            sat[i, :, k] = v / np.linalg.norm(v) * 6921.0
+    fov = 60.0
+    sig2 = np.sqrt(-(fov ** 2) / (2 * np.log(0.05))) ** 2          # :100-101
+    prox = np.zeros((n, m, T))
+    for i in range(n):
+        for j in range(m):
+            for k in range(T):
+                prox[i, j, k] = f(sat[i, :, k], task[j], fov, sig2)
+    assert (prox > 0).mean() > 0.02
+    np.savez_compressed(os.path.join(HERE, "proximities.npz"), sat_r=sat, task_r=task, fov=fov, sigma_2=sig2, prox=prox)
+
+
 def golden_parallel_runner(R):
     """The reference's ParallelRunner (runners/parallel_runner.py:12-243: one forked env process per env, pickled pre-/post-
     transition data over Pipes) + BasicMAC + RNNAgent + epsilon_greedy with B = 4 envs and injected selector draws.  Keeps
@@ -722,6 +795,11 @@ def golden_parallel_runner(R):
 if __name__ == "__main__":
     if "--runner-only" in sys.argv:
         golden_runner(ref_import.ref_modules())
+    elif "--prox-only" in sys.argv:
+        ref_import.install()
+        golden_proximities()
+    elif "--haal-only" in sys.argv:
+        golden_haal(ref_import.ref_modules())
     elif "--power-only" in sys.argv:
         golden_power_envs(ref_import.ref_modules())
     elif "--parallel-only" in sys.argv:

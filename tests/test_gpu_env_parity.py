@@ -718,3 +718,28 @@ def test_power_and_interference_envs_match_oracle(kind):
     np.testing.assert_array_equal(env.power.cpu().numpy(), want["power_states"][:, T])
     np.testing.assert_allclose(env.ep_return.cpu().numpy(), want["rewards"].sum((1, 2)), rtol=1e-12)
     assert (want["power_states"] <= 0).any()
+
+
+def test_fov_proximities_match_the_reference_function():
+    """sap_proximities_fov vs calc_fov_based_proximities_fast of the reference (HighPerformanceConstellationSim.py:308-327,
+    golden tests/golden/proximities.npz): the visible / invisible pattern exactly, the values to 1e-12 in float64 (acos / exp
+    of CUDA vs numpy's libm) and to fp32 rounding in the plane layout the env kernels read; then an env runs on them."""
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+    from marl_sap_b200.envs.proximity import fov_proximities, gaussian_sigma_2
+
+    g = _load("proximities.npz")
+    assert gaussian_sigma_2(float(g["fov"])) == pytest.approx(float(g["sigma_2"]), rel=1e-15)
+    planes, ref = fov_proximities(g["sat_r"], g["task_r"], fov=float(g["fov"]), reference_layout=True)
+    want = g["prox"]
+    got = ref.cpu().numpy()
+    np.testing.assert_array_equal(got > 0, want > 0)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(planes.cpu().numpy(), np.transpose(want, (2, 0, 1)).astype(np.float32), rtol=2e-7, atol=0)
+    n, m, T = want.shape
+    env = BatchedRealConstellationEnv(2, n, m, T, 3, 4, 3, 0.5)
+    env.set_planes(planes[None], shared=True)
+    batch = _batch_for(env, 2)
+    env.reset(batch)
+    st = O.RealState(np.broadcast_to(planes.cpu().numpy().transpose(1, 2, 0).astype(np.float64), (2, n, m, T)).copy(), 3, 4, 3, 0.5)
+    st.reset()
+    assert th.equal(batch["obs"][:, 0].cpu(), _cast(st.obs, th.float16))

@@ -407,8 +407,7 @@ def test_haa_selector_and_jumpstart_mac():
             np.testing.assert_array_equal(got[0].cpu().numpy(), want_a)
             a = want_a if t % 2 == 0 else g["follow"][t]
             runner.env.step(th.tensor(np.broadcast_to(a, (B, n)).copy(), device="cuda"), runner.batch)
-    with pytest.raises(NotImplementedError, match="haal_selector"):
-        non_rl["haal_selector"](args)
+    assert hasattr(non_rl["haal_selector"](args), "select_action")   # built: see the HAAL test below
 
 
 def test_runner_mock_env_draws_its_own_benefits_on_the_device():
@@ -670,3 +669,40 @@ def test_replay_insert_of_a_stale_ring_view_does_not_alias():
     keep = v["obs"].clone()
     buf.insert_episode_batch(v)               # stale view: lands in rows 2..4, overlapping its own storage (rows 0..2)
     assert th.equal(buf["obs"][2:5], keep) and buf.buffer_index == 5
+
+
+def test_haal_selector_matches_reference_golden_and_oracle():
+    """haal_selector on the batched env: the reference's picks along its golden episode (tests/golden/haal.npz) and the
+    oracle's on a batch of distinct envs."""
+    import os
+
+    from marl_sap_b200.action_selectors.non_rl_selectors import REGISTRY as non_rl
+    from marl_sap_b200.components.episode_buffer import EpisodeBatch
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "haal.npz")))
+    S = g["S"]
+    n, m, T = S.shape
+    L, M, N, lam = int(g["L"]), int(g["M"]), int(g["N"]), float(g["lambda_"])
+    env = BatchedRealConstellationEnv(1, n, m, T, L, M, N, lam, sat_prox_mat=S, task_prios=g["task_prios"])
+    batch = EpisodeBatch(env.scheme, {"agents": n}, 1, T + 1, preprocess=env.preprocess, device="cuda")
+    sel = non_rl["haal_selector"](SimpleNamespace(runner="episode"))
+    sel.bind_env(env)
+    env.reset(batch)
+    for t in range(T):
+        a = sel.select_action(batch, t)
+        assert a.cpu().numpy()[0].tolist() == g["haal_actions"][t].tolist(), t
+        env.step(a if t % 2 == 0 else th.tensor(g["follow"][t][None], device="cuda"), batch)
+    # a batch of distinct envs against the oracle
+    rng = np.random.default_rng(3)
+    B, n, m, T = 5, 10, 14, 6
+    S = O.gen_dense(rng, B, n, m, T)
+    env = BatchedRealConstellationEnv(B, n, m, T, 3, 4, 3, 0.5, sat_prox_mat=S)
+    batch = EpisodeBatch(env.scheme, {"agents": n}, B, T + 1, preprocess=env.preprocess, device="cuda")
+    sel.bind_env(env)
+    env.reset(batch)
+    for t in range(T):
+        want = O.haal_actions(S, t, env.prev.cpu().numpy(), 3, 0.5)
+        a = sel.select_action(batch, t)
+        np.testing.assert_array_equal(a.cpu().numpy(), want)
+        env.step(a, batch)

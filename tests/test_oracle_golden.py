@@ -230,3 +230,13 @@ def test_power_and_interference_oracle_matches_reference(name):
     np.testing.assert_allclose(want["rewards"][0, :acts.shape[0]], g["rewards"], rtol=1e-15, atol=0)
     assert want["terminated"][0, :acts.shape[0]].tolist() == [bool(d) for d in g["done"]]
     assert (g["power"][:, 5] < 0).any() and np.any((g["power"] > 0) & (g["power"] < 1e-12))
+
+
+def test_haal_oracle_matches_reference():
+    """HAALSelector of the unmodified reference (look-ahead over time-interval sequences) vs the oracle, step by step."""
+    g = _load("haal.npz")
+    S = g["S"].astype(np.float64)[None]
+    assert O.time_interval_sequences(3) == [((0, 0), (1, 1), (2, 2)), ((0, 0), (1, 2)), ((0, 1), (2, 2)), ((0, 2),)]
+    for t in range(S.shape[-1]):
+        a = O.haal_actions(S, t, g["prev"][t][None], int(g["L"]), float(g["lambda_"]), task_prios=g["task_prios"])[0]
+        np.testing.assert_array_equal(a, g["haal_actions"][t])
