@@ -29,6 +29,13 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr size_t kMaxSmem = 227 * 1024 - 1024;
 
+// timing-ablation hooks (profiling builds only: -DSAP_ABLATE); in release builds the tests below are constant false
+#ifdef SAP_ABLATE
+#define SAP_DBG(p) ((p).debug_skip_redo)
+#else
+#define SAP_DBG(p) 0
+#endif
+
 #define SAP_CE(a, b)            \
   {                             \
     uint32_t hi__ = max(a, b);  \
@@ -531,7 +538,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   }
   __syncthreads();
 
-  if (p.debug_skip_redo & 256) return;  // timing ablation: stop after the key pass
+  if (SAP_DBG(p) & 256) return;  // timing ablation: stop after the key pass
   // exact float64 window sum (the reference's beta.sum(-1), :190) straight from global memory: only the rare
   // lists that cannot be certified use it
   auto tot64 = [&](int a, int j) {
@@ -551,7 +558,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     uint32_t top[16];
     group_top16<TPL>(live ? m : 0, s, [&](int e) { return (row[e] << ib) | (imask - (uint32_t)e); }, top);
     if (live && s == 0) {
-      if (!certified(top, K2, ib) && !p.debug_skip_redo) {
+      if (!certified(top, K2, ib) && !SAP_DBG(p)) {
         qRows[atomicAdd(&sQ[0], 1)] = i;
       } else {
         // D: first M entries as they are (ties are proven ties, already in index-ascending order)
@@ -622,9 +629,9 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     }
   }
 
-  if (p.debug_skip_redo & 512) return;  // timing ablation: stop after the task lists
+  if (SAP_DBG(p) & 512) return;  // timing ablation: stop after the task lists
   // ------------------------------------------------------------------ 6. rivals (:203-206)
-  for (int base = 0; base < n * TPL && !(p.debug_skip_redo & 4); base += kThreads) {
+  for (int base = 0; base < n * TPL && !(SAP_DBG(p) & 4); base += kThreads) {
     const int g = base + tid;
     const int i = g / TPL, s = g % TPL;
     const bool live = i < n;
@@ -644,7 +651,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
                 },
                 top);
     if (live && s == 0) {
-      if (!certified(top, N, ib) && !p.debug_skip_redo) {
+      if (!certified(top, N, ib) && !SAP_DBG(p)) {
         qNbr[atomicAdd(&sQ[1], 1)] = i;
       } else {
 #pragma unroll
@@ -669,11 +676,11 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   }
   __syncthreads();
 
-  if (p.debug_skip_redo & 128) return;  // timing ablation: stop after the rival lists
+  if (SAP_DBG(p) & 128) return;  // timing ablation: stop after the rival lists
   // ------------------------------------------------------------------ 7. rivals' other top tasks (:212-217)
   // The M/2 best tasks of rival r outside D[i] under (value desc, idx desc) are the first M/2 entries of E[r]
   // not in D[i]; the reference lists them ascending, so they are stored reversed.
-  for (int it = tid; it < n * N && !(p.debug_skip_redo & 64); it += kThreads) {
+  for (int it = tid; it < n * N && !(SAP_DBG(p) & 64); it += kThreads) {
     const int i = it / N;
     const int r = sNbr[it];
     int c = 0;
@@ -690,7 +697,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   // ------------------------------------------------------------------ 8a. benefits of the window -> shared memory
   // Second read of the window (it is L2-resident: this CTA streamed it a few microseconds ago).  It lands over
   // the key tile and the scratch lists, which are dead now, already rounded to the obs dtype (:199-219 gathers).
-  if (p.debug_skip_redo & 32) {
+  if (SAP_DBG(p) & 32) {
   } else if (vec4) {
     const int total4 = nm >> 2;
     auto put4 = [&](int l, int e4, const float4& v) {
@@ -767,7 +774,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     const int rows = min(rpp, n - r0);
     unsigned char* gdst = reinterpret_cast<unsigned char*>(obs_out) + (size_t)r0 * row_bytes;
     const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15);
-    if (warp < rows && !(p.debug_skip_redo & 8)) {
+    if (warp < rows && !(SAP_DBG(p) & 8)) {
       const int i = r0 + warp;
       OutT* srow = reinterpret_cast<OutT*>(stage + phase + (size_t)warp * row_bytes);
       const IdxT* myD = sD + i * M;
@@ -830,7 +837,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
     // generic-proxy writes of the staged rows must be visible to the async proxy (TMA) before the barrier
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    const size_t bytes = (p.debug_skip_redo & 16) ? 0 : (size_t)rows * row_bytes;
+    const size_t bytes = (SAP_DBG(p) & 16) ? 0 : (size_t)rows * row_bytes;
     const unsigned char* ssrc = stage + phase;
     if (phase == 0 && (bytes & 15) == 0 && (!ain || ain_flat)) {
       // aligned block.  The obs rows leave shared memory with ONE TMA bulk store (cp.async.bulk.global.shared::cta)

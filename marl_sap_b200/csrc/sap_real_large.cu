@@ -22,6 +22,12 @@
 #include "sap_real.cuh"
 #include "sap_sortnet.cuh"
 
+#ifdef SAP_ABLATE
+#define SAP_DBG(p) ((p).debug_skip_redo)
+#else
+#define SAP_DBG(p) 0
+#endif
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 4) sap_real_large_lists(RealParams p
 #pragma unroll
       for (int t = 0; t < 15; ++t)
         if (t < K2) ok = ok && pair_ok(top[t] >> ib, top[t + 1] >> ib);
-      if (!ok && !(p.debug_skip_redo & 1)) {
+      if (!ok && !(SAP_DBG(p) & 1)) {
         q_rows[atomicAdd(&q_cnt, 1)] = i;
       } else {
         uint16_t* Dr = s.D + ((size_t)b * n + i) * M;
@@ -637,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 5) sap_real_large_main(RealParams p)
     else if (n <= 256) ok = keyed_rivals<8>(kt, wD, wN, n, m, M, N, i, lane);
     else if (n <= 384) ok = keyed_rivals<12>(kt, wD, wN, n, m, M, N, i, lane);
     else ok = keyed_rivals<16>(kt, wD, wN, n, m, M, N, i, lane);
-    need_exact = !ok && !(p.debug_skip_redo & 1);
+    need_exact = !ok && !(SAP_DBG(p) & 1);
     __syncwarp();
   }
   if (kKeyed) {

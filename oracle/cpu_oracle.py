@@ -540,10 +540,10 @@ def rollout(state, policy, scheme_kind: str, prev0=None):
     (A.5 timeline): obs, beta, prev_assigns (real only), actions, rewards, terminated, filled.
     """
     B, n, m, T = state.B, state.n, state.m, state.T
-    if scheme_kind == "real" and prev0 is None:
-        state.reset()
+    if scheme_kind == "real" and not isinstance(state, PowerState):
+        state.reset()            # the real env starts from prev_assigns = arange(n) (:129)
     else:
-        state.reset(prev0)
+        state.reset(prev0)       # mock and power-type envs draw prev_assigns (injected)
     pre = state.pretransition()
     out = {
         "obs": np.zeros((B, T + 1, n, state.obs_size)),
