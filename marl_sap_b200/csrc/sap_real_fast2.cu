@@ -366,70 +366,88 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     }
     uint32_t* Sw = reinterpret_cast<uint32_t*>(smem + f.stage1) + warp * 4 * m;  // this warp's staging tile
     const uint32_t inv_m4 = (uint32_t)((0x100000000ull + (uint32_t)m4 - 1u) / (uint32_t)m4);  // x / m4 = umulhi(x, inv)
-    // one unit = agents 4 I .. 4 I + 3, task groups [ja, ja + len)
-    auto unit = [&](auto tag, int I, int ja, int len, bool whole_rows) {
+    auto keys_of = [&](auto tag, const float4 (&v)[kL]) -> uint4 {
+      constexpr bool kFast = decltype(tag)::value;
+      double tot[4] = {(double)v[0].x, (double)v[0].y, (double)v[0].z, (double)v[0].w};  // 0.0 + x == x
+#pragma unroll
+      for (int l = 1; l < kL; ++l) {  // (planes past the horizon were loaded as zeros)
+        tot[0] += (double)v[l].x;
+        tot[1] += (double)v[l].y;
+        tot[2] += (double)v[l].z;
+        tot[3] += (double)v[l].w;
+      }
+      uint4 kk;
+      kk.x = kFast ? make_key_fast(tot[0]) : make_key_generic(tot[0]);
+      kk.y = kFast ? make_key_fast(tot[1]) : make_key_generic(tot[1]);
+      kk.z = kFast ? make_key_fast(tot[2]) : make_key_generic(tot[2]);
+      kk.w = kFast ? make_key_fast(tot[3]) : make_key_generic(tot[3]);
+      return kk;
+    };
+    // Whole agent group 4 I .. 4 I + 3 (the hot unit).  Its four rows are ONE run of 4 m floats per plane, so position
+    // fpos = lane + 32 t is simply float4 number fpos of that run - and of the staging tile: every address below is a
+    // per-lane base plus a compile-time offset.
+    const uint32_t* sw_rd = Sw + lane;            // staging read: task lane + 32 u of row r at sw_rd[r m + 32 u]
+    uint32_t* kt_wr = KT + lane * kKP;            // transposed tile: row of task lane + 32 u at kt_wr + 32 u kKP
+    auto unit_rows = [&](auto tag, int I) {
       constexpr bool kFast = decltype(tag)::value;  // full window of non-negative benefits: no predicates on the loads
-      const int cnt4 = 4 * len;                    // float4 positions of the unit
+      const float* src = win + (4 * I) * m + 4 * lane;
       float4 v[4][kL];
-      int so[4];                                   // staging offset (words) of position t, -1 = none
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const int fpos = lane + 32 * t;
-        so[t] = -1;
-        if (fpos < cnt4) {  // divergent only at the tail of a unit
-          const int r = whole_rows ? (int)__umulhi((uint32_t)fpos, inv_m4) : fpos / len;
-          const int j4 = ja + fpos - r * len;
-          so[t] = r * m + 4 * j4;
-          const float* src = win + (4 * I + r) * m + 4 * j4;
+        if (lane + 32 * t < m) {  // m float4 positions (4 rows x m / 4); divergent only in the last one
 #pragma unroll
           for (int l = 0; l < kL; ++l) {
             if (kFast) {
-              v[t][l] = ldg_hint4(src + l * nm, pol_keep);
+              v[t][l] = ldg_hint4(src + l * nm + 128 * t, pol_keep);
             } else {
               v[t][l] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (l < Leff) v[t][l] = ldg_hint4(src + l * nm, pol_keep);
+              if (l < Leff) v[t][l] = ldg_hint4(src + l * nm + 128 * t, pol_keep);
             }
           }
         }
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (so[t] >= 0) {
-          double tot[4] = {(double)v[t][0].x, (double)v[t][0].y, (double)v[t][0].z, (double)v[t][0].w};  // 0.0 + x == x
+      for (int t = 0; t < 4; ++t)
+        if (lane + 32 * t < m) *reinterpret_cast<uint4*>(Sw + 4 * lane + 128 * t) = keys_of(tag, v[t]);
+      __syncwarp();
+      const int col = (I ^ (lane & 3)) << 2;  // task & 3 == lane & 3 for every task lane + 32 u
 #pragma unroll
-          for (int l = 1; l < kL; ++l) {
-            tot[0] += (double)v[t][l].x;
-            tot[1] += (double)v[t][l].y;
-            tot[2] += (double)v[t][l].z;
-            tot[3] += (double)v[t][l].w;
-          }
-          uint4 kk;
-          kk.x = kFast ? make_key_fast(tot[0]) : make_key_generic(tot[0]);
-          kk.y = kFast ? make_key_fast(tot[1]) : make_key_generic(tot[1]);
-          kk.z = kFast ? make_key_fast(tot[2]) : make_key_generic(tot[2]);
-          kk.w = kFast ? make_key_fast(tot[3]) : make_key_generic(tot[3]);
-          *reinterpret_cast<uint4*>(Sw + so[t]) = kk;
+      for (int u = 0; u < 4; ++u)
+        if (lane + 32 * u < m) {
+          const uint4 o = make_uint4(sw_rd[32 * u], sw_rd[m + 32 * u], sw_rd[2 * m + 32 * u], sw_rd[3 * m + 32 * u]);
+          *reinterpret_cast<uint4*>(kt_wr + 32 * u * kKP + col) = o;
         }
+      __syncwarp();
+    };
+    // part of an agent group: task groups [ja, ja + len) of agents 4 I .. 4 I + 3 (the groups left over when the number
+    // of agent groups is not a multiple of the warp count are split by task range, so that no warp works an extra round)
+    auto unit_part = [&](auto tag, int I, int ja, int len) {
+      const int cnt4 = 4 * len;
+      for (int fpos = lane; fpos < cnt4; fpos += 32) {
+        const int r = fpos / len, j4 = ja + fpos - r * len;
+        const float* src = win + (4 * I + r) * m + 4 * j4;
+        float4 v[kL];
+#pragma unroll
+        for (int l = 0; l < kL; ++l) {
+          v[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (l < Leff) v[l] = ldg_hint4(src + l * nm, pol_keep);
+        }
+        *reinterpret_cast<uint4*>(Sw + r * m + 4 * j4) = keys_of(tag, v);
       }
       __syncwarp();
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int x = lane + 32 * u;  // task 4 ja + x
-        if (x < cnt4) {
-          const int jt = 4 * ja + x;
-          const uint4 o = make_uint4(Sw[jt], Sw[m + jt], Sw[2 * m + jt], Sw[3 * m + jt]);
-          *reinterpret_cast<uint4*>(KT + jt * kKP + ((I ^ (jt & 3)) << 2)) = o;
-        }
+      for (int x = lane; x < cnt4; x += 32) {
+        const int jt = 4 * ja + x;
+        const uint4 o = make_uint4(Sw[jt], Sw[m + jt], Sw[2 * m + jt], Sw[3 * m + jt]);
+        *reinterpret_cast<uint4*>(KT + jt * kKP + ((I ^ (jt & 3)) << 2)) = o;
       }
       __syncwarp();
     };
     auto run = [&](auto tag) {
       const int full = n4 / kWarps;  // rounds in which every warp has a whole agent group
-      for (int r = 0; r < full; ++r) unit(tag, r * kWarps + warp, 0, m4, true);
-      // the remaining groups are split by task range over the warps, so that no warp works a whole extra round
+      for (int r = 0; r < full; ++r) unit_rows(tag, r * kWarps + warp);
       const int len = (m4 + kWarps - 1) / kWarps, ja = warp * len, mine = min(len, m4 - ja);
       for (int I = full * kWarps; I < n4; ++I)
-        if (mine > 0) unit(tag, I, ja, mine, false);
+        if (mine > 0) unit_part(tag, I, ja, mine);
     };
     if (Leff == kL && k_nonneg) run(std::true_type{});
     else run(std::false_type{});
