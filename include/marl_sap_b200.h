@@ -142,6 +142,21 @@ int sap_real_step(const SapEnvDims* dims, const float* planes, const float* plan
 /* number of scratch doubles sap_real_reset / sap_real_step need for these dims (0: none) */
 int64_t sap_real_scratch_doubles(const SapEnvDims* dims);
 
+/* The observation of slot k + 1 (real_constellation_env.py:177-225) depends on the benefit window only - NOT on the actions of
+ * step k - except for its last M columns ("is my previous task among my top-M", :222).  So one env step can be issued as
+ *     sap_real_obs_ahead     : window -> keys -> lists -> gather -> obs rows of slot k[b] + 1 (flags 0), agent-input rows,
+ *                              top_out; reads k, writes no counter.  Runs NEXT TO the agent forward of step k (another stream).
+ *     sap_real_step_after_obs: conflict counts, beta_hat at the chosen entries, rewards (:135-164), actions / rewards /
+ *                              terminated of slot k, k += 1, prev_assigns, filled, and the flags of the new rows (from `top`).
+ * Together they write exactly what sap_real_step writes.  sap_real_obs_ahead_ok(dims) = 1 when the ahead kernel exists for
+ * these dims (the one-CTA-per-env kernel of the shipped configuration); callers fall back to sap_real_step otherwise. */
+int sap_real_obs_ahead_ok(const SapEnvDims* dims);
+int sap_real_obs_ahead(const SapEnvDims* dims, const float* planes, const float* plane_stats, const int32_t* k,
+                       const SapBatchView* view, int32_t* top_out, void* stream);
+int sap_real_step_after_obs(const SapEnvDims* dims, const float* planes, const float* task_prios, const float* T_trans,
+                            double lambda_, const int64_t* actions, int32_t* k, int32_t* prev, double* ep_return,
+                            int32_t* counts_out, const SapBatchView* view, const int32_t* top, void* stream);
+
 /* Kernel selection of sap_real_reset / sap_real_step.  AUTO picks by shape: the one-CTA-per-env kernels when the env
  * state fits one SM's shared memory (second generation for the shipped configuration M = N = 10, L = 3, fp16 scheme at
  * 64 < n <= 128; first generation otherwise), the generic kernel for unusual M / N / L, the multi-CTA path for large

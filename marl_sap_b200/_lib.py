@@ -76,6 +76,9 @@ SIGNATURES = {
     "sap_bias_act": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
     "sap_split_bias_act": (C.c_int, [_P, _I32, _F32, _P, _P, _I64, _I32, _I32, _P]),
     "sap_real_agent_in_f16_ok": (C.c_int, [_DIMS]),
+    "sap_real_obs_ahead_ok": (C.c_int, [_DIMS]),
+    "sap_real_obs_ahead": (C.c_int, [_DIMS, _P, _P, _P, _VIEW, _P, _P]),
+    "sap_real_step_after_obs": (C.c_int, [_DIMS, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P]),
     "sap_real_beta_rows": (C.c_int, [_DIMS, _P, _P, _P, _I32, _I32, _P, _I32, _P]),
     "sap_real_select_kernel": (C.c_int32, [_I32]),
     "sap_lsa_maximize": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),

@@ -91,9 +91,13 @@ class BasicMAC:
             if t > 0:
                 block.scatter_(2, batch["actions"][:, t - 1].long(), 1.0)
             col += m
-        if self.args.obs_agent_id and not getattr(batch, "agent_in_has_ids", False):
-            staged[:, :, col:col + self.n] = th.eye(self.n, device=staged.device)
-            batch.agent_in_has_ids = True
+        if self.args.obs_agent_id:  # written once per staging buffer (the runner may alternate between two)
+            done = getattr(batch, "_agent_in_ids_done", None)
+            if done is None:
+                done = batch._agent_in_ids_done = set()
+            if staged.data_ptr() not in done:
+                staged[:, :, col:col + self.n] = th.eye(self.n, device=staged.device, dtype=staged.dtype)
+                done.add(staged.data_ptr())
         return staged.view(batch.batch_size * self.n, -1)
 
     # ------------------------------------------------------------------ parameters / checkpoints (agent.th, :62-67)

@@ -27,6 +27,7 @@ struct RealParams {
   int32_t* nbr_out;       // [B,n,N] rival indices of the new observation, or null
   const int64_t* prev0;   // reset only: [B,n] initial prev_assigns instead of arange(n), or null
   int obs_row;            // elements between consecutive agents' observation rows (0 = obs_size: packed)
+  int obs_only;     // sap_real_fast2: build the observation of slot k + 1 only (no rewards, no counters, flags = 0)
   int large_exact;  // multi-CTA path: exact float64 selection even where the keyed lists would apply (selector override)
 };
 

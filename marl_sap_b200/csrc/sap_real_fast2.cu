@@ -156,8 +156,11 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   const SapBatchView& vw = p.view;
 
   // reward-phase loads that do not depend on each other are issued up front (two DRAM round trips instead of five)
+  // obs_only: the observation of slot k + 1 ahead of the step (it does not depend on the actions of step k apart from the
+  // "previous task in my top-M" flags, which sap_real_step_after_obs sets): no rewards, no counters, flags = 0
+  const bool stepping = !p.is_reset && !p.obs_only;
   int a_mine = 0, pv_mine = 0;
-  if (!p.is_reset && tid < n) {
+  if (stepping && tid < n) {
     a_mine = min(max((int)p.actions[(size_t)b * n + tid], 0), m - 1);
     pv_mine = p.prev[(size_t)b * n + tid];
   }
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   __syncthreads();
 
   // ------------------------------------------------------------------ 1. rewards at the old window (:135-164)
-  if (!p.is_reset) {
+  if (stepping) {
     float mine[kL] = {0.f, 0.f, 0.f};
     if (tid < n) {
 #pragma unroll
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
       if (vw.terminated.ptr)
         sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, done);
     }
-  } else {
+  } else if (p.is_reset) {
     for (int i = tid; i < n; i += kThreads) p.prev[(size_t)b * n + i] = i;
     if (tid == 0) {
       p.k[b] = 0;
@@ -255,8 +258,9 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
 
   // ------------------------------------------------------------------ 2. pre-transition scalars of slot k_new
   const int t_slot = k_new;
-  if (tid == 0 && vw.filled.ptr) sap_store_int(vw.filled.ptr, sap_field_off(vw.filled, b, t_slot), vw.filled.dtype, 1);
-  if (vw.prev_assigns.ptr && tid < n)
+  if (tid == 0 && vw.filled.ptr && !p.obs_only)
+    sap_store_int(vw.filled.ptr, sap_field_off(vw.filled, b, t_slot), vw.filled.dtype, 1);
+  if (vw.prev_assigns.ptr && tid < n && !p.obs_only)
     sap_store_int(vw.prev_assigns.ptr, sap_field_off(vw.prev_assigns, b, t_slot) + tid, vw.prev_assigns.dtype,
                   p.is_reset ? tid : a_mine);
   if (vw.avail_actions.ptr) {  // eager field: every action available (:267-273)
@@ -278,17 +282,25 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   // that a tensor-core GEMM can read with 128-bit loads (496 halves for 490): then the rows are copied word by word
   const int ain16_pitch = ain_half ? (int)vw.agent_in.t_stride : 0;
   const bool ain16_bulk = ain_half && ain16_pitch == kObs;
+  // fp32 rows are packed (pitch = obs size: 128-bit stores across row boundaries) or pitched (the MAC appends last-action /
+  // agent-id columns behind the observation: float2 stores row by row)
+  const int ain32_pitch = ain ? (int)vw.agent_in.t_stride : 0;
+  const bool ain32_flat = ain && ain32_pitch == kObs;
   if (done) {  // :226-228
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     uint4* o4 = reinterpret_cast<uint4*>(obs_out);
     for (int e = tid; e < (n * kRowBytes) >> 4; e += kThreads) o4[e] = z;
-    if (ain) {
+    if (ain32_flat) {
       uint4* a4 = reinterpret_cast<uint4*>(ain);
       for (int e = tid; e < (n * kObs * 4) >> 4; e += kThreads) a4[e] = z;
+    } else if (ain) {
+      for (int i = warp; i < n; i += kWarps)
+        for (int c = lane; c < kObs; c += 32) ain[(size_t)i * ain32_pitch + c] = 0.f;
     }
-    if (ain16) {  // packed or padded rows: the pad columns stay as the host initialised them (zeros)
+    if (ain16) {  // packed or padded rows: only the observation columns (the MAC owns whatever follows them)
       uint32_t* a2 = reinterpret_cast<uint32_t*>(ain16);
-      for (int e = tid; e < n * (ain16_pitch >> 1); e += kThreads) a2[e] = 0u;
+      for (int i = warp; i < n; i += kWarps)
+        for (int w = lane; w < kRowBytes / 4; w += 32) a2[(size_t)i * (ain16_pitch >> 1) + w] = 0u;
     }
     if (vw.beta.ptr) {
       const int64_t bb = sap_field_off(vw.beta, b, t_slot);
@@ -866,7 +878,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
       *reinterpret_cast<uint16_t*>(srow + slot_off + (odd ? 0u : 28u)) = (uint16_t)(odd ? w[0] : h[4]);
       // "is my previous task among my top-M" flags (:222)
       if (lane < kM) {
-        const int pv = p.prev[(size_t)b * n + i];
+        const int pv = p.obs_only ? -1 : p.prev[(size_t)b * n + i];
         const int j = sD[i * kM + lane];
         reinterpret_cast<uint16_t*>(srow)[kPairs * kL + lane] = j == pv ? (uint16_t)0x3c00u : (uint16_t)0u;
         if (p.top_out) p.top_out[((size_t)b * n + i) * kM + lane] = j;
@@ -897,7 +909,18 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
                      : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (ain_on_) {
+    if (ain_on_ && !ain32_flat) {  // pitched fp32 rows: two floats per 32-bit word of the staged fp16 row
+      constexpr int kRowWords = kRowBytes / 4;
+      const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(stage);
+      for (int r = warp; r < rows; r += kWarps) {
+        float2* drow = reinterpret_cast<float2*>(ain + (size_t)(r0 + r) * ain32_pitch);
+#pragma unroll
+        for (int w = lane; w < kRowWords; w += 32) {
+          const uint32_t hw = ssrc[r * kRowWords + w];
+          drow[w] = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+        }
+      }
+    } else if (ain_on_) {
       float* adst = ain + (size_t)r0 * kObs;
       const int chunks = (int)(bytes >> 4);
 #pragma unroll 4
@@ -929,12 +952,136 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
 
 }  // namespace
 
+// The rest of an env step once the observation of slot k + 1 is in place (sap_real_obs_ahead): conflict counts, beta_hat at
+// the chosen entries, rewards, counters, prev_assigns, and the "previous task in my top-M" flags of the new rows (:222).
+__global__ void __launch_bounds__(128) sap_real_step_only_kernel(RealParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  int32_t* sCnt = reinterpret_cast<int32_t*>(smem);
+  __shared__ double sRed[4];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const SapEnvDims d = p.d;
+  const int n = d.n, m = d.m, T = d.T, L = d.L, M = d.M, N = d.N, H = d.M / 2;
+  const SapBatchView& vw = p.view;
+  const int k_old = p.k[b];
+  if (k_old >= T) return;
+  const int k_new = k_old + 1;
+  const bool done = k_new >= T;
+  const size_t env_plane0 = d.shared_planes ? (size_t)0 : (size_t)b * T;
+  const float* env_planes = p.planes + env_plane0 * (size_t)n * m;
+  for (int j = tid; j < m; j += 128) sCnt[j] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += 128) atomicAdd(&sCnt[min(max((int)p.actions[(size_t)b * n + i], 0), m - 1)], 1);
+  __syncthreads();
+  const int flag_col = (M + N * M + N * H) * L;  // first flag column of an observation row
+  const int obs_size = flag_col + M;
+  double local = 0.0;
+  for (int i = tid; i < n; i += 128) {
+    const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
+    const int pv = p.prev[(size_t)b * n + i];
+    const double pr = p.prios ? (double)p.prios[a] : 1.0;
+    double sum = 0.0, b0 = 0.0;
+    for (int l = 0; l < L; ++l)
+      if (k_old + l < T) {
+        const double v = (double)env_planes[((size_t)(k_old + l) * n + i) * m + a] * pr;
+        if (l == 0) b0 = v;
+        sum += v;
+      }
+    const double pen = p.ttrans ? (double)p.ttrans[(size_t)pv * m + a] : (a != pv ? 1.0 : 0.0);
+    const double bh = b0 - p.lambda_ * (pen * (sum > 1e-12 ? 1.0 : 0.0));
+    const double r = bh > 0.0 ? bh / (double)sCnt[a] : bh;
+    local += r;
+    if (vw.rewards.ptr) sap_store_real(vw.rewards.ptr, sap_field_off(vw.rewards, b, k_old) + i, vw.rewards.dtype, r);
+    if (vw.actions.ptr) sap_store_int(vw.actions.ptr, sap_field_off(vw.actions, b, k_old) + i, vw.actions.dtype, a);
+    p.prev[(size_t)b * n + i] = a;
+    if (vw.prev_assigns.ptr) sap_store_int(vw.prev_assigns.ptr, sap_field_off(vw.prev_assigns, b, k_new) + i, vw.prev_assigns.dtype, a);
+    if (!done && p.top_out) {  // flags of the new row: 1 where my top-M task q is the task I just took
+      for (int q = 0; q < M; ++q)
+        if (p.top_out[((size_t)b * n + i) * M + q] == a) {
+          sap_store_real(vw.obs.ptr, sap_field_off(vw.obs, b, k_new) + (int64_t)i * obs_size + flag_col + q, vw.obs.dtype, 1.0);
+          if (vw.agent_in.ptr) {
+            const int64_t at = (int64_t)b * vw.agent_in.env_stride + (int64_t)i * vw.agent_in.t_stride + flag_col + q;
+            if (vw.agent_in.dtype == SAP_F16) reinterpret_cast<__half*>(vw.agent_in.ptr)[at] = __float2half(1.f);
+            else reinterpret_cast<float*>(vw.agent_in.ptr)[at] = 1.f;
+          }
+        }
+    }
+  }
+  if (vw.actions_onehot.ptr) {
+    const int64_t base = sap_field_off(vw.actions_onehot, b, k_old);
+    for (int e = tid; e < n * m; e += 128) {
+      const int i = e / m, j = e - i * m;
+      const int a = min(max((int)p.actions[(size_t)b * n + i], 0), m - 1);
+      sap_store_int(vw.actions_onehot.ptr, base + e, vw.actions_onehot.dtype, a == j ? 1 : 0);
+    }
+  }
+  if (p.counts_out)
+    for (int j = tid; j < m; j += 128) p.counts_out[(size_t)b * m + j] = sCnt[j];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(SAP_FULL_MASK, local, off);
+  if ((tid & 31) == 0) sRed[tid >> 5] = local;
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&p.ep_return[b], sRed[0] + sRed[1] + sRed[2] + sRed[3]);
+    p.k[b] = k_new;
+    if (vw.terminated.ptr) sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, done);
+    if (vw.filled.ptr) sap_store_int(vw.filled.ptr, sap_field_off(vw.filled, b, k_new), vw.filled.dtype, 1);
+  }
+}
+
 static bool fast2_dims_ok(const SapEnvDims& d) {
   return d.M == kM && d.N == kN && d.L == kL && d.n > 64 && d.n <= 128 && d.m <= 128 && !(d.n & 3) && !(d.m & 3) && d.m >= d.n &&
          f2_layout(d.n, d.m).total <= kMaxSmem;
 }
 
 extern "C" int sap_real_agent_in_f16_ok(const SapEnvDims* dims) { return dims && fast2_dims_ok(*dims) ? 1 : 0; }
+
+extern "C" int sap_real_obs_ahead_ok(const SapEnvDims* dims) { return dims && fast2_dims_ok(*dims) ? 1 : 0; }
+
+extern "C" int sap_real_obs_ahead(const SapEnvDims* dims, const float* planes, const float* plane_stats, const int32_t* k,
+                                  const SapBatchView* view, int32_t* top_out, void* stream) {
+  SAP_REQUIRE(dims && planes && plane_stats && k && view && view->obs.ptr && top_out, SAP_E_NULL, "sap_real_obs_ahead: null pointer");
+  RealParams p{};
+  p.d = *dims;
+  p.planes = planes;
+  p.plane_stats = plane_stats;
+  p.k = const_cast<int32_t*>(k);
+  p.view = *view;
+  p.top_out = top_out;
+  p.obs_only = 1;
+  int handled = 0;
+  const int rc = sap_real_fast2_try(p, stream, &handled);
+  if (rc != SAP_OK) return rc;
+  SAP_REQUIRE(handled, SAP_E_CONSTRAINT,
+              "sap_real_obs_ahead: only the shipped configuration (M = N = 10, L = 3, fp16 obs, no priorities, 64 < n <= 128, "
+              "m <= 128, per-plane stats) builds observations ahead of the step; use sap_real_step");
+  return SAP_OK;
+}
+
+extern "C" int sap_real_step_after_obs(const SapEnvDims* dims, const float* planes, const float* task_prios,
+                                       const float* T_trans, double lambda_, const int64_t* actions, int32_t* k, int32_t* prev,
+                                       double* ep_return, int32_t* counts_out, const SapBatchView* view, const int32_t* top,
+                                       void* stream) {
+  SAP_REQUIRE(dims && planes && actions && k && prev && ep_return && view && view->obs.ptr && top, SAP_E_NULL,
+              "sap_real_step_after_obs: null pointer");
+  SAP_REQUIRE(dims->B > 0 && dims->n > 0 && dims->m > 0 && dims->T > 0 && dims->L > 0 && dims->L <= 8, SAP_E_DIMS,
+              "sap_real_step_after_obs: bad dims");
+  RealParams p{};
+  p.d = *dims;
+  p.planes = planes;
+  p.prios = task_prios;
+  p.ttrans = T_trans;
+  p.lambda_ = lambda_;
+  p.actions = actions;
+  p.k = k;
+  p.prev = prev;
+  p.ep_return = ep_return;
+  p.counts_out = counts_out;
+  p.view = *view;
+  p.top_out = const_cast<int32_t*>(top);
+  sap_real_step_only_kernel<<<dims->B, 128, sizeof(int32_t) * (size_t)dims->m, (cudaStream_t)stream>>>(p);
+  SAP_CUDA_LAUNCH_CHECK("sap_real_step_only_kernel");
+  return SAP_OK;
+}
 
 int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
   *handled = 0;
@@ -951,8 +1098,8 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
       return SAP_E_DTYPE;
     }
     const int esz = vw.agent_in.dtype == SAP_F32 ? 4 : 2;
-    const bool padded16 = esz == 2 && vw.agent_in.t_stride > kObs && !(vw.agent_in.t_stride & 1);  // padded fp16 rows
-    if ((vw.agent_in.t_stride != kObs && !padded16) || !sap_aligned16(vw.agent_in.ptr) || ((vw.agent_in.env_stride * esz) & 15)) {
+    const bool padded = vw.agent_in.t_stride > kObs && !(vw.agent_in.t_stride & 1);  // rows with extra / pad columns
+    if ((vw.agent_in.t_stride != kObs && !padded) || !sap_aligned16(vw.agent_in.ptr) || ((vw.agent_in.env_stride * esz) & 15)) {
       if (esz == 2) {
         sap_set_error("sap_real: an f16 agent_in must be [B, n, pitch >= obs] with an even pitch and 16-byte aligned envs");
         return SAP_E_CONSTRAINT;

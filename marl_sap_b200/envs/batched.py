@@ -226,6 +226,8 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
         self.task_prios = None if task_prios is None else \
             th.as_tensor(np.asarray(task_prios), dtype=th.float32).contiguous().to(self.device)
         self.top = th.zeros(B, n, M, dtype=th.int32, device=self.device)
+        self._top_next, self._ahead = None, False
+        self._top_home = self.top   # reset() always starts from this buffer (captured CUDA graphs bake the alternation in)
         self.scheme, self.preprocess = real_scheme(n, m, L, self.obs_size)
         need = int(self.lib.sap_real_scratch_doubles(self.dims()))
         self.scratch = th.empty(need, dtype=th.float64, device=self.device) if need > 0 else None
@@ -235,6 +237,9 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
 
     def reset(self, batch):
         self._check_batch(batch)
+        if self.top is not self._top_home:
+            self.top, self._top_next = self._top_next, self.top
+        self._ahead = False
         view = batch.kernel_view()
         _lib.check(self.lib.sap_real_reset(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
                                            _lib.ptr(self.task_prios), _lib.ptr(self.k), _lib.ptr(self.prev),
@@ -242,9 +247,48 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
                                            _lib.stream_ptr(self.device)), "sap_real_reset")
         self.t_host = 0
 
-    def step(self, actions, batch):
-        view = batch.kernel_view()
+    # ------------------------------------------------------------------ observation ahead of the step
+    def supports_obs_ahead(self, batch):
+        """True when the observation of slot t + 1 can be built next to the agent forward of step t
+        (``sap_real_obs_ahead``): the shipped configuration on the one-CTA-per-env kernel."""
+        return (type(self) is BatchedRealConstellationEnv and self.task_prios is None and self.plane_stats is not None
+                and not getattr(self, "bids_as_actions", False) and batch.scheme["obs"]["dtype"] == th.float16
+                and bool(self.lib.sap_real_obs_ahead_ok(self.dims())))
+
+    @staticmethod
+    def _with_agent_in(view, agent_in):
+        if agent_in is not None:
+            f = _lib.SapField()
+            f.ptr, f.env_stride, f.t_stride, f.dtype = agent_in.data_ptr(), agent_in.stride(0), agent_in.stride(1), _lib.sap_dtype(agent_in.dtype)
+            view.agent_in = f
+        return view
+
+    def obs_ahead(self, batch, agent_in=None):
+        """Enqueue (on the current stream) the observation build of slot k + 1: it reads the benefit window only, so it may
+        run while the agent network and the selector are still working on slot k.  The following ``step`` then only
+        computes rewards / counters and sets the "previous task in my top-M" flags.  ``agent_in``: the staging rows to fill
+        (the runner double-buffers them: the agent is reading the other buffer)."""
+        view = self._with_agent_in(batch.kernel_view(), agent_in)
+        if self._top_next is None:
+            self._top_next = th.zeros_like(self.top)
+        _lib.check(self.lib.sap_real_obs_ahead(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats), _lib.ptr(self.k),
+                                               view, _lib.ptr(self._top_next), _lib.stream_ptr(self.device)), "sap_real_obs_ahead")
+        self._ahead = True
+
+    def step(self, actions, batch, agent_in=None):
+        view = self._with_agent_in(batch.kernel_view(), agent_in)
         actions = self._actions_for_step(actions, view, batch)
+        if self._ahead:  # the observation rows of the new slot are already there
+            _lib.check(self.lib.sap_real_step_after_obs(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.task_prios),
+                                                        _lib.ptr(self.T_trans), self.lambda_, actions.data_ptr(), _lib.ptr(self.k),
+                                                        _lib.ptr(self.prev), _lib.ptr(self.ep_return), _lib.ptr(self.counts), view,
+                                                        _lib.ptr(self._top_next), _lib.stream_ptr(self.device)),
+                       "sap_real_step_after_obs")
+            self._ahead = False
+            self.t_host += 1
+            if self.t_host < self.T:  # env.top = top-M tasks of the newest observation (a finished env builds none)
+                self.top, self._top_next = self._top_next, self.top
+            return self.t_host >= self.T
         _lib.check(self.lib.sap_real_step(self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
                                           _lib.ptr(self.task_prios),
                                           _lib.ptr(self.T_trans), self.lambda_, actions.data_ptr(), _lib.ptr(self.k),

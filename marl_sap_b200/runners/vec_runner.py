@@ -177,6 +177,13 @@ class CudaVecRunner:
                                      "one-CTA-per-env kernel takes (M = N = 10, L = 3, 64 < n <= 128, m <= 128)")
                 dtype, row = th.float16, (row + 7) // 8 * 8
             self.agent_in = th.zeros(self.batch_size, self.env.n, row, dtype=dtype, device=self.device)
+        # args.overlap_obs_build (default on): build the next observation next to the agent forward (second stream)
+        self._overlap = bool(getattr(self.args, "overlap_obs_build", True)) and self.env.kind == "real"
+        self._agent_in_bufs, self._side_stream = None, None
+        if self._overlap:
+            self._side_stream = th.cuda.Stream(device=self.device)
+            if self.agent_in is not None:
+                self._agent_in_bufs = [self.agent_in, th.zeros_like(self.agent_in)]
 
     def get_env(self):
         """The reference returns worker 0's env, pickled through the Pipe (parallel_runner.py:246-247, 281-282): a COPY
@@ -232,7 +239,8 @@ class CudaVecRunner:
             self._batch = self.batch
         if self.env.kind == "real":
             self.batch.top_agent_tasks = self.env.top
-        self.batch.agent_in = getattr(self, "agent_in", None)
+        self.batch.agent_in = getattr(self, "agent_in", None)   # (= buffer 0 of the double-buffered rows)
+        self.batch._agent_in_ids_done = set()   # the MAC rewrites the agent-id columns once per staging buffer and episode
         self.env.reset(self.batch, **reset_kwargs)
         if "beta" in self.lazy:
             # a lazily rebuilt `beta`: the batch rows remember which planes (row, generation) they were rolled out on
@@ -242,7 +250,37 @@ class CudaVecRunner:
         self.kernel_launches += self.env.launches_per_step
         self.t = 0
 
+    def _rollout_loop_overlapped(self, test_mode):
+        """The T-step loop with the observation build taken off the critical path.  The observation of slot t + 1 depends on
+        the benefit window only - not on the actions of step t, apart from M flag columns per agent - so
+        ``sap_real_obs_ahead`` builds it on a second stream WHILE the agent network and the selector work on slot t; the
+        step itself (``sap_real_step_after_obs``: rewards, counters, flags) then costs microseconds.  The fp32 / fp16
+        agent-input rows are double-buffered because the agent is still reading slot t's rows."""
+        main = th.cuda.current_stream(self.device)
+        side = self._side_stream
+        self.mac.init_hidden(batch_size=self.batch_size)
+        bufs = self._agent_in_bufs
+        for t in range(self.T):
+            nxt = None if bufs is None else bufs[(t + 1) % 2]
+            side.wait_stream(main)      # step t - 1 is done: k = t, and nobody reads the rows about to be overwritten
+            with th.cuda.stream(side):
+                self.env.obs_ahead(self.batch, agent_in=nxt)
+            if bufs is not None:
+                self.batch.agent_in = bufs[t % 2]
+            self.batch.top_agent_tasks = self.env.top   # top-M tasks of slot t (slot t + 1's go to the other buffer)
+            actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+            main.wait_stream(side)
+            self.env.step(actions, self.batch, agent_in=nxt)
+            self.batch.agent_in_t = t + 1
+            if bufs is not None:
+                self.batch.agent_in = nxt
+            self.t += 1
+        self.batch.top_agent_tasks = self.env.top
+        self.episode_ctr += 1
+
     def _rollout_loop(self, test_mode):
+        if self._overlap and self.env.supports_obs_ahead(self.batch):
+            return self._rollout_loop_overlapped(test_mode)
         self.mac.init_hidden(batch_size=self.batch_size)
         for t in range(self.T):
             # agent forward (torch) + selection kernel; obs / avail / beta for slot t were written by the env kernel

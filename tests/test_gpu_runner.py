@@ -706,3 +706,47 @@ def test_haal_selector_matches_reference_golden_and_oracle():
         a = sel.select_action(batch, t)
         np.testing.assert_array_equal(a.cpu().numpy(), want)
         env.step(a, batch)
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph", "fp16_split", "filtered"])
+def test_runner_overlapped_obs_build_equals_fused_step(mode):
+    """args.overlap_obs_build (default): the observation of slot t + 1 is built on a second stream next to the agent forward
+    of step t (sap_real_obs_ahead) and the step only adds rewards / counters / flags (sap_real_step_after_obs).  Every
+    field of the episode batch must equal the fused-step rollout bit for bit - eagerly, as a captured CUDA graph, with the
+    fp16 staging rows of the split-precision agent, and with the filtered selector (which reads the env's top-M tasks)."""
+    rng = np.random.default_rng(29)
+    B, n, m, T, L, M, N = 5, 100, 100, 5, 3, 10, 10
+    S = O.gen_dense(rng, B, n, m, T)
+    S[:, :, ::9] = 0.0
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=0.5, sat_prox_mat=S, graphs=1)
+    draws = {"u_explore": rng.random((2 * T, B, n), dtype=np.float32), "u_action": rng.random((2 * T, B, n), dtype=np.float32)}
+    if mode == "filtered":
+        draws["u_tie"] = rng.random((2 * T, B, n, m), dtype=np.float32)
+    out = []
+    for overlap in (False, True):
+        kw = dict(overlap_obs_build=overlap, epsilon_start=0.3, epsilon_finish=0.3, obs_last_action=True, obs_agent_id=True,
+                  use_cuda_graph=mode == "graph", reuse_episode_batch=True)
+        if mode == "fp16_split":
+            kw["agent_fc1"] = "fp16_split"
+        if mode == "filtered":
+            kw.update(agent="flat_const_agent", selector="filtered_const_epsilon_greedy")
+        args = make_args("real_constellation_env", env_args, B, **kw)
+        runner, mac, buffer, _ = build(args)
+        assert runner._overlap == overlap
+        inj = None if mode == "graph" else DrawInjector(mac.action_selector, draws)   # graphs: in-kernel Philox (same seeds)
+        eps = []
+        with th.no_grad():
+            for _ in range(3 if mode == "graph" else 2):
+                b = runner.run(test_mode=False)
+                eps.append({k: v.clone() for k, v in b.data.transition_data.items()})
+                if inj is not None and len(eps) == 1:
+                    inj.t = T   # second episode: the second half of the draws
+        out.append((eps, runner.env.ep_return.clone(), runner.env.top.clone(), runner.env.prev.clone()))
+        if mode == "graph":
+            assert len(runner._graphs) == 1
+    (ea, ra, ta, pa), (eb, rb, tb, pb) = out
+    for x, y in zip(ea, eb):
+        for k in x:
+            assert th.equal(x[k], y[k]), k
+    assert th.equal(ra, rb) and th.equal(ta, tb) and th.equal(pa, pb)
+    assert eb[0]["obs"][:, 1:, :, -M:].any() and not th.equal(eb[0]["obs"], eb[1]["obs"])
