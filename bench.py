@@ -208,7 +208,7 @@ def bytes_8d(w):
 
 
 def build_runner(w, rank_seed, planes, use_graph=True, selector="epsilon_greedy", lazy=("beta", "avail_actions", "actions_onehot"),
-                 agent_fc1="fp32", global_batch=None):
+                 agent_fc1="fp32", global_batch=None, overlap=True):
     import torch as th
 
     from marl_sap_b200.components.episode_buffer import ReplayBuffer
@@ -233,7 +233,8 @@ def build_runner(w, rank_seed, planes, use_graph=True, selector="epsilon_greedy"
                            obs_agent_id=False, obs_last_action=False, agent_output_type="q", test_nepisode=planes.shape[0],
                            runner_log_interval=10 ** 12, seed=rank_seed, use_mps_action_selection=True,
                            lazy_buffer_fields=tuple(lazy), reuse_episode_batch=True, use_cuda_graph=bool(use_graph),
-                           agent_fc1=agent_fc1)
+                           agent_fc1=agent_fc1, overlap_obs_build=overlap,
+                           overlap_submit_order=os.environ.get("SAP_OVERLAP_ORDER", "agent_first"))
     logger = Logger()
     runner = r_REGISTRY["parallel"](args=args, logger=logger)
     assert runner.batch_size == planes.shape[0], (runner.batch_size, planes.shape)
@@ -261,15 +262,15 @@ class Rollout:
         self.ev_pairs, self.timing = [], False
         orig = runner.env.step
 
-        def timed_step(actions, batch):
+        def timed_step(actions, batch, **kw):
             if self.timing:
                 a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
                 a.record()
-                r = orig(actions, batch)
+                r = orig(actions, batch, **kw)
                 b.record()
                 self.ev_pairs.append((a, b))
                 return r
-            return orig(actions, batch)
+            return orig(actions, batch, **kw)
 
         runner.env.step = timed_step
 
@@ -308,15 +309,19 @@ class Rollout:
         self.barrier()
         self.timing = False
         launches = self.launches() - l0
-        if graph:
-            # the timed region replayed captured CUDA graphs (no per-launch events possible): take the per-launch
-            # durations from one extra eager episode right after it
+        overlapped = getattr(self.runner, "_overlap", False)
+        if graph or overlapped:
+            # the timed region replayed captured CUDA graphs and / or built the observations on a second stream next to
+            # the agent's GEMMs (no clean per-launch events possible): the env kernel's own launch duration comes from one
+            # extra episode right after it, launched eagerly with the fused step (sap_real_step) alone on the stream
             self.runner.args.use_cuda_graph = False
-            self.timing = True
+            self.runner._overlap = False
+            self.timing, self.ev_pairs = True, []
             self.step()
             th.cuda.synchronize()
             self.timing = False
-            self.runner.args.use_cuda_graph = True
+            self.runner.args.use_cuda_graph = graph
+            self.runner._overlap = overlapped
         ms = e0.elapsed_time(e1)
         kern = sum(a.elapsed_time(b) for a, b in self.ev_pairs) / max(len(self.ev_pairs), 1)
         t = th.tensor([ms, kern], dtype=th.float64, device="cuda")
@@ -369,6 +374,7 @@ def gpu_arm(opts, w):
     value = agent_steps / (ms * 1e-3)
     e_ain = 0 if runner.agent_in is None else runner.agent_in.element_size()
     multi_cta = getattr(runner.env, "launches_per_step", 1) == 4
+    runner_overlap = SimpleNamespace(value=bool(getattr(runner, "_overlap", False)) and runner.env.supports_obs_ahead(runner.batch))
 
     # ------------------------------------------------------------------ e2e: host inputs in, host results out
     e2e, e2e_fresh = None, None
@@ -406,6 +412,8 @@ def gpu_arm(opts, w):
                 "rows and fc1 is ONE fp16 tensor-core GEMM against [W0|W1|W2] with fp32 accumulation + a fold/bias/ReLU "
                 "kernel (max rel. error vs float64 9.5e-7; the fp32 sgemm: 1.4e-6)" if other == "fp16_split" else
                 "default fp32 agent: fp32 staging rows, torch/cuBLAS sgemm", agent_fc1=other)
+        variant("fused_step", "args.overlap_obs_build=False: the observation is built inside the step kernel, after the "
+                "selection (one stream; the round-1 schedule)", agent_fc1=opts.agent_fc1, overlap=False)
         free, _ = th.cuda.mem_get_info(dev)
         eager_bytes = B * (T + 1) * (n * obs_size(w) * 2 + n * m * w["L"] * 2 + n * m * 1 + n * m * 2 + 64 * n)
         if eager_bytes * 1.1 < free:
@@ -465,6 +473,7 @@ def gpu_arm(opts, w):
                                f"{opts.selector} + fc agent(hidden 64)",
                    "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch",
                    "cuda_graph": bool(graph), "agent_fc1": opts.agent_fc1,
+                   "overlap_obs_build": bool(getattr(runner_overlap, "value", False)),
                    "inputs": f"benefit planes {planes.numel() * 4 / 2 ** 30:.1f} GiB per GPU (> 126 MB L2), distinct per env",
                    "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
                    "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy (rebuilt "

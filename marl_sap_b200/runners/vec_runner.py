@@ -260,15 +260,28 @@ class CudaVecRunner:
         side = self._side_stream
         self.mac.init_hidden(batch_size=self.batch_size)
         bufs = self._agent_in_bufs
+        order = getattr(self.args, "overlap_submit_order", "agent_first")
         for t in range(self.T):
             nxt = None if bufs is None else bufs[(t + 1) % 2]
-            side.wait_stream(main)      # step t - 1 is done: k = t, and nobody reads the rows about to be overwritten
-            with th.cuda.stream(side):
-                self.env.obs_ahead(self.batch, agent_in=nxt)
+            # step t - 1 is done at this point of the main stream: k = t, and nobody reads the rows about to be overwritten
+            ready = th.cuda.Event()
+            ready.record(main)
+
+            def ahead():
+                side.wait_event(ready)
+                with th.cuda.stream(side):
+                    self.env.obs_ahead(self.batch, agent_in=nxt)
+
+            if order != "agent_first":
+                ahead()
             if bufs is not None:
                 self.batch.agent_in = bufs[t % 2]
             self.batch.top_agent_tasks = self.env.top   # top-M tasks of slot t (slot t + 1's go to the other buffer)
             actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+            if order == "agent_first":
+                # submitted AFTER the agent's GEMMs: those take the SMs first and the observation kernel's CTAs (75 KB of
+                # shared memory each) fill what is left, instead of locking the GEMMs out
+                ahead()
             main.wait_stream(side)
             self.env.step(actions, self.batch, agent_in=nxt)
             self.batch.agent_in_t = t + 1
@@ -347,7 +360,10 @@ class CudaVecRunner:
             self._rollout_loop(test_mode)
         if self.compat_quirks:
             self._apply_parallel_runner_quirks(test_mode)
-        self.kernel_launches += (1 + self.env.launches_per_step) * self.T  # selector + env kernel(s) per timestep
+        per_step = 1 + self.env.launches_per_step  # selector + env kernel(s) per timestep
+        if self._overlap and self.env.supports_obs_ahead(self.batch):
+            per_step += 1                           # observation kernel + step kernel instead of one fused launch
+        self.kernel_launches += per_step * self.T
         self.last_episode_returns = self.env.ep_return.clone()
         self._finish_run(test_mode)
         return self.batch
