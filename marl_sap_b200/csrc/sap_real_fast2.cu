@@ -1120,10 +1120,14 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
     configured = true;
   }
   *handled = 1;
+#ifdef SAP_ABLATE
   {
-    const char* la = getenv("SAP_F2_LOOKAHEAD");  // blocks of L2 look-ahead (measured: no gain at 4096 x 100 x 100, off by default)
+    const char* la = getenv("SAP_F2_LOOKAHEAD");  // blocks of L2 look-ahead (measured: no gain at 4096 x 100 x 100)
     p.lookahead = la ? atoi(la) : 0;
   }
+#else
+  p.lookahead = 0;
+#endif
   sap_real_fast2_kernel<<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_fast2_kernel");
   return SAP_OK;
