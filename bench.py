@@ -208,7 +208,7 @@ def bytes_8d(w):
 
 
 def build_runner(w, rank_seed, planes, use_graph=True, selector="epsilon_greedy", lazy=("beta", "avail_actions", "actions_onehot"),
-                 agent_fc1="fp32", global_batch=None, overlap=True):
+                 agent_fc1="fp32", global_batch=None, overlap=True, fuse_select=True):
     import torch as th
 
     from marl_sap_b200.components.episode_buffer import ReplayBuffer
@@ -233,7 +233,7 @@ def build_runner(w, rank_seed, planes, use_graph=True, selector="epsilon_greedy"
                            obs_agent_id=False, obs_last_action=False, agent_output_type="q", test_nepisode=planes.shape[0],
                            runner_log_interval=10 ** 12, seed=rank_seed, use_mps_action_selection=True,
                            lazy_buffer_fields=tuple(lazy), reuse_episode_batch=True, use_cuda_graph=bool(use_graph),
-                           agent_fc1=agent_fc1, overlap_obs_build=overlap,
+                           agent_fc1=agent_fc1, overlap_obs_build=overlap, fuse_select_step=fuse_select,
                            overlap_submit_order=os.environ.get("SAP_OVERLAP_ORDER", "agent_first"))
     logger = Logger()
     runner = r_REGISTRY["parallel"](args=args, logger=logger)
@@ -310,17 +310,21 @@ class Rollout:
         self.timing = False
         launches = self.launches() - l0
         overlapped = getattr(self.runner, "_overlap", False)
-        if graph or overlapped:
-            # the timed region replayed captured CUDA graphs and / or built the observations on a second stream next to
-            # the agent's GEMMs (no clean per-launch events possible): the env kernel's own launch duration comes from one
-            # extra episode right after it, launched eagerly with the fused step (sap_real_step) alone on the stream
+        fused_sel = getattr(self.runner.args, "fuse_select_step", True)
+        if graph or overlapped or not self.ev_pairs:
+            # the timed region replayed captured CUDA graphs, built the observations on a second stream next to the agent's
+            # GEMMs and / or selected inside the step launch (no clean per-launch events of the env step possible): the
+            # env kernel's own launch duration comes from one extra episode right after it, launched eagerly with the
+            # full step (sap_real_step: rewards + observation build, no selection) alone on the stream
             self.runner.args.use_cuda_graph = False
+            self.runner.args.fuse_select_step = False
             self.runner._overlap = False
             self.timing, self.ev_pairs = True, []
             self.step()
             th.cuda.synchronize()
             self.timing = False
             self.runner.args.use_cuda_graph = graph
+            self.runner.args.fuse_select_step = fused_sel
             self.runner._overlap = overlapped
         ms = e0.elapsed_time(e1)
         kern = sum(a.elapsed_time(b) for a, b in self.ev_pairs) / max(len(self.ev_pairs), 1)
@@ -374,7 +378,8 @@ def gpu_arm(opts, w):
     value = agent_steps / (ms * 1e-3)
     e_ain = 0 if runner.agent_in is None else runner.agent_in.element_size()
     multi_cta = getattr(runner.env, "launches_per_step", 1) == 4
-    runner_overlap = SimpleNamespace(value=bool(getattr(runner, "_overlap", False)) and runner.env.supports_obs_ahead(runner.batch))
+    runner_overlap = SimpleNamespace(value=bool(getattr(runner, "_overlap", False)) and runner.env.supports_obs_ahead(runner.batch),
+                                     fused_select=bool(runner._fused_select()))
 
     # ------------------------------------------------------------------ e2e: host inputs in, host results out
     e2e, e2e_fresh = None, None
@@ -412,6 +417,8 @@ def gpu_arm(opts, w):
                 "rows and fc1 is ONE fp16 tensor-core GEMM against [W0|W1|W2] with fp32 accumulation + a fold/bias/ReLU "
                 "kernel (max rel. error vs float64 9.5e-7; the fp32 sgemm: 1.4e-6)" if other == "fp16_split" else
                 "default fp32 agent: fp32 staging rows, torch/cuBLAS sgemm", agent_fc1=other)
+        variant("separate_selector", "args.fuse_select_step=False: sap_select_epsilon_greedy and the env step as two launches "
+                "(default: sap_rollout_step selects inside the step launch of the overlapped schedule)", agent_fc1=opts.agent_fc1, fuse_select=False)
         variant("fused_step", "args.overlap_obs_build=False: the observation is built inside the step kernel, after the "
                 "selection (one stream; the round-1 schedule)", agent_fc1=opts.agent_fc1, overlap=False)
         free, _ = th.cuda.mem_get_info(dev)
@@ -474,6 +481,7 @@ def gpu_arm(opts, w):
                    "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch",
                    "cuda_graph": bool(graph), "agent_fc1": opts.agent_fc1,
                    "overlap_obs_build": bool(getattr(runner_overlap, "value", False)),
+                   "fuse_select_step": bool(getattr(runner_overlap, "fused_select", False)),
                    "inputs": f"benefit planes {planes.numel() * 4 / 2 ** 30:.1f} GiB per GPU (> 126 MB L2), distinct per env",
                    "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
                    "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy (rebuilt "

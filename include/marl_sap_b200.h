@@ -243,6 +243,31 @@ int sap_select_filtered_epsilon_greedy(const float* q, const int32_t* top, const
 int sap_topm_from_beta(const void* beta, int32_t dtype, int32_t B, int32_t n, int32_t m, int32_t L, int32_t M,
                        int32_t* top_out, void* stream);
 
+/* ---- selection + env step in ONE launch (SURVEY.md 7.4 `sap_rollout_step`) -------------------
+ * What runners/episode_runner.py:75-84 does per timestep after the agent forward - `action_selector.select_action`
+ * (classic_selectors.py:37-54, every action available) followed by `env.step(actions)` (real_constellation_env.py:135-175)
+ * - for B environments at once: the CTA of an env selects its n agents' actions (same Philox keys / injected draws as
+ * sap_select_epsilon_greedy, so the actions are identical), writes them to `actions_out` [B, n] and steps.
+ * top_ahead == null: the full step (sap_real_step; `top`, `plane_stats` required);
+ * top_ahead != null: the observation of slot k + 1 was built by sap_real_obs_ahead into this top-M buffer
+ *   (sap_real_step_after_obs).
+ * Only the shipped configuration on the one-CTA-per-env kernel (sap_rollout_step_ok); other shapes make the two calls. */
+typedef struct SapSelectArgs {
+  const float* q;              /* [B, n, m] fp32, contiguous                                   */
+  const float* eps_dev;        /* nullable: device scalar overriding `eps` (CUDA-graph replays) */
+  const uint64_t* episode_ctr; /* nullable device counter                                       */
+  const float* u_explore;      /* nullable [B*n] injected uniforms (with u_action)              */
+  const float* u_action;
+  uint64_t seed;
+  float eps;
+  int32_t reserved;
+} SapSelectArgs;
+int sap_rollout_step_ok(const SapEnvDims* dims);
+int sap_rollout_step(const SapSelectArgs* sel, const SapEnvDims* dims, const float* planes, const float* plane_stats,
+                     const float* T_trans, double lambda_, int64_t* actions_out, int32_t* k, int32_t* prev,
+                     double* ep_return, int32_t* counts_out, const SapBatchView* view, int32_t* top,
+                     const int32_t* top_ahead, void* stream);
+
 /* sap_sample_categorical = `Categorical(probs).sample()` of the policy-sampling selectors
  *   (action_selectors/classic_selectors.py:15-27 MultinomialActionSelector, :56-64 SoftPoliciesSelector,
  *   filtered_classic_selectors.py:65-102): rows of `A` unnormalised probabilities (masked by `avail` when given).

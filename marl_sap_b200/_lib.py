@@ -44,6 +44,12 @@ class SapBatchView(C.Structure):
     _fields_ = [(k, SapField) for k in VIEW_FIELDS]
 
 
+class SapSelectArgs(C.Structure):
+    """Selector side of ``sap_rollout_step`` (selection + env step in one launch)."""
+    _fields_ = [("q", C.c_void_p), ("eps_dev", C.c_void_p), ("episode_ctr", C.c_void_p), ("u_explore", C.c_void_p),
+                ("u_action", C.c_void_p), ("seed", C.c_uint64), ("eps", C.c_float), ("reserved", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/marl_sap_b200.h one to one
 _P, _I32, _I64, _U64, _F32, _F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
 _DIMS, _VIEW = C.POINTER(SapEnvDims), C.POINTER(SapBatchView)
@@ -79,6 +85,8 @@ SIGNATURES = {
     "sap_real_obs_ahead_ok": (C.c_int, [_DIMS]),
     "sap_real_obs_ahead": (C.c_int, [_DIMS, _P, _P, _P, _VIEW, _P, _P]),
     "sap_real_step_after_obs": (C.c_int, [_DIMS, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P]),
+    "sap_rollout_step_ok": (C.c_int, [_DIMS]),
+    "sap_rollout_step": (C.c_int, [C.POINTER(SapSelectArgs), _DIMS, _P, _P, _P, _F64, _P, _P, _P, _P, _P, _VIEW, _P, _P, _P]),
     "sap_real_beta_rows": (C.c_int, [_DIMS, _P, _P, _P, _I32, _I32, _P, _I32, _P]),
     "sap_real_select_kernel": (C.c_int32, [_I32]),
     "sap_lsa_maximize": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),

@@ -136,6 +136,27 @@ class EpsilonGreedyActionSelector(_KernelSelectorBase):
         return out
 
 
+    def fused_select_args(self, agent_inputs, t_env, test_mode=False):
+        """The same selection as ``select_action`` (every action available), described for ``sap_rollout_step``: the env
+        kernel then selects and steps in one launch.  Returns (SapSelectArgs, actions_out [B, n] int64, keepalive)."""
+        eps = self._eps(t_env, test_mode)
+        _lib.require_cuda(agent_inputs, "agent_inputs")
+        q = agent_inputs.detach()
+        if q.dtype != th.float32:
+            q = q.float()
+        q = q.contiguous()
+        B, n, _ = q.shape
+        out = th.empty(B, n, dtype=th.int64, device=q.device)
+        inj = self._injected or {}
+        self._injected = None
+        ue, ua = inj.get("u_explore"), inj.get("u_action")
+        ctr, _ = self._counters(q.device, B)
+        a = _lib.SapSelectArgs()
+        a.q, a.eps_dev, a.episode_ctr = q.data_ptr(), self._eps_ptr(eps, q.device), _lib.ptr(ctr)
+        a.u_explore, a.u_action, a.seed, a.eps = _lib.ptr(ue), _lib.ptr(ua), self.seed, eps
+        return a, out, (q, ue, ua, ctr)
+
+
 class FilteredEpsilonGreedyActionSelector(_KernelSelectorBase):
     """Epsilon-greedy in the "top-M tasks + anything-else baseline" action space.
 

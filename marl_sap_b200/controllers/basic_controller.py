@@ -48,6 +48,22 @@ class BasicMAC:
             return self.action_selector.select_action(q, avail, t_env, test_mode=test_mode, top=top[bs])
         return self.action_selector.select_action(q, avail, t_env, test_mode=test_mode, beta=ep_batch["beta"][bs, t_ep])
 
+    def supports_select_and_step(self, env, ep_batch):
+        """True when ``select_and_step`` applies: the classic epsilon-greedy selector on Q-values and an env whose step
+        kernel can select its own actions (``sap_rollout_step``)."""
+        return (type(self.action_selector).__name__ == "EpsilonGreedyActionSelector" and self.agent_output_type == "q"
+                and hasattr(self.action_selector, "fused_select_args") and hasattr(env, "supports_select_step")
+                and env.supports_select_step(ep_batch))
+
+    def select_and_step(self, ep_batch, t_ep, t_env, env, test_mode=False, agent_in=None):
+        """``select_actions`` followed by ``env.step`` (episode_runner.py:75-84) as ONE kernel launch after the agent
+        forward: the env's CTA draws / arg-maxes its own agents' actions and steps.  Returns the actions [B, n]."""
+        q = self.forward(ep_batch, t_ep, test_mode=test_mode, action_selection_mode=True)
+        sel, actions, keep = self.action_selector.fused_select_args(q, t_env, test_mode=test_mode)
+        env.step_select(sel, actions, ep_batch, agent_in=agent_in)
+        del keep
+        return actions
+
     def forward(self, ep_batch, t, test_mode=False, action_selection_mode=False):
         outs, self.hidden_states = self.agent(self._build_inputs(ep_batch, t), self.hidden_states)
         if self.agent_output_type == "pi_logits":

@@ -1,6 +1,7 @@
 // Parameters shared by the generic (sap_real.cu) and the fast (sap_real_fast.cu) RealConstellationEnv kernels.
 #pragma once
 #include "sap_common.cuh"
+#include "sap_select.cuh"
 
 struct RealParams {
   SapEnvDims d;
@@ -28,7 +29,11 @@ struct RealParams {
   const int64_t* prev0;   // reset only: [B,n] initial prev_assigns instead of arange(n), or null
   int obs_row;            // elements between consecutive agents' observation rows (0 = obs_size: packed)
   int obs_only;     // sap_real_fast2: build the observation of slot k + 1 only (no rewards, no counters, flags = 0)
-  int large_exact;  // multi-CTA path: exact float64 selection even where the keyed lists would apply (selector override)
+  int large_exact;
+  // sap_rollout_step: when sel.q is set the CTA of an env first selects its agents' actions (classic epsilon-greedy,
+  // everything available) into sel.out == actions, then steps; only the one-CTA-per-env kernels of sap_real_fast2.cu
+  SelParams sel;
+  int sel_vec4;  // multi-CTA path: exact float64 selection even where the keyed lists would apply (selector override)
 };
 
 

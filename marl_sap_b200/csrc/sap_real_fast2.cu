@@ -127,6 +127,28 @@ __device__ __forceinline__ void stg_hint4(void* p, const uint4& v, uint64_t pol)
 }
 __device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
 
+// sap_rollout_step: the env's CTA selects the actions of its own n agents before stepping (the selector's launch and the
+// actions round trip through HBM between two launches disappear).  Warp c handles rows [32 c, 32 c + 32) of the env; the
+// Philox draws are keyed by the global row, the env's step counter and the episode counter exactly as in the stand-alone
+// selector kernel, so the two produce the same actions.  Ends with a barrier: the CTA reads the actions back from global
+// memory (written by its own threads).
+template <int kCtaWarps>
+__device__ __forceinline__ void select_own_actions(const RealParams& p, int b, int n, int T, int tid) {
+  if (p.k[b] < T) {
+    const int lane = tid & 31;
+    for (int c = tid >> 5; c * 32 < n; c += kCtaWarps) {
+      const int64_t base = (int64_t)b * n + c * 32;
+      const int nrows = min(32, n - c * 32);
+      const int a = sap_classic_select_rows(p.sel, base, nrows, p.sel_vec4, lane);
+      if (lane < nrows) p.sel.out[base + lane] = (int64_t)a;
+    }
+  }
+  __syncthreads();
+}
+
+// kSelect: the sap_rollout_step instantiation (selection first); a separate instantiation so that the plain step keeps
+// its register allocation
+template <bool kSelect>
 __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int b = blockIdx.x;
@@ -159,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   // obs_only: the observation of slot k + 1 ahead of the step (it does not depend on the actions of step k apart from the
   // "previous task in my top-M" flags, which sap_real_step_after_obs sets): no rewards, no counters, flags = 0
   const bool stepping = !p.is_reset && !p.obs_only;
+  if (kSelect && stepping) select_own_actions<kWarps>(p, b, n, T, tid);
   int a_mine = 0, pv_mine = 0;
   if (stepping && tid < n) {
     a_mine = min(max((int)p.actions[(size_t)b * n + tid], 0), m - 1);
@@ -962,6 +985,7 @@ __global__ void __launch_bounds__(128) sap_real_step_only_kernel(RealParams p) {
   const SapEnvDims d = p.d;
   const int n = d.n, m = d.m, T = d.T, L = d.L, M = d.M, N = d.N, H = d.M / 2;
   const SapBatchView& vw = p.view;
+  if (p.sel.q) select_own_actions<4>(p, b, n, T, tid);
   const int k_old = p.k[b];
   if (k_old >= T) return;
   const int k_new = k_old + 1;
@@ -1083,6 +1107,61 @@ extern "C" int sap_real_step_after_obs(const SapEnvDims* dims, const float* plan
   return SAP_OK;
 }
 
+extern "C" int sap_rollout_step_ok(const SapEnvDims* dims) { return dims && fast2_dims_ok(*dims) ? 1 : 0; }
+
+extern "C" int sap_rollout_step(const SapSelectArgs* sel, const SapEnvDims* dims, const float* planes, const float* plane_stats,
+                                const float* T_trans, double lambda_, int64_t* actions_out, int32_t* k, int32_t* prev,
+                                double* ep_return, int32_t* counts_out, const SapBatchView* view, int32_t* top,
+                                const int32_t* top_ahead, void* stream) {
+  SAP_REQUIRE(sel && sel->q && dims && planes && actions_out && k && prev && ep_return && view && view->obs.ptr, SAP_E_NULL,
+              "sap_rollout_step: null pointer");
+  SAP_REQUIRE(dims->B > 0 && dims->T > 0 && fast2_dims_ok(*dims), SAP_E_CONSTRAINT,
+              "sap_rollout_step: only the shipped configuration (M = N = 10, L = 3, 64 < n <= 128, m <= 128, n and m multiples "
+              "of 4) selects and steps in one launch; call sap_select_epsilon_greedy + sap_real_step");
+  SAP_REQUIRE((sel->u_explore == nullptr) == (sel->u_action == nullptr), SAP_E_NULL,
+              "sap_rollout_step: u_explore and u_action are injected together");
+  SAP_REQUIRE(top_ahead || (top && plane_stats), SAP_E_NULL, "sap_rollout_step: top / plane_stats is null");
+  RealParams p{};
+  p.d = *dims;
+  p.planes = planes;
+  p.plane_stats = plane_stats;
+  p.ttrans = T_trans;
+  p.lambda_ = lambda_;
+  p.actions = actions_out;
+  p.k = k;
+  p.prev = prev;
+  p.ep_return = ep_return;
+  p.counts_out = counts_out;
+  p.view = *view;
+  p.sel.q = sel->q;
+  p.sel.B = dims->B;
+  p.sel.n = dims->n;
+  p.sel.A = p.sel.m = dims->m;
+  p.sel.eps = sel->eps;
+  p.sel.eps_dev = sel->eps_dev;
+  p.sel.seed = sel->seed;
+  p.sel.episode_ctr = sel->episode_ctr;
+  p.sel.k = k;
+  p.sel.u_explore = sel->u_explore;
+  p.sel.u_action = sel->u_action;
+  p.sel.out = actions_out;
+  p.sel_vec4 = sap_aligned16(sel->q) ? 1 : 0;  // m is a multiple of 4 here
+  if (top_ahead) {  // the observation of the new slot is in place (sap_real_obs_ahead): selection + the light step
+    p.top_out = const_cast<int32_t*>(top_ahead);
+    sap_real_step_only_kernel<<<dims->B, 128, sizeof(int32_t) * (size_t)dims->m, (cudaStream_t)stream>>>(p);
+    SAP_CUDA_LAUNCH_CHECK("sap_real_step_only_kernel");
+    return SAP_OK;
+  }
+  p.top_out = top;
+  int handled = 0;
+  const int rc = sap_real_fast2_try(p, stream, &handled);
+  if (rc != SAP_OK) return rc;
+  SAP_REQUIRE(handled, SAP_E_CONSTRAINT,
+              "sap_rollout_step: the buffers do not meet the one-CTA-per-env kernel's layout (fp16 obs, 16-byte aligned rows, "
+              "per-plane stats); call sap_select_epsilon_greedy + sap_real_step");
+  return SAP_OK;
+}
+
 int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
   *handled = 0;
   const SapEnvDims& d = p.d;
@@ -1110,12 +1189,13 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
   const F2Layout f = f2_layout(d.n, d.m);
   static thread_local bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sap_real_fast2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(sap_real_fast2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e != cudaSuccess) {
-      sap_set_error("sap_real_fast2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
+    for (const void* fn : {(const void*)sap_real_fast2_kernel<false>, (const void*)sap_real_fast2_kernel<true>}) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+      if (e != cudaSuccess) {
+        sap_set_error("sap_real_fast2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+      }
     }
     configured = true;
   }
@@ -1128,7 +1208,8 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
 #else
   p.lookahead = 0;
 #endif
-  sap_real_fast2_kernel<<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
+  if (p.sel.q && !p.is_reset && !p.obs_only) sap_real_fast2_kernel<true><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
+  else sap_real_fast2_kernel<false><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_fast2_kernel");
   return SAP_OK;
 }

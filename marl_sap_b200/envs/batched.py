@@ -298,6 +298,27 @@ class BatchedRealConstellationEnv(_BatchedEnvBase):
         self.t_host += 1
         return self.t_host >= self.T
 
+    def supports_select_step(self, batch):
+        """True when ``step_select`` applies (``sap_rollout_step``: selection + step in one launch)."""
+        return self.supports_obs_ahead(batch) and bool(self.lib.sap_rollout_step_ok(self.dims()))
+
+    def step_select(self, sel, actions_out, batch, agent_in=None):
+        """Epsilon-greedy selection (``sel``: a ``SapSelectArgs`` from the selector's ``fused_select_args``) and the env
+        step in one launch; the chosen actions land in ``actions_out`` [B, n] int64.  Same results as
+        ``selector.select_action`` + ``step``."""
+        view = self._with_agent_in(batch.kernel_view(), agent_in)
+        ahead = self._ahead
+        _lib.check(self.lib.sap_rollout_step(sel, self.dims(), _lib.ptr(self.planes), _lib.ptr(self.plane_stats),
+                                             _lib.ptr(self.T_trans), self.lambda_, actions_out.data_ptr(), _lib.ptr(self.k),
+                                             _lib.ptr(self.prev), _lib.ptr(self.ep_return), _lib.ptr(self.counts), view,
+                                             _lib.ptr(self.top), _lib.ptr(self._top_next) if ahead else None,
+                                             _lib.stream_ptr(self.device)), "sap_rollout_step")
+        self._ahead = False
+        self.t_host += 1
+        if ahead and self.t_host < self.T:
+            self.top, self._top_next = self._top_next, self.top
+        return self.t_host >= self.T
+
     def beta_field(self, dtype=th.float16):
         """The `beta` buffer field [B, T+1, n, m, L] rebuilt from the planes (lazy materialisation)."""
         out = th.empty(self.B, self.T + 1, self.n, self.m, self.L, dtype=dtype, device=self.device)

@@ -261,6 +261,7 @@ class CudaVecRunner:
         self.mac.init_hidden(batch_size=self.batch_size)
         bufs = self._agent_in_bufs
         order = getattr(self.args, "overlap_submit_order", "agent_first")
+        fused = self._fused_select()
         for t in range(self.T):
             nxt = None if bufs is None else bufs[(t + 1) % 2]
             # step t - 1 is done at this point of the main stream: k = t, and nobody reads the rows about to be overwritten
@@ -277,13 +278,23 @@ class CudaVecRunner:
             if bufs is not None:
                 self.batch.agent_in = bufs[t % 2]
             self.batch.top_agent_tasks = self.env.top   # top-M tasks of slot t (slot t + 1's go to the other buffer)
-            actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
-            if order == "agent_first":
-                # submitted AFTER the agent's GEMMs: those take the SMs first and the observation kernel's CTAs (75 KB of
-                # shared memory each) fill what is left, instead of locking the GEMMs out
-                ahead()
-            main.wait_stream(side)
-            self.env.step(actions, self.batch, agent_in=nxt)
+            if fused:
+                # selection happens inside the step launch (sap_rollout_step): only the agent forward precedes it
+                q = self.mac.forward(self.batch, t, test_mode=test_mode, action_selection_mode=True)
+                if order == "agent_first":
+                    ahead()
+                main.wait_stream(side)
+                sel, actions, keep = self.mac.action_selector.fused_select_args(q, self.t_env, test_mode=test_mode)
+                self.env.step_select(sel, actions, self.batch, agent_in=nxt)
+                del keep
+            else:
+                actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+                if order == "agent_first":
+                    # submitted AFTER the agent's GEMMs: those take the SMs first and the observation kernel's CTAs (75 KB
+                    # of shared memory each) fill what is left, instead of locking the GEMMs out
+                    ahead()
+                main.wait_stream(side)
+                self.env.step(actions, self.batch, agent_in=nxt)
             self.batch.agent_in_t = t + 1
             if bufs is not None:
                 self.batch.agent_in = nxt
@@ -291,15 +302,33 @@ class CudaVecRunner:
         self.batch.top_agent_tasks = self.env.top
         self.episode_ctr += 1
 
+    def _fused_select(self):
+        """args.fuse_select_step: the classic epsilon-greedy selection runs inside the env step launch (``sap_rollout_step``)
+        when MAC, selector and env shape allow it (BasicMAC + ``epsilon_greedy`` + the shipped real-env configuration).
+        True (default): with the overlapped schedule, where the step launch is the light ``sap_real_step_after_obs`` kernel;
+        "always": also in front of the full step kernel (measured slower there: the Q rows are read at the head of a kernel
+        that is already latency-bound); False: never."""
+        mode = getattr(self.args, "fuse_select_step", True)
+        if not mode or type(self.mac).__name__ != "BasicMAC" or not hasattr(self.mac, "supports_select_and_step"):
+            return False
+        if mode != "always" and not (self._overlap and self.env.supports_obs_ahead(self.batch)):
+            return False
+        return self.mac.supports_select_and_step(self.env, self.batch)
+
     def _rollout_loop(self, test_mode):
         if self._overlap and self.env.supports_obs_ahead(self.batch):
             return self._rollout_loop_overlapped(test_mode)
         self.mac.init_hidden(batch_size=self.batch_size)
+        fused = self._fused_select()
         for t in range(self.T):
-            # agent forward (torch) + selection kernel; obs / avail / beta for slot t were written by the env kernel
-            actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
-            # fused env kernel: rewards/actions/terminated at slot t, obs/prev_assigns/filled at slot t+1
-            self.env.step(actions, self.batch)
+            if fused:
+                # agent forward (torch), then ONE launch: selection + env step (sap_rollout_step)
+                self.mac.select_and_step(self.batch, t, self.t_env, self.env, test_mode=test_mode)
+            else:
+                # agent forward (torch) + selection kernel; obs / avail / beta for slot t were written by the env kernel
+                actions = self.mac.select_actions(self.batch, t_ep=t, t_env=self.t_env, test_mode=test_mode)
+                # fused env kernel: rewards/actions/terminated at slot t, obs/prev_assigns/filled at slot t+1
+                self.env.step(actions, self.batch)
             self.batch.agent_in_t = t + 1
             self.t += 1
         self.episode_ctr += 1
@@ -363,6 +392,8 @@ class CudaVecRunner:
         per_step = 1 + self.env.launches_per_step  # selector + env kernel(s) per timestep
         if self._overlap and self.env.supports_obs_ahead(self.batch):
             per_step += 1                           # observation kernel + step kernel instead of one fused launch
+        if self._fused_select():
+            per_step -= 1                           # the selector runs inside the step launch
         self.kernel_launches += per_step * self.T
         self.last_episode_returns = self.env.ep_return.clone()
         self._finish_run(test_mode)

@@ -43,15 +43,17 @@ def test_ctypes_structs_match_c_header(tmp_path):
 
     prog = tmp_path / "abi.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "marl_sap_b200.h"\nint main(void){\n'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SapEnvDims), sizeof(SapField), sizeof(SapBatchView),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(SapEnvDims), sizeof(SapField), sizeof(SapBatchView),'
                     ' offsetof(SapField, env_stride), offsetof(SapField, dtype), offsetof(SapBatchView, agent_in),'
-                    ' offsetof(SapEnvDims, shared_planes));\nreturn 0;}\n')
+                    ' offsetof(SapEnvDims, shared_planes), sizeof(SapSelectArgs), offsetof(SapSelectArgs, seed),'
+                    ' offsetof(SapSelectArgs, eps));\nreturn 0;}\n')
     exe = tmp_path / "abi"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.SapEnvDims), ctypes.sizeof(_lib.SapField), ctypes.sizeof(_lib.SapBatchView),
             _lib.SapField.env_stride.offset, _lib.SapField.dtype.offset, _lib.SapBatchView.agent_in.offset,
-            _lib.SapEnvDims.shared_planes.offset]
+            _lib.SapEnvDims.shared_planes.offset, ctypes.sizeof(_lib.SapSelectArgs), _lib.SapSelectArgs.seed.offset,
+            _lib.SapSelectArgs.eps.offset]
     assert got == want
 
 

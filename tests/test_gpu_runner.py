@@ -48,11 +48,22 @@ class DrawInjector:
         self.sel, self.draws, self.t = selector, draws, 0
         self.orig = selector.select_action
         selector.select_action = self
+        if hasattr(selector, "fused_select_args"):  # the selection inside the env step launch (sap_rollout_step)
+            fused = selector.fused_select_args
 
-    def __call__(self, *a, **k):
+            def hooked(*a, **k):
+                self._inject()
+                return fused(*a, **k)
+
+            selector.fused_select_args = hooked
+
+    def _inject(self):
         d = {name: th.tensor(v[self.t]).cuda() for name, v in self.draws.items()}
         self.sel.inject_draws(**d)
         self.t += 1
+
+    def __call__(self, *a, **k):
+        self._inject()
         return self.orig(*a, **k)
 
 
@@ -750,3 +761,89 @@ def test_runner_overlapped_obs_build_equals_fused_step(mode):
             assert th.equal(x[k], y[k]), k
     assert th.equal(ra, rb) and th.equal(ta, tb) and th.equal(pa, pb)
     assert eb[0]["obs"][:, 1:, :, -M:].any() and not th.equal(eb[0]["obs"], eb[1]["obs"])
+
+
+@pytest.mark.parametrize("mode", ["injected", "philox", "graph"])
+@pytest.mark.parametrize("overlap", [False, True])
+def test_runner_fused_select_step_equals_two_launches(mode, overlap):
+    """args.fuse_select_step (default): the epsilon-greedy selection runs inside the env step launch (sap_rollout_step,
+    SURVEY.md 7.4).  Every buffer field, the env state and the returns equal the selector kernel + step kernel schedule,
+    with injected draws and with the in-kernel Philox stream, eagerly and replayed from a CUDA graph."""
+    rng = np.random.default_rng(77)
+    B, n, m, T, L, M, N = 5, 100, 100, 5, 3, 10, 10
+    S = O.gen_dense(rng, B, n, m, T)
+    env_args = dict(num_planes=1, num_sats_per_plane=n, m=m, T=T, N=N, M=M, L=L, lambda_=0.5, sat_prox_mat=S, graphs=1)
+    draws = {"u_explore": rng.random((2 * T, B, n), dtype=np.float32), "u_action": rng.random((2 * T, B, n), dtype=np.float32)}
+    out = []
+    for fuse in (False, True):
+        args = make_args("real_constellation_env", env_args, B, overlap_obs_build=overlap,
+                         fuse_select_step=("always" if fuse else False),
+                         epsilon_start=0.4, epsilon_finish=0.4, obs_agent_id=True, use_cuda_graph=mode == "graph",
+                         reuse_episode_batch=True)
+        runner, mac, buffer, _ = build(args)
+        inj = DrawInjector(mac.action_selector, draws) if mode == "injected" else None
+        eps = []
+        with th.no_grad():
+            for _ in range(3 if mode == "graph" else 2):
+                b = runner.run(test_mode=False)
+                eps.append({k: v.clone() for k, v in b.data.transition_data.items()})
+                if inj is not None and len(eps) == 1:
+                    inj.t = T
+        assert runner._fused_select() == fuse
+        runner.args.fuse_select_step = True   # the default fuses only in front of the light step of the overlapped schedule
+        assert runner._fused_select() == overlap
+        out.append((eps, runner.env.ep_return.clone(), runner.env.top.clone(), runner.env.prev.clone(), runner.env.counts.clone()))
+    (ea, *sa), (eb, *sb) = out
+    for x, y in zip(ea, eb):
+        for k in x:
+            assert th.equal(x[k], y[k]), k
+    for x, y in zip(sa, sb):
+        assert th.equal(x, y)
+    acts = eb[0]["actions"][:, :T, :, 0].long()
+    assert acts.min() >= 0 and acts.max() < m and len(th.unique(acts)) > m // 2
+    assert not th.equal(eb[0]["actions"], eb[1]["actions"])
+
+
+def test_rollout_step_entry_point_matches_selector_plus_step_and_the_oracle():
+    """sap_rollout_step through the C ABI: actions == oracle epsilon-greedy on the same Q and draws, and the step it performs
+    == sap_real_step on those actions (both schedules: full step, and after sap_real_obs_ahead)."""
+    from marl_sap_b200 import _lib
+    from marl_sap_b200.components.episode_buffer import EpisodeBatch
+    from marl_sap_b200.envs.batched import BatchedRealConstellationEnv, real_obs_size, real_scheme
+
+    rng = np.random.default_rng(5)
+    B, n, m, T, L, M, N = 3, 100, 100, 4, 3, 10, 10
+    S = O.gen_dense(rng, B, n, m, T)
+    scheme, preprocess = real_scheme(n, m, L, real_obs_size(M, N, L))
+    eps = 0.35
+
+    def fresh():
+        env = BatchedRealConstellationEnv(B, n, m, T, L, M, N, 0.5, sat_prox_mat=S, device="cuda")
+        batch = EpisodeBatch(scheme, {"agents": n}, B, T + 1, preprocess=preprocess, device="cuda")
+        env.reset(batch)
+        return env, batch
+
+    for ahead in (False, True):
+        (env_a, batch_a), (env_b, batch_b) = fresh(), fresh()
+        state = O.RealState(S.astype(np.float64), L, M, N, 0.5)
+        state.reset()
+        for t in range(T):
+            q = rng.standard_normal((B, n, m)).astype(np.float32)
+            q[:, :, 7] = q[:, :, 3]  # ties: first index wins
+            ue, ua = rng.random((B, n), dtype=np.float32), rng.random((B, n), dtype=np.float32)
+            want = O.select_epsilon_greedy(q, np.ones((B, n, m), bool), eps, ue, ua)
+            qd, ued, uad = th.tensor(q).cuda(), th.tensor(ue).cuda(), th.tensor(ua).cuda()
+            sel = _lib.SapSelectArgs()
+            sel.q, sel.u_explore, sel.u_action, sel.eps, sel.seed = qd.data_ptr(), ued.data_ptr(), uad.data_ptr(), eps, 1
+            acts = th.full((B, n), -1, dtype=th.int64, device="cuda")
+            if ahead:
+                env_a.obs_ahead(batch_a)
+                env_b.obs_ahead(batch_b)
+            env_a.step_select(sel, acts, batch_a)
+            np.testing.assert_array_equal(acts.cpu().numpy(), want)
+            env_b.step(th.tensor(want).cuda(), batch_b)
+            state.step(want)
+        for k in batch_a.data.transition_data:
+            assert th.equal(batch_a.data.transition_data[k], batch_b.data.transition_data[k]), k
+        assert th.equal(env_a.ep_return, env_b.ep_return) and th.equal(env_a.prev, env_b.prev) and th.equal(env_a.k, env_b.k)
+        np.testing.assert_array_equal(env_a.prev.cpu().numpy(), state.prev)
