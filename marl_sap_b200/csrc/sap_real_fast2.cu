@@ -14,8 +14,7 @@
 //   * the gather works on 30-byte SLOTS of the observation row: lane = (rival, half of my top tasks | its other
 //     tasks), i.e. 32 slots = 32 lanes per agent row, five (agent, task) pairs each.  A lane reads one rival index
 //     and five task indices instead of one LUT word and three indices PER PAIR, and writes its 15 halves as
-//     7 words + 1 half;
-//   * the benefit tile is pitched (odd word pitch) so that the ten rivals of a row fall into different banks.
+//     7 words + 1 half.
 // Lists are certified exactly as before (keys are a monotone fixed-point image of the float64 window sum plus an
 // "inexact" bit; an uncertified list is redone by the exact float64 warp selection), so results never depend on the
 // key resolution.

@@ -2,9 +2,12 @@
 
 Replaces /root/reference/src/runners/parallel_runner.py:12-299 (ParallelRunner + env_worker processes +
 pickle over Pipes) and runners/episode_runner.py:8-137 (EpisodeRunner) for the SAP envs: all
-``batch_size_run`` environments live in one device-resident batched env and advance in lockstep: per timestep the
-torch agent forward, one selection kernel and one env kernel (step -> obs(t+1) -> buffer writes; four launches on the
-multi-CTA path of the large shapes).
+``batch_size_run`` environments live in one device-resident batched env and advance in lockstep.  Per timestep: the torch
+agent forward, one selection kernel and one env kernel (step -> obs(t+1) -> buffer writes; four launches on the multi-CTA
+path of the large shapes).  For the shipped real-env configuration at the bench shape the default schedule is instead: the
+observation of slot t + 1 built on a second stream next to the agent forward (``overlap_obs_build``) and ONE launch that
+selects and steps (``fuse_select_step``, ``sap_rollout_step``); the T-step loop can be replayed as a CUDA graph
+(``use_cuda_graph``).
 
 Same surface as the reference runners: ``Runner(args, logger)``, ``setup(scheme, groups, preprocess, mac)``,
 ``get_env()``, ``run(test_mode) -> EpisodeBatch``, ``close_env()``, ``save_replay()``, attributes
@@ -24,8 +27,9 @@ are keyed by the GLOBAL index of its first env, so no two ranks draw the same ex
 is one all-reduce of [sum return, sum return^2, n_episodes, sum ep_length] per ``run()``.
 
 ``compat_parallel_runner_quirks = True`` reproduces what the reference ParallelRunner writes into ``terminated``
-(parallel_runner.py:181-187: the flag is assigned from the truthiness of the per-agent reward LIST, not from the env's
-done flag, so every stored ``terminated`` is True) - off by default, EpisodeRunner semantics otherwise.
+(parallel_runner.py:181-187: the flag comes from list truthiness instead of the env's done flag - env 0 is never marked
+terminated, every other env always) and its extra selection stored at t = T; off by default, EpisodeRunner semantics
+otherwise (golden ``runner_parallel.npz``).
 """
 from __future__ import annotations
 
