@@ -254,6 +254,21 @@ def build_runner(w, rank_seed, planes, use_graph=True, selector="epsilon_greedy"
     return runner, buffer, weights
 
 
+def workload_config(opts, w, world):
+    """The `config` object of the JSON line: the workload only, identical in both arms (implementation switches of the GPU
+    arm go to `impl_config`)."""
+    planes_gib = w["B"] * w["T"] * w["n"] * w["m"] * 4 / 2 ** 30
+    return {"workload": f"{opts.workload}: {w['desc']}, T={w['T']}, L={w['L']}, M={w['M']}, N={w['N']}, {w['env']} env, "
+                        f"{opts.selector} + fc agent(hidden 64)",
+            "envs_per_gpu": w["B"], "agents": w["n"], "tasks": w["m"], "T": w["T"],
+            "step": "runner.run() + ReplayBuffer.insert_episode_batch",
+            "inputs": (f"benefit planes {planes_gib:.1f} GiB per GPU (> 126 MB L2), distinct per env" if planes_gib > 0.2 else
+                       f"benefit planes {planes_gib * 1024:.2f} MiB per GPU: smaller than L2 and not flushed (a latency-bound "
+                       "workload; the L2-independent lines are c2 / c3 / c4)"),
+            "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
+            "parallelism": f"envs block-partitioned, {world} rank(s), no data-path collective"}
+
+
 class Rollout:
     """runner + buffer with per-launch timing of the env kernel and the timed-step helper shared by every measurement."""
 
@@ -476,18 +491,13 @@ def gpu_arm(opts, w):
         "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": opts.steps,
         "warmup": opts.warmup, "ms_per_step": ms / opts.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{opts.workload}: {w['desc']}, T={T}, L={w['L']}, M={w['M']}, N={w['N']}, {w['env']} env, "
-                               f"{opts.selector} + fc agent(hidden 64)",
-                   "envs_per_gpu": B, "agents": n, "tasks": m, "T": T, "step": "runner.run() + ReplayBuffer.insert_episode_batch",
-                   "cuda_graph": bool(graph), "agent_fc1": opts.agent_fc1,
-                   "overlap_obs_build": bool(getattr(runner_overlap, "value", False)),
-                   "fuse_select_step": bool(getattr(runner_overlap, "fused_select", False)),
-                   "inputs": f"benefit planes {planes.numel() * 4 / 2 ** 30:.1f} GiB per GPU (> 126 MB L2), distinct per env",
-                   "env_arithmetic": "f64 sums/rewards on f32 benefits; obs/rewards stored in the scheme dtype",
-                   "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy (rebuilt "
-                                    "on access from the episode's planes); episodes rolled out in place in the replay ring; "
-                                    "variants.eager_buffer has every field materialised",
-                   "parallelism": f"envs block-partitioned, {world} rank(s), no data-path collective"},
+        "config": workload_config(opts, w, world),
+        "impl_config": {"cuda_graph": bool(graph), "agent_fc1": opts.agent_fc1,
+                        "overlap_obs_build": bool(getattr(runner_overlap, "value", False)),
+                        "fuse_select_step": bool(getattr(runner_overlap, "fused_select", False)),
+                        "buffer_fields": "obs/actions/rewards/terminated/filled/prev_assigns eager; beta/avail/onehot lazy "
+                                         "(rebuilt on access from the episode's planes); episodes rolled out in place in the "
+                                         "replay ring; variants.eager_buffer has every field materialised"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": a8, "peak": peak, "unit": "GB/s", "frac": a8 / peak,
                      "traffic": traffic, "kernel": kernel_name,
@@ -761,10 +771,7 @@ def reference_arm(opts, w):
     line = {"impl": "reference", "metric": "agent_steps_per_sec", "value": v, "unit": "agent-steps/s", "n_gpus": world,
             "steps": opts.steps, "warmup": opts.warmup, "ms_per_step": 1e3 * sum(x[1] for x in vals) / len(vals),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{opts.workload}: {w['desc']}, T={T}, L={w['L']}, M={w['M']}, N={w['N']}, {w['env']} env, "
-                                   "epsilon_greedy + fc agent(hidden 64)",
-                       "envs_per_gpu": w["B"], "agents": w["n"], "tasks": w["m"], "T": T,
-                       "step": "runner.run() + ReplayBuffer.insert_episode_batch", "note": note},
+            "config": workload_config(opts, w, world), "note": note,
             "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
