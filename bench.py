@@ -728,6 +728,19 @@ def cpu_baseline(w, weights, seconds):
         try:
             v, cores, sample, _ = reference_throughput(w, weights, seconds)
             out = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "reference", "sample": sample}
+            # also the reference's EpisodeRunner on one core and the reference env alone
+            # (step + get_pretransition_data, no agent, no buffer) for the kernel-vs-kernel comparison
+            T_s = min(w["T"], 12 if w["n"] * w["m"] >= 2500 else 40)
+            name, env_args = RR.reference_env_args(w, T=T_s, seed=7)
+            try:
+                out["episode_runner_1core"] = {"value": RR.time_reference_episode_runner(name, env_args, weights=weights),
+                                               "unit": "agent-steps/s", "cores": 1,
+                                               "sample": f"reference EpisodeRunner, one process, T={T_s}, median of 2 episodes"}
+                es = RR.time_reference_env_only(name, env_args)
+                out["env_only_1core"] = {"value": es, "unit": "env-steps/s", "agent_steps_per_s": es * w["n"], "cores": 1,
+                                         "sample": f"reference env.step + get_pretransition_data, random actions, T={T_s}, 2 episodes"}
+            except Exception as e:
+                out["episode_runner_1core"] = {"value": None, "error": f"{type(e).__name__}: {e}"[:200]}
         except Exception as e:
             out = None
             err = f"{type(e).__name__}: {e}"[:200]

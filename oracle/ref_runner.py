@@ -106,6 +106,49 @@ def time_reference_rollout(env_name, env_args, procs, weights=None, episodes=3, 
     return per_ep / med, med, per_ep
 
 
+def time_reference_episode_runner(env_name, env_args, weights=None, episodes=2, warmup=1):
+    """the reference's EpisodeRunner, one process, one core.  Returns agent-steps/s."""
+    import torch as th
+
+    th.set_num_threads(1)
+    args = make_args(env_name, env_args, 1, runner="episode")
+    runner, mac, buffer, _ = build_reference_runner(args, weights)
+    per_ep = args.n * args.T
+    times = []
+    with th.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        for i in range(warmup + episodes):
+            t0 = time.perf_counter()
+            batch = runner.run(test_mode=False)
+            buffer.insert_episode_batch(batch)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    times.sort()
+    return per_ep / times[len(times) // 2]
+
+
+def time_reference_env_only(env_name, env_args, episodes=2):
+    """the reference env alone on one core - ``step(actions)`` + ``get_pretransition_data()`` with uniform
+    random actions, no agent, no buffer (the kernel-vs-kernel comparison).  Returns env-steps/s."""
+    from oracle import ref_import
+
+    R = ref_import.ref_modules()
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = R.envs.REGISTRY[env_name](**env_args)
+    rng = np.random.default_rng(0)
+    steps, total = 0, 0.0
+    for _ in range(episodes):
+        env.reset()
+        done = False
+        while not done:
+            a = rng.integers(0, env.m, size=env.n)
+            t0 = time.perf_counter()
+            _, done, _ = env.step(a)
+            env.get_pretransition_data()
+            total += time.perf_counter() - t0
+            steps += 1
+    return steps / total
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0)) or 1
