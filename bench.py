@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -459,9 +460,13 @@ def gpu_arm(opts, w):
             strong = {"value": B * n * T * opts.steps / (sms * 1e-3), "unit": "agent-steps/s", "total_envs": B, "envs_per_gpu": Bl,
                       "ms_per_step": sms / opts.steps, "us_per_timestep": 1e3 * sms / opts.steps / T, "env_kernel_ms": sk,
                       "env_kernel_frac_8d": a8 / peak,
-                      "limiter": (f"{Bl} one-CTA envs on {148 * 3} resident CTA slots = {Bl / (148 * 3):.2f} waves: the env kernel "
-                                  "runs a partial wave and the agent GEMMs shrink with it; what remains per timestep is launch / "
-                                  "graph-node latency of the ~8 kernels of a timestep") if ctas else "multi-CTA path",
+                      "efficiency_vs_weak": (B * n * T * opts.steps / (sms * 1e-3)) / value,
+                      "limiter": (f"kernel time, not launches: {Bl} one-CTA envs on {148 * 3} resident CTA slots = "
+                                  f"{Bl / (148 * 3):.2f} waves, so the observation kernel needs {math.ceil(Bl / (148 * 3))} "
+                                  f"full env latencies ({sk * 1e3:.0f} us per launch measured alone) and the agent's SIMT sgemms on "
+                                  f"{Bl * n} rows take most of the rest of the {1e3 * sms / opts.steps / T:.0f} us timestep; the two "
+                                  "take turns on the SMs (an observation CTA needs 75 KB of shared memory and 20 K registers)")
+                      if ctas else "multi-CTA path",
                       "note": "batch_size_run_is_global=True: utils.dist.env_partition block-partitions the envs, no data-path "
                               "collective; CUDA-graph replay of the T-step loop" if graph else "eager launches"}
             del x, r, bf

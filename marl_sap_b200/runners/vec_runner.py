@@ -373,14 +373,22 @@ class CudaVecRunner:
             g = th.cuda.CUDAGraph()
             th.cuda.synchronize(self.device)
             t_host = self.env.t_host
+            agent = getattr(self.mac, "agent", None)
+            a0 = getattr(agent, "kernel_launches", 0)
             with th.cuda.graph(g):
                 self._rollout_loop(test_mode)
             self.env.t_host = t_host  # capture only recorded the launches
             self.t = 0
-            entry = (g, self.batch, extras)
+            # this repo's kernels inside the agent forward (bias / ReLU epilogues) per captured episode: the host counter
+            # does not advance on a replay, so the replay adds them
+            entry = (g, self.batch, extras, getattr(agent, "kernel_launches", 0) - a0)
+            if agent is not None and entry[3]:
+                agent.__dict__["kernel_launches"] = a0
             graphs[key] = entry
         g = entry[0]
         g.replay()
+        if entry[3]:
+            self.mac.agent.__dict__["kernel_launches"] = getattr(self.mac.agent, "kernel_launches", 0) + entry[3]
         self.env.t_host += self.T
         self.t = self.T
         self.batch.agent_in_t = self.T
