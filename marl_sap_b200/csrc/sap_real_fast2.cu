@@ -36,9 +36,21 @@ constexpr int kRows = kWarps;                   // observation rows staged per p
 constexpr size_t kMaxSmem = 227 * 1024 - 1024;
 
 #ifdef SAP_ABLATE
+// profiling builds only: SAP_DEBUG_SKIP_REDO == k ends the kernel after phase k (timing ablation); == 99 makes thread 0 of
+// every CTA record %globaltimer at the phase boundaries into p.scratch[b * 16 + k] (phase timeline, profiles/phase_timeline.py)
+__device__ __forceinline__ unsigned long long sap_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SAP_TS(k)                                                                                        \
+  if (p.debug_skip_redo == 99 && threadIdx.x == 0 && p.scratch)                                          \
+    reinterpret_cast<unsigned long long*>(p.scratch)[(size_t)blockIdx.x * 16 + (k)] = sap_globaltimer();
 #define SAP_STOP_AFTER(k)                      \
-  if (p.debug_skip_redo == (k)) return;  // timing ablation: the kernel ends after phase k (profiling builds only)
+  SAP_TS(k)                                    \
+  if (p.debug_skip_redo == (k)) return;
 #else
+#define SAP_TS(k)
 #define SAP_STOP_AFTER(k)
 #endif
 
@@ -180,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   // obs_only: the observation of slot k + 1 ahead of the step (it does not depend on the actions of step k apart from the
   // "previous task in my top-M" flags, which sap_real_step_after_obs sets): no rewards, no counters, flags = 0
   const bool stepping = !p.is_reset && !p.obs_only;
+  SAP_TS(0)
   if (kSelect && stepping) select_own_actions<kWarps>(p, b, n, T, tid);
   int a_mine = 0, pv_mine = 0;
   if (stepping && tid < n) {
@@ -866,8 +879,14 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   const bool odd = slot & 1;
   const uint32_t slot_off = 30u * slot;
   const bool ain_on = ain != nullptr;
+#ifdef SAP_ABLATE
+  long long dbg_gather = 0, dbg_store = 0, dbg_t0 = 0;
+#endif
   for (int r0 = 0; r0 < n; r0 += kRows) {
     const int rows = min(kRows, n - r0);
+#ifdef SAP_ABLATE
+    dbg_t0 = clock64();
+#endif
     unsigned char* gdst = reinterpret_cast<unsigned char*>(obs_out) + (size_t)r0 * kRowBytes;
     if (warp < rows) {
       const int i = r0 + warp;
@@ -909,6 +928,10 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     // generic-proxy writes of the staged rows must be visible to the async proxy (TMA) before the barrier
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+#ifdef SAP_ABLATE
+    const long long dbg_t1 = clock64();
+    dbg_gather += dbg_t1 - dbg_t0;
+#endif
     const uint32_t bytes = (uint32_t)rows * kRowBytes;
     // the obs rows leave shared memory with ONE TMA bulk store issued by thread 0; meanwhile all threads widen the
     // same rows to fp32 for the agent network (128-bit stores)
@@ -968,8 +991,22 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     // the staging rows may be overwritten once the bulk store has finished READING them
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
+#ifdef SAP_ABLATE
+    dbg_store += clock64() - dbg_t1;
+#endif
   }
   if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores complete before exit
+  SAP_TS(7)
+#ifdef SAP_ABLATE
+  if (p.debug_skip_redo == 99 && tid == 0 && p.scratch) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* ts = reinterpret_cast<unsigned long long*>(p.scratch) + (size_t)blockIdx.x * 16;
+    ts[8] = smid;
+    ts[9] = (unsigned long long)dbg_gather;   // SM cycles spent gathering (sum over the row blocks)
+    ts[10] = (unsigned long long)dbg_store;   // ... and storing
+  }
+#endif
 }
 
 }  // namespace
