@@ -167,7 +167,9 @@ enum {
   SAP_REAL_PATH_GENERIC = 1,
   SAP_REAL_PATH_LARGE_KEYED = 2,
   SAP_REAL_PATH_LARGE_EXACT = 3,
-  SAP_REAL_PATH_FAST_GEN1 = 4
+  SAP_REAL_PATH_FAST_GEN1 = 4,
+  SAP_REAL_PATH_FAST_RUNTIME_SHAPE = 5 /* AUTO, but the one-CTA-per-env kernel reads n, m at run time also at 100 x 100,
+                                          where AUTO launches the instantiation with the shape compiled in */
 };
 int32_t sap_real_select_kernel(int32_t which);
 

@@ -16,8 +16,10 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "build")
-LIB_PATH = os.path.join(PKG, "libmarl_sap_b200.so")
+# SAP_ABLATE=1 builds (and _lib.py then loads) a SEPARATE library with the profiling hooks, next to the release one
+ABLATE = os.environ.get("SAP_ABLATE") == "1"
+OBJ = os.path.join(PKG, "build_ablate" if ABLATE else "build")
+LIB_PATH = os.path.join(PKG, "libmarl_sap_b200_ablate.so" if ABLATE else "libmarl_sap_b200.so")
 STAMP = os.path.join(OBJ, "libmarl_sap_b200.stamp")
 SOURCES = ["sap_real.cu", "sap_real_fast.cu", "sap_real_fast2.cu", "sap_real_large.cu", "sap_mock.cu", "sap_select.cu",
            "sap_lsa.cu", "sap_buffer.cu", "sap_power.cu", "sap_proximity.cu"]
@@ -33,7 +35,7 @@ def nvcc_path() -> str:
 
 def _extra_flags() -> list[str]:
     # SAP_ABLATE=1 compiles the timing-ablation / forced-path hooks into the kernels (profiling builds only)
-    return ["-DSAP_ABLATE=1"] if os.environ.get("SAP_ABLATE") == "1" else []
+    return ["-DSAP_ABLATE=1"] if ABLATE else []
 
 
 def _headers() -> list[str]:

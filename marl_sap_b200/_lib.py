@@ -10,7 +10,8 @@ import os
 import torch
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libmarl_sap_b200.so")
+# SAP_ABLATE=1: the profiling build with the timing-ablation hooks (SAP_ABLATE=1 python -m marl_sap_b200._build)
+LIB_PATH = os.path.join(PKG, "libmarl_sap_b200_ablate.so" if os.environ.get("SAP_ABLATE") == "1" else "libmarl_sap_b200.so")
 
 SAP_F32, SAP_F16, SAP_I64, SAP_I16, SAP_I32, SAP_U8 = range(6)
 
@@ -150,7 +151,8 @@ def field_of(t, B_T_leading: bool = True) -> SapField:
     return f
 
 
-REAL_PATH_AUTO, REAL_PATH_GENERIC, REAL_PATH_LARGE_KEYED, REAL_PATH_LARGE_EXACT, REAL_PATH_FAST_GEN1 = range(5)
+(REAL_PATH_AUTO, REAL_PATH_GENERIC, REAL_PATH_LARGE_KEYED, REAL_PATH_LARGE_EXACT, REAL_PATH_FAST_GEN1,
+ REAL_PATH_FAST_RUNTIME_SHAPE) = range(6)
 
 
 class select_real_kernel:

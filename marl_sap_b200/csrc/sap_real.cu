@@ -319,7 +319,7 @@ int launch(RealParams& p, void* stream) {
                 "sap_real: the power / interference envs run on the one-CTA-per-env generic kernel, which needs the window "
                 "sums of an env in shared memory (n=%d m=%d does not fit)", d.n, d.m);
   }
-  if (!extras && path != SAP_REAL_PATH_AUTO && path != SAP_REAL_PATH_FAST_GEN1)  // every other kernel widens into an fp32 agent_in
+  if (!extras && path != SAP_REAL_PATH_AUTO && path != SAP_REAL_PATH_FAST_GEN1 && path != SAP_REAL_PATH_FAST_RUNTIME_SHAPE)  // every other kernel widens into an fp32 agent_in
     SAP_REQUIRE(!p.view.agent_in.ptr || p.view.agent_in.dtype == SAP_F32, SAP_E_DTYPE, "sap_real: agent_in must be f32");
   if (!extras && (path == SAP_REAL_PATH_LARGE_KEYED || path == SAP_REAL_PATH_LARGE_EXACT)) {
     p.large_exact = path == SAP_REAL_PATH_LARGE_EXACT;
@@ -352,8 +352,10 @@ int launch(RealParams& p, void* stream) {
 
 }  // namespace
 
+int sap_real_path_override() { return g_real_path.load(std::memory_order_relaxed); }
+
 extern "C" int32_t sap_real_select_kernel(int32_t which) {
-  if (which < SAP_REAL_PATH_AUTO || which > SAP_REAL_PATH_FAST_GEN1) return -1;
+  if (which < SAP_REAL_PATH_AUTO || which > SAP_REAL_PATH_FAST_RUNTIME_SHAPE) return -1;
   return g_real_path.exchange(which);
 }
 

@@ -111,6 +111,8 @@ __device__ __forceinline__ void warp_select_cached(int len, int count, bool idx_
 int sap_real_fast_try(RealParams& p, void* stream, int* handled, bool gen1_only = false);
 // Second-generation kernel for the shipped configuration (M = N = 10, L = 3, fp16) at 64 < n <= 128 (sap_real_fast2.cu).
 int sap_real_fast2_try(RealParams& p, void* stream, int* handled);
+// current sap_real_select_kernel override (sap_real.cu)
+int sap_real_path_override();
 
 // One environment spread over many CTAs, for shapes whose window sums do not fit shared memory (sap_real_large.cu).
 int sap_real_large_launch(RealParams& p, void* stream);

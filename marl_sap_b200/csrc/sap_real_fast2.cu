@@ -159,12 +159,14 @@ __device__ __forceinline__ void select_own_actions(const RealParams& p, int b, i
 
 // kSelect: the sap_rollout_step instantiation (selection first); a separate instantiation so that the plain step keeps
 // its register allocation
-template <bool kSelect>
+// kFixed: n = m = kFixed known at compile time (the bench shape 100 x 100: every tile pitch, loop bound and layout offset
+// folds into an immediate); 0 = any eligible shape
+template <bool kSelect, int kFixed>
 __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int b = blockIdx.x;
   const SapEnvDims d = p.d;
-  const int n = d.n, m = d.m, T = d.T;
+  const int n = kFixed ? kFixed : d.n, m = kFixed ? kFixed : d.m, T = d.T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nm = n * m;
   const F2Layout f = f2_layout(n, m);
@@ -1225,7 +1227,8 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
   const F2Layout f = f2_layout(d.n, d.m);
   static thread_local bool configured = false;
   if (!configured) {
-    for (const void* fn : {(const void*)sap_real_fast2_kernel<false>, (const void*)sap_real_fast2_kernel<true>}) {
+    for (const void* fn : {(const void*)sap_real_fast2_kernel<false, 0>, (const void*)sap_real_fast2_kernel<true, 0>,
+                           (const void*)sap_real_fast2_kernel<false, 100>, (const void*)sap_real_fast2_kernel<true, 100>}) {
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
       if (e != cudaSuccess) {
@@ -1244,8 +1247,12 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
 #else
   p.lookahead = 0;
 #endif
-  if (p.sel.q && !p.is_reset && !p.obs_only) sap_real_fast2_kernel<true><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
-  else sap_real_fast2_kernel<false><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
+  const bool sel = p.sel.q && !p.is_reset && !p.obs_only;
+  const bool fixed100 = d.n == 100 && d.m == 100 && sap_real_path_override() != SAP_REAL_PATH_FAST_RUNTIME_SHAPE;
+  if (sel && fixed100) sap_real_fast2_kernel<true, 100><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
+  else if (sel) sap_real_fast2_kernel<true, 0><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
+  else if (fixed100) sap_real_fast2_kernel<false, 100><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
+  else sap_real_fast2_kernel<false, 0><<<d.B, kThreads, f.total, (cudaStream_t)stream>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_fast2_kernel");
   return SAP_OK;
 }

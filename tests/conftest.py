@@ -27,7 +27,8 @@ def golden_dir():
 def real_kernel_path():
     """Run the real-env step on a named kernel path for the rest of the test (``sap_real_select_kernel``):
     0 automatic, 1 generic one-CTA-per-env kernel, 2 / 3 multi-CTA path (keyed lists / exact float64 selection),
-    4 first-generation shared-memory kernel.  Reset to automatic afterwards."""
+    4 first-generation shared-memory kernel, 5 automatic but with the run-time-shape instantiation of the bench kernel at
+    100 x 100.  Reset to automatic afterwards."""
     from marl_sap_b200 import _lib
 
     lib = _lib.load()
