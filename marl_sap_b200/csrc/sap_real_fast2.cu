@@ -32,7 +32,7 @@ constexpr int kPairs = kM + kN * kM + kN * kH;  // 160 (agent, task) pairs per o
 constexpr int kObs = kPairs * kL + kM;          // 490
 constexpr int kRowBytes = kObs * 2;             // 980
 constexpr int kKP = 128;                        // key tile pitch in words
-constexpr int kRows = kWarps;                   // observation rows staged per pass
+constexpr int kStagePitch = 1008;                // per-warp staging row: 980 bytes + up to 12 of misalignment, 16-byte pitch
 constexpr size_t kMaxSmem = 227 * 1024 - 1024;
 
 #ifdef SAP_ABLATE
@@ -62,7 +62,7 @@ __device__ __forceinline__ unsigned long long sap_globaltimer() {
   }
 
 struct F2Layout {
-  uint32_t D, nbr, other;                    // live through the whole kernel
+  uint32_t D, nbr, other, pv;                // live through the whole kernel
   uint32_t KT, E, dmask, cnt, red, queue, stage1;  // overlay 1: list building
   uint32_t t01, t2, stage;                   // overlay 2: gather
   uint32_t total;
@@ -77,6 +77,7 @@ __host__ __device__ inline F2Layout f2_layout(int n, int m) {
   f.D = off;     off = up16(off + n * kM);
   f.nbr = off;   off = up16(off + n * kN);
   f.other = off; off = up16(off + n * kN * kH);
+  f.pv = off;    off = up16(off + n);
   const uint32_t base = (off + 127u) & ~127u;
   off = base;
   f.KT = off;    off += 4u * ((m + 7) & ~7) * kKP;  // rows m .. 8 ceil(m / 8) hold zero keys (list padding)
@@ -93,7 +94,7 @@ __host__ __device__ inline F2Layout f2_layout(int n, int m) {
   off = base;
   f.t01 = off;   off = up16(off + 4u * n * f.p01);
   f.t2 = off;    off = up16(off + 2u * n * f.p2);
-  f.stage = off; off = up16(off + (uint32_t)kRows * kRowBytes);
+  f.stage = off; off = up16(off + (uint32_t)kWarps * kStagePitch);
   const uint32_t end2 = off;
   f.total = end1 > end2 ? end1 : end2;
   return f;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
   uint8_t* sD = smem + f.D;                                     // [n][10] top-M tasks (value desc, idx asc)
   uint8_t* sNbr = smem + f.nbr;                                 // [n][10] rivals
   uint8_t* sOther = smem + f.other;                             // [n][10][5] rivals' other tasks (ascending value)
+  uint8_t* sPrev = smem + f.pv;                                 // [n] previous task of every agent (0xff: none, obs_only)
   uint32_t* KT = reinterpret_cast<uint32_t*>(smem + f.KT);      // [m][128] keys, column group g of row j at g ^ (j & 3)
   uint8_t* sE = smem + f.E;                                     // [n][16] top-15 tasks (value desc, idx DESC)
   uint32_t* sMask = reinterpret_cast<uint32_t*>(smem + f.dmask);  // [n][4] membership bits of D[i]
@@ -201,6 +203,9 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     a_mine = min(max((int)p.actions[(size_t)b * n + tid], 0), m - 1);
     pv_mine = p.prev[(size_t)b * n + tid];
   }
+  // what the flag columns of the new rows compare with (:222): the task just taken, i at reset, nothing when the
+  // observation is built ahead of the step (sap_real_step_after_obs sets those flags)
+  if (tid < n) sPrev[tid] = (uint8_t)(p.obs_only ? 0xff : (p.is_reset ? tid : a_mine));
   const int k_old = p.is_reset ? -1 : p.k[b];
   if (!p.is_reset && k_old >= T) return;
   const int k_new = k_old + 1;
@@ -665,6 +670,8 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     }
     *reinterpret_cast<uint4*>(sMask + i * 4) = make_uint4(w0, w1, w2, w3);
   }
+  if (p.top_out)  // the top-M lists are final: one coalesced pass instead of ten lanes per row in the gather
+    for (int e = tid; e < n * kM; e += kThreads) p.top_out[(size_t)b * n * kM + e] = sD[e];
 
   SAP_STOP_AFTER(3)
   // ------------------------------------------------------------------ 6. rivals (:203-206)
@@ -884,15 +891,28 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
 #ifdef SAP_ABLATE
   long long dbg_gather = 0, dbg_store = 0, dbg_t0 = 0;
 #endif
-  for (int r0 = 0; r0 < n; r0 += kRows) {
-    const int rows = min(kRows, n - r0);
+  // Every warp owns ONE staging row and works through rows warp, warp + 8, ... on its own: gather the row, read it back
+  // in 128-bit pieces, store it as the fp16 observation row and widened to fp32 for the agent network.  No block barrier
+  // and no wait for a bulk store inside the phase: while one warp gathers, others store (the phase used to cost two
+  // barriers and one TMA read-completion wait per 8 rows, profiles/r02_phase_timeline.txt).
+  // A row is 980 bytes, so row i starts 4 (i & 3) bytes past a 16-byte boundary in global memory; the staging row is
+  // placed at the same offset, which makes every 16-byte piece of the row aligned on both sides.  2 x 245 floats per row
+  // keep the same property for the packed fp32 rows.
+  constexpr int kRowWords = kRowBytes / 4;  // 245
+  unsigned char* wstage = stage + warp * kStagePitch;
+  const bool ain_on_rt =
+#ifdef SAP_ABLATE
+      ain_on && p.debug_skip_redo != 8;  // 8: fp16 obs store only, no fp32 agent-input copy
+#else
+      ain_on;
+#endif
+  for (int i = warp; i < n; i += kWarps) {
 #ifdef SAP_ABLATE
     dbg_t0 = clock64();
 #endif
-    unsigned char* gdst = reinterpret_cast<unsigned char*>(obs_out) + (size_t)r0 * kRowBytes;
-    if (warp < rows) {
-      const int i = r0 + warp;
-      unsigned char* srow = stage + warp * kRowBytes;
+    const int mis = i & 3;
+    unsigned char* srow = wstage + 4 * mis;
+    {
       const int a = is_own ? i : (int)sNbr[i * kN + gp];
       const uint8_t* jp = smem + idx_base + i * idx_stride;
       const uint32_t* r01 = t01 + a * f.p01;
@@ -921,83 +941,70 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
       *reinterpret_cast<uint16_t*>(srow + slot_off + (odd ? 0u : 28u)) = (uint16_t)(odd ? w[0] : h[4]);
       // "is my previous task among my top-M" flags (:222)
       if (lane < kM) {
-        const int pv = p.obs_only ? -1 : p.prev[(size_t)b * n + i];
+        const int pv = sPrev[i];
         const int j = sD[i * kM + lane];
         reinterpret_cast<uint16_t*>(srow)[kPairs * kL + lane] = j == pv ? (uint16_t)0x3c00u : (uint16_t)0u;
-        if (p.top_out) p.top_out[((size_t)b * n + i) * kM + lane] = j;
       }
     }
-    // generic-proxy writes of the staged rows must be visible to the async proxy (TMA) before the barrier
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    __syncwarp();
 #ifdef SAP_ABLATE
     const long long dbg_t1 = clock64();
     dbg_gather += dbg_t1 - dbg_t0;
+    if (p.debug_skip_redo == 7) continue;  // gather only: no stores
 #endif
-    const uint32_t bytes = (uint32_t)rows * kRowBytes;
-    // the obs rows leave shared memory with ONE TMA bulk store issued by thread 0; meanwhile all threads widen the
-    // same rows to fp32 for the agent network (128-bit stores)
-#ifdef SAP_ABLATE
-    if (p.debug_skip_redo == 7) {  // gather only: no stores
-      __syncthreads();
-      continue;
-    }
-    const bool ain_on_ = ain_on && p.debug_skip_redo != 8;  // 8: fp16 obs store only, no fp32 agent-input copy
-#else
-    const bool ain_on_ = ain_on;
-#endif
-    if (tid == 0) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
-                   "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes), "l"(pol_drop)
-                   : "memory");
-      if (ain16_bulk)
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ain16 + (size_t)r0 * kObs),
-                     "r"((uint32_t)__cvta_generic_to_shared(stage)), "r"(bytes)
-                     : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    if (ain_on_ && !ain32_flat) {  // pitched fp32 rows: two floats per 32-bit word of the staged fp16 row
-      constexpr int kRowWords = kRowBytes / 4;
-      const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(stage);
-      for (int r = warp; r < rows; r += kWarps) {
-        float2* drow = reinterpret_cast<float2*>(ain + (size_t)(r0 + r) * ain32_pitch);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(srow);
+    uint32_t* gobs = reinterpret_cast<uint32_t*>(obs_out) + (size_t)i * kRowWords;
+    const int w0 = (4 - mis) & 3;             // first word of the row that starts a 16-byte piece
+    const int ng = (kRowWords - w0) >> 2;     // whole 16-byte pieces (60 or 61)
+    const int tail0 = w0 + 4 * ng, nfrag = w0 + (kRowWords - tail0);  // <= 6 words outside the pieces
+    const int fw = lane < w0 ? lane : tail0 + lane - w0;  // this lane's head / tail word (lanes < nfrag)
+    const bool flat32 = ain_on_rt && ain32_flat;
 #pragma unroll
-        for (int w = lane; w < kRowWords; w += 32) {
-          const uint32_t hw = ssrc[r * kRowWords + w];
-          drow[w] = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+    for (int u = 0; u < 2; ++u) {
+      const int g = lane + 32 * u;
+      if (g < ng) {
+        const int wq = w0 + 4 * g;
+        const uint4 v = *reinterpret_cast<const uint4*>(sw + wq);
+        stg_hint4(gobs + wq, v, pol_drop);
+        if (flat32) {
+          const __half2* hh = reinterpret_cast<const __half2*>(&v);
+          const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]), f2 = __half22float2(hh[2]),
+                       f3 = __half22float2(hh[3]);
+          float* o = ain + (size_t)i * kObs + 2 * wq;
+          const float4 lo4 = make_float4(f0.x, f0.y, f1.x, f1.y), hi4 = make_float4(f2.x, f2.y, f3.x, f3.y);
+          stg_hint4(o, *reinterpret_cast<const uint4*>(&lo4), pol_drop);
+          stg_hint4(o + 4, *reinterpret_cast<const uint4*>(&hi4), pol_drop);
+        } else if (ain16_bulk) {  // packed fp16 staging rows: the same bytes a second time
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(ain16) + (size_t)i * kRowWords + wq) = v;
         }
       }
-    } else if (ain_on_) {
-      float* adst = ain + (size_t)r0 * kObs;
-      const int chunks = (int)(bytes >> 4);
-#pragma unroll 4
-      for (int c = tid; c < chunks; c += kThreads) {
-        const uint4 v = *reinterpret_cast<const uint4*>(stage + (size_t)c * 16);
-        const __half2* hh = reinterpret_cast<const __half2*>(&v);
-        const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]), f2 = __half22float2(hh[2]),
-                     f3 = __half22float2(hh[3]);
-        float* o = adst + (size_t)c * 8;
-        const float4 lo4 = make_float4(f0.x, f0.y, f1.x, f1.y), hi4 = make_float4(f2.x, f2.y, f3.x, f3.y);
-        stg_hint4(o, *reinterpret_cast<const uint4*>(&lo4), pol_drop);
-        stg_hint4(o + 4, *reinterpret_cast<const uint4*>(&hi4), pol_drop);
+    }
+    if (lane < nfrag) {
+      const uint32_t hw = sw[fw];
+      gobs[fw] = hw;
+      if (flat32)
+        *reinterpret_cast<float2*>(ain + (size_t)i * kObs + 2 * fw) = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+      else if (ain16_bulk)
+        (reinterpret_cast<uint32_t*>(ain16) + (size_t)i * kRowWords)[fw] = hw;
+    }
+    if (ain_on_rt && !ain32_flat) {  // pitched fp32 rows (the MAC appends columns): two floats per word of the fp16 row
+      float2* drow = reinterpret_cast<float2*>(ain + (size_t)i * ain32_pitch);
+#pragma unroll
+      for (int w = lane; w < kRowWords; w += 32) {
+        const uint32_t hw = sw[w];
+        drow[w] = __half22float2(*reinterpret_cast<const __half2*>(&hw));
       }
     }
     if (ain16 && !ain16_bulk) {  // padded fp16 rows: 245 words per row, coalesced 32-bit stores
-      constexpr int kRowWords = kRowBytes / 4;
-      const uint32_t* ssrc = reinterpret_cast<const uint32_t*>(stage);
-      uint32_t* adst = reinterpret_cast<uint32_t*>(ain16 + (size_t)r0 * ain16_pitch);
-      for (int r = warp; r < rows; r += kWarps)
+      uint32_t* adst = reinterpret_cast<uint32_t*>(ain16 + (size_t)i * ain16_pitch);
 #pragma unroll
-        for (int w = lane; w < kRowWords; w += 32) adst[r * (ain16_pitch >> 1) + w] = ssrc[r * kRowWords + w];
+      for (int w = lane; w < kRowWords; w += 32) adst[w] = sw[w];
     }
-    // the staging rows may be overwritten once the bulk store has finished READING them
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncthreads();
+    __syncwarp();  // the row is rewritten by this warp's next gather
 #ifdef SAP_ABLATE
     dbg_store += clock64() - dbg_t1;
 #endif
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores complete before exit
   SAP_TS(7)
 #ifdef SAP_ABLATE
   if (p.debug_skip_redo == 99 && tid == 0 && p.scratch) {
