@@ -181,9 +181,10 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
   return r;
 }
 
-template <typename OutT_, typename IdxT_, bool kPrios_, bool kCommon_, int kTPL_ = 2>
+template <typename OutT_, typename IdxT_, bool kPrios_, bool kCommon_, int kTPL_ = 2, int kFixed_ = 0>
 struct Cfg {
   static constexpr int kTPL = kTPL_;
+  static constexpr int kFixed = kFixed_;  // n = m = kFixed compiled in (BASELINE config 50 x 50); 0 = read at run time
   static constexpr int kMinBlocks = kTPL_ == 4 ? 5 : 3;  // small shapes need little shared memory: more CTAs per SM
   using OutT = OutT_;
   using IdxT = IdxT_;
@@ -197,7 +198,13 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   using IdxT = typename C::IdxT;
   constexpr bool kPrios = C::kPrios;
   constexpr int TPL = C::kTPL;
-  const SapEnvDims d = p.d;
+  SapEnvDims d = p.d;
+  if (C::kFixed) d.n = d.m = C::kFixed;
+  if (C::kFixed && C::kCommon) {  // the layout below then folds into constants
+    d.L = 3;
+    d.M = 10;
+    d.N = 10;
+  }
   const int n = d.n, m = d.m, T = d.T;
   const int L = C::kCommon ? 3 : d.L, M = C::kCommon ? 10 : d.M, N = C::kCommon ? 10 : d.N;
   const int H = M / 2, K2 = M + H;
@@ -940,6 +947,8 @@ int sap_real_fast_try(RealParams& p, void* stream, int* handled, bool gen1_only)
   }
   *handled = 1;
   if (common) {
+    if (idx8 && d.n == 50 && d.m == 50 && sap_real_path_override() != SAP_REAL_PATH_FAST_RUNTIME_SHAPE)
+      return launch_fast<Cfg<__half, uint8_t, false, true, 4, 50>>(p, stream, f.total);
     if (idx8 && d.n <= 64) return launch_fast<Cfg<__half, uint8_t, false, true, 4>>(p, stream, f.total);
     if (idx8) return launch_fast<Cfg<__half, uint8_t, false, true>>(p, stream, f.total);
     return launch_fast<Cfg<__half, uint16_t, false, true>>(p, stream, f.total);

@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
           by[u].w = umax3(by[u].w, c0.w, c1.w);
         }
       }
-      if (seven) {
+      if (seven && 96 + 4 * s < n) {  // quads of column 6 past the last agent hold zero keys: bx[3] stays zero
         const uint4 a0 = *reinterpret_cast<const uint4*>(r0 + 16 * 6);
         const uint4 a1 = *reinterpret_cast<const uint4*>(r1 + 16 * 6);
         bx[3].x = umax3(bx[3].x, a0.x, a1.x);
