@@ -14,7 +14,9 @@
 //   * the gather works on 30-byte SLOTS of the observation row: lane = (rival, half of my top tasks | its other
 //     tasks), i.e. 32 slots = 32 lanes per agent row, five (agent, task) pairs each.  A lane reads one rival index
 //     and five task indices instead of one LUT word and three indices PER PAIR, and writes its 15 halves as
-//     7 words + 1 half.
+//     7 words + 1 half;
+//   * gather and stores run per warp on a private staging row, with no block barrier inside the phase;
+//   * the bench shape 100 x 100 has its own instantiation with n and m compiled in (kFixed).
 // Lists are certified exactly as before (keys are a monotone fixed-point image of the float64 window sum plus an
 // "inexact" bit; an uncertified list is redone by the exact float64 warp selection), so results never depend on the
 // key resolution.
@@ -315,12 +317,12 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     }
   }
   __half* obs_out = reinterpret_cast<__half*>(vw.obs.ptr) + sap_field_off(vw.obs, b, t_slot);
-  // agent-input staging rows of this env: fp32 (widened here) or fp16 (the same bytes, bulk-stored a second time)
+  // agent-input staging rows of this env: fp32 (widened here) or fp16 (the same bytes, stored a second time)
   const bool ain_half = vw.agent_in.ptr && vw.agent_in.dtype == SAP_F16;
   float* ain = vw.agent_in.ptr && !ain_half ? reinterpret_cast<float*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride
                                             : nullptr;
   __half* ain16 = ain_half ? reinterpret_cast<__half*>(vw.agent_in.ptr) + (int64_t)b * vw.agent_in.env_stride : nullptr;
-  // fp16 staging rows are either packed (pitch = obs size: one more bulk store of the same bytes) or padded to a pitch
+  // fp16 staging rows are either packed (pitch = obs size: the same 128-bit pieces once more) or padded to a pitch
   // that a tensor-core GEMM can read with 128-bit loads (496 halves for 490): then the rows are copied word by word
   const int ain16_pitch = ain_half ? (int)vw.agent_in.t_stride : 0;
   const bool ain16_bulk = ain_half && ain16_pitch == kObs;
@@ -1214,7 +1216,7 @@ int sap_real_fast2_try(RealParams& p, void* stream, int* handled) {
   if (!fast2_dims_ok(d) || p.prios || vw.obs.dtype != SAP_F16) return SAP_OK;
   if (!p.plane_stats || (reinterpret_cast<uintptr_t>(p.plane_stats) & 7)) return SAP_OK;
   if (!sap_aligned16(p.planes)) return SAP_OK;
-  // every observation block of 8 rows must start 16-byte aligned (TMA bulk store, 128-bit agent-input stores)
+  // the rows of an env must start 16-byte aligned (128-bit observation and agent-input stores, see the gather)
   if (!sap_aligned16(vw.obs.ptr) || ((vw.obs.env_stride * 2) & 15) || ((vw.obs.t_stride * 2) & 15)) return SAP_OK;
   if (vw.agent_in.ptr) {
     if (vw.agent_in.dtype != SAP_F32 && vw.agent_in.dtype != SAP_F16) {
