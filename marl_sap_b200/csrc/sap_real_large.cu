@@ -135,6 +135,24 @@ __device__ __forceinline__ void group_top16(int len, int s, KeyFn key, uint32_t 
 
 // env index of a CTA: grid = (chunks, min(B, 32768), ceil(B / 32768))
 constexpr int kEnvFold = 32768;
+// kShape: what the kernel knows at compile time.  0 = nothing (any M / N / L / n / m); 1 = the shipped configuration
+// M = N = 10, L = 3 (every list length and the observation layout fold into constants, the per-pair loops unroll);
+// 2 = that configuration at the constellation shape 324 x 450 of BASELINE config 3 (pitches and tile counts too).
+template <int kShape>
+__device__ __forceinline__ SapEnvDims shaped_dims(const SapEnvDims& in) {
+  SapEnvDims d = in;
+  if (kShape >= 1) {
+    d.L = 3;
+    d.M = 10;
+    d.N = 10;
+  }
+  if (kShape == 2) {
+    d.n = 324;
+    d.m = 450;
+  }
+  return d;
+}
+
 __device__ __forceinline__ int env_of_block() { return (int)(blockIdx.z * kEnvFold + blockIdx.y); }
 
 // adjacent keys strictly decreasing, or ties between two EXACT keys (bit 0 clear): then the order is proven
@@ -214,12 +232,12 @@ __global__ void __launch_bounds__(kThreads) sap_real_large_prep(RealParams p, in
 }
 
 // ---------------------------------------------------------------------------------------------------- K1
-template <bool kKeyed>
+template <bool kKeyed, int kShape = 0>
 __global__ void __launch_bounds__(kThreads) sap_real_large_keys(RealParams p) {
   // tile = kTileI agents x 32 tasks: 8 agent rows (x L planes) in flight per thread
   __shared__ double tile_d[kKeyed ? 1 : kTileI][kKeyed ? 1 : 33];
   __shared__ uint32_t tile_k[kKeyed ? kTileI : 1][kKeyed ? 33 : 1];
-  const SapEnvDims d = p.d;
+  const SapEnvDims d = shaped_dims<kShape>(p.d);
   const int b = env_of_block(), n = d.n, m = d.m, T = d.T, L = d.L;
   if (b >= d.B) return;
   LargeScratch s;
@@ -388,12 +406,12 @@ __device__ __forceinline__ void reward_phase(const RealParams& p, int b, int k_o
 }
 
 // ---------------------------------------------------------------------------------------------------- K2
-template <bool kKeyed, int kTPL>
+template <bool kKeyed, int kTPL, int kShape = 0>
 __global__ void __launch_bounds__(kThreads, 4) sap_real_large_lists(RealParams p) {
   constexpr int kRowsPerCta = kThreads / kTPL;
   __shared__ int32_t q_cnt;
   __shared__ int32_t q_rows[kMaxRowsPerCta];
-  const SapEnvDims d = p.d;
+  const SapEnvDims d = shaped_dims<kShape>(p.d);
   const int b = env_of_block(), n = d.n, m = d.m, M = d.M, K2 = d.M + d.M / 2;
   if (b >= d.B) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -579,10 +597,10 @@ __device__ __noinline__ void exact_select_scores(const double* sScore, int n, in
 }
 
 // ---------------------------------------------------------------------------------------------------- K3
-template <bool kKeyed>
+template <bool kKeyed, int kShape = 0>
 __global__ void __launch_bounds__(kThreads, 5) sap_real_large_main(RealParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SapEnvDims d = p.d;
+  const SapEnvDims d = shaped_dims<kShape>(p.d);
   const int b = env_of_block();
   if (b >= d.B) return;
   const int n = d.n, m = d.m, T = d.T, L = d.L, M = d.M, N = d.N, H = d.M / 2, K2 = d.M + d.M / 2;
@@ -790,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 5) sap_real_large_main(RealParams p)
   }
 }
 
-template <bool kKeyed>
+template <bool kKeyed, int kShape = 0>
 int launch_mode(RealParams& p, cudaStream_t st) {
   const SapEnvDims& d = p.d;
   const int H = d.M / 2;
@@ -802,14 +820,14 @@ int launch_mode(RealParams& p, cudaStream_t st) {
   const dim3 g2((d.n + rows_per_cta - 1) / rows_per_cta, gy, gz), g3((d.n + kWarps - 1) / kWarps, gy, gz);
   sap_real_large_prep<<<d.B, kThreads, 0, st>>>(p, kKeyed ? 1 : 0);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_prep");
-  sap_real_large_keys<kKeyed><<<g1, kThreads, 0, st>>>(p);
+  sap_real_large_keys<kKeyed, kShape><<<g1, kThreads, 0, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_keys");
-  if (wide) sap_real_large_lists<kKeyed, 8><<<g2, kThreads, 0, st>>>(p);
-  else sap_real_large_lists<kKeyed, 4><<<g2, kThreads, 0, st>>>(p);
+  if (wide) sap_real_large_lists<kKeyed, 8, kShape><<<g2, kThreads, 0, st>>>(p);
+  else sap_real_large_lists<kKeyed, 4, kShape><<<g2, kThreads, 0, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_lists");
   const size_t smem = sizeof(uint16_t) * (size_t)kWarps * (d.M + d.N + d.N * H) + 16 + sizeof(uint32_t) * 16 * kWarps +
                       sizeof(uint32_t) * (size_t)(d.M + d.N * d.M + d.N * H) + 16 + sizeof(double) * (size_t)d.n;
-  sap_real_large_main<kKeyed><<<g3, kThreads, smem, st>>>(p);
+  sap_real_large_main<kKeyed, kShape><<<g3, kThreads, smem, st>>>(p);
   SAP_CUDA_LAUNCH_CHECK("sap_real_large_main");
   return SAP_OK;
 }
@@ -822,6 +840,11 @@ int sap_real_large_launch(RealParams& p, void* stream) {
   const SapEnvDims& d = p.d;
   SAP_REQUIRE(p.scratch, SAP_E_SMEM, "sap_real: this problem size needs scratch of sap_real_scratch_doubles() doubles");
   SAP_REQUIRE(d.n <= 512 && d.m <= 512, SAP_E_DIMS, "sap_real (large path): n, m must be <= 512");
-  if (large_keyed(d) && !p.large_exact) return launch_mode<true>(p, (cudaStream_t)stream);  // large_exact: selector override
+  if (large_keyed(d) && !p.large_exact) {  // large_exact: selector override
+    const bool common = d.M == 10 && d.N == 10 && d.L == 3 && sap_real_path_override() != SAP_REAL_PATH_FAST_RUNTIME_SHAPE;
+    if (common && d.n == 324 && d.m == 450) return launch_mode<true, 2>(p, (cudaStream_t)stream);
+    if (common) return launch_mode<true, 1>(p, (cudaStream_t)stream);
+    return launch_mode<true>(p, (cudaStream_t)stream);
+  }
   return launch_mode<false>(p, (cudaStream_t)stream);
 }

@@ -342,9 +342,12 @@ def test_real_env_full_size_fast_equals_generic(real_kernel_path):
     assert th.equal(ain, obs.permute(1, 0, 2, 3).float())  # agent_in == float(obs[:, t]) for every t
 
 
-def test_real_env_constellation_scale_matches_oracle():
+@pytest.mark.parametrize("path", [0, 5])  # 0: instantiation with the shape compiled in; 5: shape read at run time
+def test_real_env_constellation_scale_matches_oracle(path, real_kernel_path):
     """324 agents x 450 tasks (real_constellation_env.yaml): too large for one SM: runs the multi-CTA path."""
     from marl_sap_b200.envs.batched import BatchedRealConstellationEnv
+
+    real_kernel_path(path)
 
     rng = np.random.default_rng(11)
     B, n, m, T, L, M, N = 2, 324, 450, 3, 3, 10, 10
