@@ -47,7 +47,7 @@ constexpr size_t kMaxSmem = 227 * 1024 - 1024;
 // scratch lists; for the gather it is refilled with the benefits (rounded to the obs dtype) and the staging rows.
 // At 100 x 100 (fp16 obs, 8-bit indices) that is 7.3 KB persistent + max(45 KB, 68 KB) = 75 KB: three CTAs per SM.
 struct FastLayout {
-  size_t D, nbr, other, lut, prios;            // live through the whole kernel
+  size_t D, nbr, other, lut, prios, pv;        // live through the whole kernel
   size_t k32, E, dmask, cnt, red, queue;       // overlay 1: list building
   size_t tile, stage;                          // overlay 2: gather
   size_t total;
@@ -67,6 +67,7 @@ __host__ __device__ inline FastLayout fast_layout(const SapEnvDims& d, int out_e
   f.other = off; off = up16(off + (size_t)idx_esz * d.n * d.N * H);
   f.lut = off;   off = up16(off + sizeof(uint16_t) * (size_t)(d.M + d.N * d.M + d.N * H));
   f.prios = off; off = up16(off + (prios ? sizeof(double) * (size_t)d.m : 0));
+  f.pv = off;    off = up16(off + sizeof(uint16_t) * (size_t)d.n);
   const size_t base = off;
   f.k32 = off;   off = up16(off + sizeof(uint32_t) * (size_t)d.n * f.ms);
   f.E = off;     off = up16(off + (size_t)idx_esz * d.n * K2);
@@ -226,6 +227,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   double* sRed = reinterpret_cast<double*>(smem + f.red);
   int32_t* sQ = reinterpret_cast<int32_t*>(smem + f.queue);          // [0]=rows count, [1]=nbr count, then ids
   uint16_t* sLut = reinterpret_cast<uint16_t*>(smem + f.lut);        // output pair -> (rival slot << 8 | column slot)
+  uint16_t* sPrev = reinterpret_cast<uint16_t*>(smem + f.pv);        // [n] the NEW previous task of every agent (flag columns, :222)
   int32_t* qRows = sQ + 4;
   int32_t* qNbr = sQ + 4 + n;
 
@@ -304,6 +306,7 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
       if (vw.rewards.ptr) sap_store_real(vw.rewards.ptr, sap_field_off(vw.rewards, b, k_old) + i, vw.rewards.dtype, r);
       if (vw.actions.ptr) sap_store_int(vw.actions.ptr, sap_field_off(vw.actions, b, k_old) + i, vw.actions.dtype, a);
       p.prev[(size_t)b * n + i] = a;
+      sPrev[i] = (uint16_t)a;
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) local_ret += __shfl_xor_sync(SAP_FULL_MASK, local_ret, off);
@@ -329,7 +332,10 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
         sap_store_int(vw.terminated.ptr, sap_field_off(vw.terminated, b, k_old), vw.terminated.dtype, done);
     }
   } else {
-    for (int i = tid; i < n; i += kThreads) p.prev[(size_t)b * n + i] = i;
+    for (int i = tid; i < n; i += kThreads) {
+      p.prev[(size_t)b * n + i] = i;
+      sPrev[i] = (uint16_t)i;
+    }
     if (tid == 0) {
       p.k[b] = 0;
       p.ep_return[b] = 0.0;
@@ -777,6 +783,8 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
   const size_t row_bytes = sizeof(OutT) * (size_t)obs_size;
   const int rpp = f.rows_per_pass;
   const bool ain_flat = ain && ain_row == obs_size && ((reinterpret_cast<uintptr_t>(ain) & 15) == 0);
+  if (p.top_out)  // the top-M lists are final: one coalesced pass instead of M lanes of every row
+    for (int e = tid; e < n * M; e += kThreads) p.top_out[(size_t)b * n * M + e] = sD[e];
   for (int r0 = 0; r0 < n; r0 += rpp) {
     const int rows = min(rpp, n - r0);
     unsigned char* gdst = reinterpret_cast<unsigned char*>(obs_out) + (size_t)r0 * row_bytes;
@@ -834,12 +842,8 @@ __device__ __forceinline__ void process_env(const RealParams& p, const int b, un
         }
       }
       // "is my previous task among my top-M" flags (:222)
-      const int pv = p.prev[(size_t)b * n + i];
-      for (int q = lane; q < M; q += 32) {
-        const int j = myD[q];
-        srow[npairs * L + q] = to_out_f<OutT>(j == pv ? 1.f : 0.f);
-        if (p.top_out) p.top_out[((size_t)b * n + i) * M + q] = j;
-      }
+      const int pv = sPrev[i];  // shared-memory copy: no global load per row
+      for (int q = lane; q < M; q += 32) srow[npairs * L + q] = to_out_f<OutT>((int)myD[q] == pv ? 1.f : 0.f);
     }
     // generic-proxy writes of the staged rows must be visible to the async proxy (TMA) before the barrier
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
