@@ -52,11 +52,14 @@ def main(rounds):
             S = S.cuda()
             acts = [th.randint(0, m, (B, n), generator=g).cuda() for _ in range(T)]
             ref = rollout(_lib.REAL_PATH_FAST_GEN1, S, acts, False)
-            for ahead in (False, True, False, True):
-                got = rollout(_lib.REAL_PATH_AUTO, S, acts, ahead)
+            # AUTO = the instantiation with 100 x 100 compiled in; FAST_RUNTIME_SHAPE = the same kernel reading n, m at run time
+            for path, ahead in ((_lib.REAL_PATH_AUTO, False), (_lib.REAL_PATH_AUTO, True), (_lib.REAL_PATH_AUTO, False),
+                                (_lib.REAL_PATH_AUTO, True), (_lib.REAL_PATH_FAST_RUNTIME_SHAPE, False),
+                                (_lib.REAL_PATH_FAST_RUNTIME_SHAPE, True)):
+                got = rollout(path, S, acts, ahead)
                 ok = all(th.equal(a, b) for a, b in zip(ref, got))
                 bad += not ok
-                print(f"round {r} {name:10s} ahead={ahead}: {'ok' if ok else 'MISMATCH'}", flush=True)
+                print(f"round {r} {name:10s} path={path} ahead={ahead}: {'ok' if ok else 'MISMATCH'}", flush=True)
     print("stress:", "PASS" if bad == 0 else f"{bad} FAILURES")
     return bad
 
