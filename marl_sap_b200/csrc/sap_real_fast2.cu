@@ -810,14 +810,15 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     const int r = sNbr[itc];
     const uint4 e4 = *reinterpret_cast<const uint4*>(sE + r * 16);
     const uint32_t ew[4] = {e4.x, e4.y, e4.z, e4.w};
-    const uint32_t* mk = sMask + i * 4;
+    const uint4 mk = *reinterpret_cast<const uint4*>(sMask + i * 4);  // membership bits of D[i]: registers, not one LDS per entry
     uint8_t* dst = sOther + itc * kH + (kH - 1);
     int c = act ? 0 : kH;
 #pragma unroll
     for (int e = 0; e < kK2; ++e) {
       if (e >= kH + 1 && (e & 1) == 0 && __all_sync(SAP_FULL_MASK, c >= kH)) break;  // whole warp has its five
       const uint32_t j = (ew[e >> 2] >> (8 * (e & 3))) & 0xffu;
-      const bool in_d = (mk[j >> 5] >> (j & 31)) & 1u;
+      const uint32_t mw = (j & 64u) ? ((j & 32u) ? mk.w : mk.z) : ((j & 32u) ? mk.y : mk.x);
+      const bool in_d = (mw >> (j & 31u)) & 1u;
       if (c < kH && !in_d) {
         *dst = (uint8_t)j;
         --dst;
