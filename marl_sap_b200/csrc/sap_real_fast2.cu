@@ -917,13 +917,19 @@ __global__ void __launch_bounds__(kThreads, 3) sap_real_fast2_kernel(RealParams 
     unsigned char* srow = wstage + 4 * mis;
     {
       const int a = is_own ? i : (int)sNbr[i * kN + gp];
-      const uint8_t* jp = smem + idx_base + i * idx_stride;
+      // my five task indices: two aligned words around the 5 bytes + a funnel shift instead of five byte loads (the
+      // index arrays are followed by other shared-memory arrays, so the second word is always inside the allocation)
+      const uint32_t jaddr = idx_base + i * idx_stride;
+      const uint2 jw = make_uint2(*reinterpret_cast<const uint32_t*>(smem + (jaddr & ~3u)),
+                                  *reinterpret_cast<const uint32_t*>(smem + (jaddr & ~3u) + 4));
+      const uint32_t jsh = (jaddr & 3u) * 8u;
+      const uint32_t j03 = __funnelshift_r(jw.x, jw.y, jsh), j4 = (jw.y >> jsh) & 0xffu;
       const uint32_t* r01 = t01 + a * f.p01;
       const __half* r2 = t2 + a * f.p2;
       uint32_t w[kH], h[kH];  // w: planes 0, 1 of pair q; h: plane 2 (low 16 bits)
 #pragma unroll
       for (int q = 0; q < kH; ++q) {
-        const int j = jp[q];
+        const int j = q < 4 ? (int)((j03 >> (8 * q)) & 0xffu) : (int)j4;
         w[q] = r01[j];
         h[q] = (uint32_t)__half_as_ushort(r2[j]);
       }
