@@ -186,7 +186,8 @@ template <typename OutT_, typename IdxT_, bool kPrios_, bool kCommon_, int kTPL_
 struct Cfg {
   static constexpr int kTPL = kTPL_;
   static constexpr int kFixed = kFixed_;  // n = m = kFixed compiled in (BASELINE config 50 x 50); 0 = read at run time
-  static constexpr int kMinBlocks = kTPL_ == 4 ? 5 : 3;  // small shapes need little shared memory: more CTAs per SM
+  static constexpr int kMinBlocks = kFixed_ == 50 ? 7 : (kTPL_ == 4 ? 5 : 3);  // small shapes need little shared memory: more CTAs per SM;
+                                        // 50 x 50 compiled in fits 32 registers (20 bytes of spill): 7 CTAs per SM = 1036 slots, one wave for 1024 envs
   using OutT = OutT_;
   using IdxT = IdxT_;
   static constexpr bool kPrios = kPrios_;

@@ -5,4 +5,3 @@ mkdir -p $OUT
 export PYTHONPATH=$PWD
 python -m pytest tests/test_gpu_env_parity.py -x -q -m gpu -k "constellation or multi_cta or full_size or large" 2>&1 | tail -3
 for path in 0 5; do python profiles/time_env_step.py 64 324 450 $path; python profiles/time_env_step.py 256 324 450 $path; done 2>&1 | tee $OUT/ab_c4.log
-NS=200 BS=4096 bash profiles/gpu_ab.sh "" "--kernel-path 5" 2>&1 | tee -a $OUT/ab_c4.log
